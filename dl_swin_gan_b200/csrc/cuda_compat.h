@@ -1,0 +1,129 @@
+// Compatibility layer so that the kernel sources (*.cuh) and the C-ABI dispatch
+// (sense_api.cu) compile both with nvcc for sm_100a (the product) and with plain
+// g++ (TEST INFRASTRUCTURE ONLY: tests/host builds an emulated copy where every
+// CUDA thread of a block is an OS thread and __syncthreads/__syncwarp are real
+// barriers; it exists to debug index math without a GPU and is never shipped or
+// used as a fallback — the product library is the nvcc build and nothing else).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+
+#include <cuda_runtime.h>
+#define DLSG_KERNEL __global__
+#define DLSG_DEVICE __device__ __forceinline__
+#define DLSG_DYN_SMEM(type, name)                                       \
+    extern __shared__ __align__(16) unsigned char dlsg_dyn_smem_raw[];  \
+    type* name = reinterpret_cast<type*>(dlsg_dyn_smem_raw)
+#define DLSG_LAUNCH_BOUNDS(...) __launch_bounds__(__VA_ARGS__)
+
+namespace dlsg {
+using stream_t = cudaStream_t;
+template <typename K, typename... A>
+inline int launch(K kernel, dim3 grid, dim3 block, size_t smem, stream_t s, A... args) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    }
+    kernel<<<grid, block, smem, s>>>(args...);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+}  // namespace dlsg
+
+#else  // ---------------------------------------------------------------- host emulation
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include <mutex>
+#include <condition_variable>
+
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+
+namespace dlsg_emu {
+class Barrier {
+public:
+    explicit Barrier(int n) : n_(n), count_(0), gen_(0) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m_);
+        int g = gen_;
+        if (++count_ == n_) { count_ = 0; ++gen_; cv_.notify_all(); }
+        else cv_.wait(lk, [&] { return g != gen_; });
+    }
+private:
+    int n_, count_, gen_;
+    std::mutex m_;
+    std::condition_variable cv_;
+};
+struct BlockCtx { Barrier* block_bar; std::vector<Barrier*> warp_bars; unsigned char* smem; };
+extern thread_local dim3 t_threadIdx;
+extern thread_local dim3 t_blockIdx;
+extern thread_local BlockCtx* t_ctx;
+extern dim3 g_blockDim, g_gridDim;
+}  // namespace dlsg_emu
+
+#define threadIdx (dlsg_emu::t_threadIdx)
+#define blockIdx (dlsg_emu::t_blockIdx)
+#define blockDim (dlsg_emu::g_blockDim)
+#define gridDim (dlsg_emu::g_gridDim)
+static inline void __syncthreads() { dlsg_emu::t_ctx->block_bar->wait(); }
+static inline void __syncwarp() { dlsg_emu::t_ctx->warp_bars[dlsg_emu::t_threadIdx.x >> 5]->wait(); }
+static inline void sincospif(float a, float* s, float* c) {
+    const double pi = 3.14159265358979323846;
+    *s = (float)std::sin(pi * (double)a); *c = (float)std::cos(pi * (double)a);
+}
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+using std::min;
+using std::max;
+
+#define DLSG_KERNEL
+#define DLSG_DEVICE inline
+#define DLSG_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(dlsg_emu::t_ctx->smem)
+#define DLSG_LAUNCH_BOUNDS(...)
+
+namespace dlsg {
+using stream_t = void*;
+template <typename K, typename... A>
+inline int launch(K kernel, dim3 grid, dim3 block, size_t smem, stream_t, A... args) {
+    using namespace dlsg_emu;
+    if (smem > 227 * 1024 || block.x > 1024 || block.y != 1 || block.z != 1) return -1;
+    g_blockDim = block; g_gridDim = grid;
+    const size_t smem_alloc = ((smem + 255) / 128) * 128;
+    unsigned char* smem_buf = static_cast<unsigned char*>(std::aligned_alloc(128, smem_alloc));
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+        Barrier block_bar((int)block.x);
+        unsigned nwarps = (block.x + 31) / 32;
+        std::vector<Barrier*> wb;
+        for (unsigned w = 0; w < nwarps; ++w) {
+            unsigned lanes = (w + 1) * 32 <= block.x ? 32 : block.x - w * 32;
+            wb.push_back(new Barrier((int)lanes));
+        }
+        BlockCtx ctx{&block_bar, wb, smem_buf};
+        std::memset(smem_buf, 0xCD, smem_alloc);   // poison: catches reads of unwritten smem
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < block.x; ++t) {
+            th.emplace_back([&, t] {
+                t_threadIdx = dim3(t, 0, 0); t_blockIdx = dim3(bx, by, bz); t_ctx = &ctx;
+                kernel(args...);
+            });
+        }
+        for (auto& x : th) x.join();
+        for (auto* b : wb) delete b;
+    }
+    std::free(smem_buf);
+    return 0;
+}
+}  // namespace dlsg
+
+#endif

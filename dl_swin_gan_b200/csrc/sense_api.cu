@@ -1,0 +1,310 @@
+// C-ABI entry points of the SENSE operator (declared in include/dlsg_b200.h):
+// argument checks, chunking of the L2-resident intermediate, kernel selection by
+// axis length, launches.  No allocation, no synchronisation, no global state.
+#include "../../include/dlsg_b200.h"
+#include "sense_kernels.cuh"
+
+#include <cmath>
+
+namespace dlsg {
+namespace {
+
+constexpr int kMaxDirectX = 4096;
+constexpr int kMaxDirectY = 1536;
+constexpr long long kTargetWarps = 148LL * 32;     // row pass: >= 2 waves of 16 warps/SM
+constexpr long long kTargetColCtas = 148LL * 4;
+
+inline int radix_of(int n) {   // R if n == 32*R with a compiled radix, else 0
+    if (n % 32) return 0;
+    const int r = n / 32;
+    switch (r) { case 1: case 2: case 3: case 4: case 5: case 6: case 8: case 10: return r; default: return 0; }
+}
+
+struct Problem {          // what stays fixed over the chunk walk
+    WeightStrides ws;
+    float2* tmp;
+    int ndims;
+    float step;
+    const float* step_dev;
+    int epi;
+    stream_t stream;
+};
+
+#define DLSG_TRY(expr) do { if ((expr) != 0) return DLSG_ELAUNCH; } while (0)
+
+// ---- row pass, forward --------------------------------------------------------------
+template <int RX>
+int launch_rows_fwd(const float2* x, const float2* maps, float2* tmp, const SenseDims& d, stream_t s) {
+    using Cfg = RowCfg<RX>;
+    const long long base = (long long)d.B * d.Y;
+    long long want = (kTargetWarps + base - 1) / base;
+    if (want < 1) want = 1;
+    if (want > d.t_count) want = d.t_count;
+    const int tchunk = (int)((d.t_count + want - 1) / want);
+    const int nchunks = (d.t_count + tchunk - 1) / tchunk;
+    const long long warps = base * nchunks;
+    const unsigned grid = (unsigned)((warps + Cfg::WARPS - 1) / Cfg::WARPS);
+    return launch(sense_rows_fwd_kernel<RX>, dim3(grid), dim3(32 * Cfg::WARPS), Cfg::SMEM, s,
+                  x, maps, tmp, d, tchunk, nchunks);
+}
+
+int rows_fwd(const Problem& p, const float2* x, const float2* maps, const float* w, float2* k,
+             const SenseDims& d, float scale, int final1d) {
+    const int rx = (p.ndims == 2) ? radix_of(d.X) : 0;
+    switch (rx) {
+        case 1: return launch_rows_fwd<1>(x, maps, p.tmp, d, p.stream);
+        case 2: return launch_rows_fwd<2>(x, maps, p.tmp, d, p.stream);
+        case 3: return launch_rows_fwd<3>(x, maps, p.tmp, d, p.stream);
+        case 4: return launch_rows_fwd<4>(x, maps, p.tmp, d, p.stream);
+        case 5: return launch_rows_fwd<5>(x, maps, p.tmp, d, p.stream);
+        case 6: return launch_rows_fwd<6>(x, maps, p.tmp, d, p.stream);
+        case 8: return launch_rows_fwd<8>(x, maps, p.tmp, d, p.stream);
+        case 10: return launch_rows_fwd<10>(x, maps, p.tmp, d, p.stream);
+        default: break;
+    }
+    const size_t smem = (size_t)2 * d.X * sizeof(float2);
+    const unsigned grid = (unsigned)((long long)d.B * d.t_count * d.Y);
+    float2* dst = (final1d == 1) ? k : p.tmp;
+    return launch(sense_rows_fwd_direct_kernel, dim3(grid), dim3(256), smem, p.stream,
+                  x, maps, dst, w, p.ws, scale, final1d, d);
+}
+
+// ---- row pass, adjoint --------------------------------------------------------------
+template <int RX, int EMAX>
+int launch_rows_adj(const float2* maps, float2* out, const float2* xin, const float2* aty,
+                    const Problem& p, const SenseDims& d, int e0) {
+    using Cfg = RowCfg<RX>;
+    const long long base = (long long)d.B * d.Y;
+    long long want = (kTargetWarps + base - 1) / base;
+    if (want < 1) want = 1;
+    if (want > d.t_count) want = d.t_count;
+    const int tchunk = (int)((d.t_count + want - 1) / want);
+    const int nchunks = (d.t_count + tchunk - 1) / tchunk;
+    const long long warps = base * nchunks;
+    const unsigned grid = (unsigned)((warps + Cfg::WARPS - 1) / Cfg::WARPS);
+    return launch(sense_rows_adj_kernel<RX, EMAX>, dim3(grid), dim3(32 * Cfg::WARPS), Cfg::SMEM, p.stream,
+                  (const float2*)p.tmp, maps, out, xin, aty, p.step, p.step_dev, p.epi, d, tchunk, nchunks, e0);
+}
+
+template <int RX>
+int rows_adj_groups(const float2* maps, float2* out, const float2* xin, const float2* aty,
+                    const Problem& p, const SenseDims& d) {
+    for (int e0 = 0; e0 < d.E; e0 += 2) {
+        if (d.E - e0 >= 2) DLSG_TRY((launch_rows_adj<RX, 2>(maps, out, xin, aty, p, d, e0)));
+        else               DLSG_TRY((launch_rows_adj<RX, 1>(maps, out, xin, aty, p, d, e0)));
+    }
+    return 0;
+}
+
+int rows_adj(const Problem& p, const float2* src_k, const float2* maps, const float* w, float2* out,
+             const float2* xin, const float2* aty, const SenseDims& d, float scale, int final1d) {
+    const int rx = (p.ndims == 2) ? radix_of(d.X) : 0;
+    switch (rx) {
+        case 1: return rows_adj_groups<1>(maps, out, xin, aty, p, d);
+        case 2: return rows_adj_groups<2>(maps, out, xin, aty, p, d);
+        case 3: return rows_adj_groups<3>(maps, out, xin, aty, p, d);
+        case 4: return rows_adj_groups<4>(maps, out, xin, aty, p, d);
+        case 5: return rows_adj_groups<5>(maps, out, xin, aty, p, d);
+        case 6: return rows_adj_groups<6>(maps, out, xin, aty, p, d);
+        case 8: return rows_adj_groups<8>(maps, out, xin, aty, p, d);
+        case 10: return rows_adj_groups<10>(maps, out, xin, aty, p, d);
+        default: break;
+    }
+    const size_t smem = (size_t)(2 + d.E) * d.X * sizeof(float2);
+    const unsigned grid = (unsigned)((long long)d.B * d.t_count * d.Y);
+    const float2* src = (final1d == 1) ? src_k : (const float2*)p.tmp;
+    return launch(sense_rows_adj_direct_kernel, dim3(grid), dim3(256), smem, p.stream,
+                  src, maps, out, xin, aty, p.step, p.step_dev, p.epi, w, p.ws, scale, final1d, d);
+}
+
+// ---- column pass --------------------------------------------------------------------
+template <int RY, int MODE>
+int launch_cols(const float2* src, float2* dst, const float* w, const Problem& p, const SenseDims& d, float scale) {
+    using Cfg = ColCfg<RY>;
+    const long long base = (long long)(d.X / 32) * d.t_count * d.B;
+    long long want = (kTargetColCtas + base - 1) / base;
+    if (want < 1) want = 1;
+    if (want > d.C) want = d.C;
+    const int cchunk = (int)((d.C + want - 1) / want);
+    const int ncchunks = (d.C + cchunk - 1) / cchunk;
+    const unsigned grid = (unsigned)(base * ncchunks);
+    return launch(sense_cols_kernel<RY, MODE>, dim3(grid), dim3(Cfg::NT), Cfg::SMEM, p.stream,
+                  src, dst, w, p.ws, scale, d, cchunk, ncchunks);
+}
+
+template <int MODE>
+int cols(const Problem& p, const float2* src, float2* dst, const float* w, const SenseDims& d, float scale) {
+    // the fast column kernel walks 32-column slabs, so it also needs X % 32 == 0
+    const int ry = (d.X % 32 == 0) ? radix_of(d.Y) : 0;
+    switch (ry) {
+        case 1: return launch_cols<1, MODE>(src, dst, w, p, d, scale);
+        case 2: return launch_cols<2, MODE>(src, dst, w, p, d, scale);
+        case 3: return launch_cols<3, MODE>(src, dst, w, p, d, scale);
+        case 4: return launch_cols<4, MODE>(src, dst, w, p, d, scale);
+        case 5: return launch_cols<5, MODE>(src, dst, w, p, d, scale);
+        case 6: return launch_cols<6, MODE>(src, dst, w, p, d, scale);
+        case 8: return launch_cols<8, MODE>(src, dst, w, p, d, scale);
+        case 10: return launch_cols<10, MODE>(src, dst, w, p, d, scale);
+        default: break;
+    }
+    const size_t smem = ((size_t)2 * d.Y * kDirectColW + d.Y) * sizeof(float2);
+    const int ncolblk = (d.X + kDirectColW - 1) / kDirectColW;
+    const unsigned grid = (unsigned)((long long)d.B * d.C * d.t_count * ncolblk);
+    return launch(sense_cols_direct_kernel<MODE>, dim3(grid), dim3(256), smem, p.stream, src, dst, w, p.ws, scale, d);
+}
+
+// ---- problem validation and chunk walk ------------------------------------------------
+enum Op { OP_FWD, OP_ADJ, OP_NORMAL };
+
+size_t per_bt_bytes(int C, int Y, int X) { return (size_t)C * Y * X * sizeof(float2); }
+
+int check_sizes(int B, int E, int C, int T, int Y, int X, int ndims) {
+    if (B <= 0 || E <= 0 || C <= 0 || T <= 0 || Y <= 0 || X <= 0) return DLSG_EINVAL;
+    if (ndims != 1 && ndims != 2) return DLSG_EINVAL;
+    const bool fast_x = (ndims == 2) && radix_of(X);
+    if (!fast_x && X > kMaxDirectX) return DLSG_EUNSUPPORTED;
+    if (ndims == 2) {
+        const bool fast_y = radix_of(Y) && (X % 32 == 0);
+        if (!fast_y && Y > kMaxDirectY) return DLSG_EUNSUPPORTED;
+    }
+    return DLSG_OK;
+}
+
+// in : x (forward / normal) or k (adjoint);  out : k (forward) or x (adjoint / normal)
+int run(Op op, const float2* in, const float2* maps, const float* w, const long long* w_strides,
+        float2* out, const float2* aty, float step, const float* step_dev, int epi,
+        void* workspace, size_t workspace_bytes,
+        int B, int E, int C, int T, int Y, int X, int ndims, void* stream) {
+    const int st = check_sizes(B, E, C, T, Y, X, ndims);
+    if (st != DLSG_OK) return st;
+    if (!in || !out) return DLSG_EINVAL;          // maps may be NULL: unit sensitivities
+    if (w && !w_strides) return DLSG_EINVAL;
+    if (epi == EPI_DC && !aty) return DLSG_EINVAL;
+
+    Problem p{};
+    if (w) p.ws = WeightStrides{w_strides[0], w_strides[1], w_strides[2], w_strides[3], w_strides[4]};
+    p.tmp = static_cast<float2*>(workspace);
+    p.ndims = ndims;
+    p.step = step;
+    p.step_dev = step_dev;
+    p.epi = epi;
+    p.stream = static_cast<stream_t>(stream);
+
+    const size_t per_bt = per_bt_bytes(C, Y, X);
+    const bool need_tmp = (ndims == 2) || (op == OP_NORMAL);
+    long long bchunk = B, tcount = T;
+    if (need_tmp) {
+        if (!workspace || workspace_bytes < per_bt) return DLSG_EWORKSPACE;
+        const long long max_bt = (long long)(workspace_bytes / per_bt);
+        if (max_bt >= T) { bchunk = max_bt / T; if (bchunk > B) bchunk = B; tcount = T; }
+        else             { bchunk = 1; tcount = max_bt; }
+    }
+    const double npts = (ndims == 2) ? (double)Y * (double)X : (double)X;
+    const float scale = (float)(1.0 / sqrt(npts));      // norm='ortho' (transforms.py:18)
+
+    const size_t x_slice = (size_t)E * T * Y * X, m_slice = (size_t)E * C * Y * X, k_slice = (size_t)C * T * Y * X;
+    for (long long b0 = 0; b0 < B; b0 += bchunk) {
+        const int bc = (int)((B - b0 < bchunk) ? (B - b0) : bchunk);
+        const float2* maps_b = maps ? maps + b0 * m_slice : nullptr;
+        const float* w_b = w ? w + b0 * p.ws.b : nullptr;
+        for (long long t0 = 0; t0 < T; t0 += tcount) {
+            const int tc = (int)((T - t0 < tcount) ? (T - t0) : tcount);
+            const SenseDims d{bc, E, C, T, Y, X, (int)t0, tc};
+            if (op == OP_FWD) {
+                const float2* x_b = in + b0 * x_slice;
+                float2* k_b = out + b0 * k_slice;
+                if (ndims == 2) {
+                    DLSG_TRY(rows_fwd(p, x_b, maps_b, w_b, k_b, d, scale, 0));
+                    DLSG_TRY(cols<MODE_FWD>(p, p.tmp, k_b, w_b, d, scale));
+                } else {
+                    DLSG_TRY(rows_fwd(p, x_b, maps_b, w_b, k_b, d, scale, 1));
+                }
+            } else if (op == OP_ADJ) {
+                const float2* k_b = in + b0 * k_slice;
+                float2* x_b = out + b0 * x_slice;
+                if (ndims == 2) {
+                    DLSG_TRY(cols<MODE_ADJ>(p, k_b, p.tmp, w_b, d, scale));
+                    DLSG_TRY(rows_adj(p, k_b, maps_b, w_b, x_b, nullptr, nullptr, d, scale, 0));
+                } else {
+                    DLSG_TRY(rows_adj(p, k_b, maps_b, w_b, x_b, nullptr, nullptr, d, scale, 1));
+                }
+            } else {
+                const float2* x_b = in + b0 * x_slice;
+                const float2* aty_b = aty ? aty + b0 * x_slice : nullptr;
+                float2* o_b = out + b0 * x_slice;
+                if (ndims == 2) {
+                    DLSG_TRY(rows_fwd(p, x_b, maps_b, w_b, nullptr, d, scale, 0));
+                    DLSG_TRY(cols<MODE_NORMAL>(p, p.tmp, p.tmp, w_b, d, scale));
+                    DLSG_TRY(rows_adj(p, nullptr, maps_b, w_b, o_b, x_b, aty_b, d, scale, 0));
+                } else {
+                    DLSG_TRY(rows_fwd(p, x_b, maps_b, w_b, nullptr, d, scale, 2));
+                    DLSG_TRY(rows_adj(p, nullptr, maps_b, w_b, o_b, x_b, aty_b, d, scale, 2));
+                }
+            }
+        }
+    }
+    return DLSG_OK;
+}
+
+}  // namespace
+}  // namespace dlsg
+
+extern "C" {
+
+int dlsg_version(void) { return 100; }
+
+const char* dlsg_status_string(int status) {
+    switch (status) {
+        case DLSG_OK: return "ok";
+        case DLSG_EINVAL: return "invalid argument (null pointer, non-positive extent, or ndims not in {1,2})";
+        case DLSG_EWORKSPACE: return "workspace missing or smaller than dlsg_sense_workspace_bytes(..., 0)";
+        case DLSG_EUNSUPPORTED: return "axis length not supported (direct-DFT limits: X <= 4096, Y <= 1536 unless 32*R)";
+        case DLSG_ELAUNCH: return "CUDA kernel launch failed";
+        default: return "unknown status";
+    }
+}
+
+size_t dlsg_sense_workspace_bytes(int B, int E, int C, int T, int Y, int X, int ndims, size_t budget_bytes) {
+    (void)E; (void)ndims;
+    if (B <= 0 || C <= 0 || T <= 0 || Y <= 0 || X <= 0) return 0;
+    const size_t per_bt = dlsg::per_bt_bytes(C, Y, X);
+    if (budget_bytes <= per_bt) return per_bt;
+    const size_t per_slice = per_bt * (size_t)T;
+    if (budget_bytes >= per_slice) {
+        size_t nb = budget_bytes / per_slice;
+        if (nb > (size_t)B) nb = (size_t)B;
+        return nb * per_slice;
+    }
+    return (budget_bytes / per_bt) * per_bt;
+}
+
+int dlsg_sense_forward_c64(const void* x, const void* maps, const float* weights, const long long* w_strides,
+                           void* k_out, void* workspace, size_t workspace_bytes,
+                           int B, int E, int C, int T, int Y, int X, int ndims, void* stream) {
+    return dlsg::run(dlsg::OP_FWD, (const float2*)x, (const float2*)maps, weights, w_strides, (float2*)k_out,
+                     nullptr, 0.f, nullptr, dlsg::EPI_PLAIN, workspace, workspace_bytes, B, E, C, T, Y, X, ndims, stream);
+}
+
+int dlsg_sense_adjoint_c64(const void* k, const void* maps, const float* weights, const long long* w_strides,
+                           void* x_out, void* workspace, size_t workspace_bytes,
+                           int B, int E, int C, int T, int Y, int X, int ndims, void* stream) {
+    return dlsg::run(dlsg::OP_ADJ, (const float2*)k, (const float2*)maps, weights, w_strides, (float2*)x_out,
+                     nullptr, 0.f, nullptr, dlsg::EPI_PLAIN, workspace, workspace_bytes, B, E, C, T, Y, X, ndims, stream);
+}
+
+int dlsg_sense_normal_c64(const void* x, const void* maps, const float* weights, const long long* w_strides,
+                          void* x_out, void* workspace, size_t workspace_bytes,
+                          int B, int E, int C, int T, int Y, int X, int ndims, void* stream) {
+    return dlsg::run(dlsg::OP_NORMAL, (const float2*)x, (const float2*)maps, weights, w_strides, (float2*)x_out,
+                     nullptr, 0.f, nullptr, dlsg::EPI_PLAIN, workspace, workspace_bytes, B, E, C, T, Y, X, ndims, stream);
+}
+
+int dlsg_sense_dc_step_c64(const void* x, const void* aty, const void* maps, const float* weights,
+                           const long long* w_strides, float step, const float* step_dev, void* x_out,
+                           void* workspace, size_t workspace_bytes,
+                           int B, int E, int C, int T, int Y, int X, int ndims, void* stream) {
+    return dlsg::run(dlsg::OP_NORMAL, (const float2*)x, (const float2*)maps, weights, w_strides, (float2*)x_out,
+                     (const float2*)aty, step, step_dev, dlsg::EPI_DC, workspace, workspace_bytes, B, E, C, T, Y, X, ndims, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+/* dlsg_b200 — C ABI of the B200-native hot path of dl-cs-dynamic (tjtiger86/dl-swin-gan).
+ *
+ * The reference has no FFI: its seam is Python duck-typing.  These
+ * entry points are what a ctypes/cffi binding of that seam calls; the Python mirror
+ * of the reference classes lives in dl_swin_gan_b200/mri/transforms.py (SenseModel,
+ * FFT) and dl_swin_gan_b200/swin/window_attention.py (WindowAttention3D).
+ *
+ * Conventions for every function
+ *   - all pointers are DEVICE pointers owned by the caller (outputs and workspace too);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream) and the call returns without synchronising;
+ *   - tensors are contiguous, row-major, X fastest; complex64 = interleaved fp32;
+ *   - return value: DLSG_OK (0) or a negative DLSG_E* code; nothing is written on error;
+ *   - the library keeps no mutable global state: it is re-entrant and honours the
+ *     calling thread's current CUDA device (nn.DataParallel threads, reconstruct.py:199).
+ */
+#ifndef DLSG_B200_H
+#define DLSG_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLSG_OK 0
+#define DLSG_EINVAL (-1)      /* null pointer, non-positive extent, ndims not in {1,2} */
+#define DLSG_EWORKSPACE (-2)  /* workspace smaller than dlsg_sense_workspace_bytes(..., 0) */
+#define DLSG_EUNSUPPORTED (-3)/* axis length beyond the direct-DFT limits (X > 4096 or Y > 1536 when not 32*R) */
+#define DLSG_ELAUNCH (-4)     /* cudaGetLastError() != cudaSuccess after a launch */
+
+/* Library version (major*10000 + minor*100 + patch). */
+int dlsg_version(void);
+
+/* Human-readable text for a status code (static storage). */
+const char* dlsg_status_string(int status);
+
+/* Scratch the SENSE entry points need for a problem of this shape.
+ *   budget_bytes == 0 : the minimum (one (slice, frame) set of coil images:  C*Y*X*8; 0 when ndims == 1
+ *                       except for dlsg_sense_normal_c64 / dlsg_sense_dc_step_c64, which need it in 1-D too);
+ *   budget_bytes  > 0 : the largest useful size not above max(budget, minimum).  The row-transformed
+ *                       intermediate of one chunk lives here; keeping it a fraction of the 126 MB L2
+ *                       keeps it on chip between the row and the column pass.
+ */
+size_t dlsg_sense_workspace_bytes(int B, int E, int C, int T, int Y, int X, int ndims, size_t budget_bytes);
+
+/* SENSE forward operator, replaces SenseModel._forward_op (dl_cs/mri/transforms.py:92-98):
+ *     k[b,c,t] = W[b,c,t] * FFT_ortho( sum_e maps[b,e,c] * x[b,e,t] )
+ *   x     [B,E,T,Y,X] complex64 (in)      maps [B,E,C,Y,X] complex64 (in; the reference's
+ *   k_out [B,C,T,Y,X] complex64 (out)          [B,E,C,1,Y,X] with the singleton dropped)
+ *   weights : real fp32 k-space weights or NULL (the reference's `weights=None -> 1.0`,
+ *             transforms.py:79-82); addressed as weights[b*ws[0]+c*ws[1]+t*ws[2]+y*ws[3]+x*ws[4]]
+ *             with ws = w_strides (element strides, 0 on broadcast axes; any expand()ed view works).
+ *   ndims   : 2 = FFT over (Y,X); 1 = FFT over X only (what the reference derives from a
+ *             maps tensor whose squeezed image is 1-D, transforms.py:76).
+ *   maps    : may be NULL = unit sensitivities; with E = C = 1 the call is then the plain ortho
+ *             (i)FFT of FFT.forward (transforms.py:28-46) over a batch of B*T images.
+ */
+int dlsg_sense_forward_c64(const void* x, const void* maps, const float* weights, const long long* w_strides,
+                           void* k_out, void* workspace, size_t workspace_bytes,
+                           int B, int E, int C, int T, int Y, int X, int ndims, void* stream);
+
+/* SENSE adjoint operator, replaces SenseModel._adjoint_op (dl_cs/mri/transforms.py:84-90):
+ *     x[b,e,t] = sum_c conj(maps[b,e,c]) * IFFT_ortho( W[b,c,t] * k[b,c,t] )
+ */
+int dlsg_sense_adjoint_c64(const void* k, const void* maps, const float* weights, const long long* w_strides,
+                           void* x_out, void* workspace, size_t workspace_bytes,
+                           int B, int E, int C, int T, int Y, int X, int ndims, void* stream);
+
+/* Fused normal operator  x_out = A^H(A(x))  — the core of the data-consistency update
+ * A(A(x), adjoint=True) at dl_cs/models/unrolledswin.py:109 and unrolled.py:104.
+ * k-space never leaves the chip's L2: the weights are applied squared between the two column passes.
+ * x_out must not alias x. */
+int dlsg_sense_normal_c64(const void* x, const void* maps, const float* weights, const long long* w_strides,
+                          void* x_out, void* workspace, size_t workspace_bytes,
+                          int B, int E, int C, int T, int Y, int X, int ndims, void* stream);
+
+/* Fused data-consistency update (dl_cs/models/unrolledswin.py:109):
+ *     x_out = x + step * ( A^H(A(x)) - aty )
+ * aty [B,E,T,Y,X] complex64 is A^H y precomputed once per reconstruction (unrolledswin.py:96).
+ * step: the PGD step size (nn.Parameter init -2.0, unrolledswin.py:88-89).  If step_dev is non-NULL the
+ * kernel reads the scalar from that device address instead (no host sync on a CUDA parameter, graph-safe).
+ * x_out must not alias x or aty. */
+int dlsg_sense_dc_step_c64(const void* x, const void* aty, const void* maps, const float* weights,
+                           const long long* w_strides, float step, const float* step_dev, void* x_out,
+                           void* workspace, size_t workspace_bytes,
+                           int B, int E, int C, int T, int Y, int X, int ndims, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLSG_B200_H */
