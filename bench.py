@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the SENSE data-consistency hot path (BASELINE.json configs[1]).
+
+Workload (config.workload = "config_recon.yaml"): unrolled-network inference on a batch of 64
+synthetic cine slices per GPU — E=1 map set, 8 coils, 20 frames, 192x160, 12x k-t mask, NUM_UNROLLS=5
+(/root/reference/configs/config_recon.yaml:5-17).  One *step* is one pass of the hot path over that
+batch: ATy = A^H y, then 5 data-consistency updates x <- x + s (A^H A x - ATy)
+(dl_cs/models/unrolled.py:96-104), through the reference-facing API (SenseModel + the PGD loop mirror).
+The denoiser between the updates is not part of this path and is not run.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = slices/s with inputs resident in HBM; `e2e` = the same through
+the same API from pinned host buffers (H2D of y/maps/mask and D2H of x inside the timed region);
+`roofline` = the dominant SENSE op (the fused DC step) in algorithmic GB/s against the measured HBM
+peak; `ops` gives forward / adjoint / normal too; `cpu_baseline` = the torch-CPU port of the
+reference path (oracle/sense_oracle_torch.py) on a bounded sample.  `--impl reference` times only
+that CPU port (the Python reference itself cannot travel to the GPU box; kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOAD = dict(B=64, E=1, C=8, T=20, Y=192, X=160, unrolls=5, step=-2.0, accel=12)
+METRIC = "cine slices/sec (SENSE data-consistency path of the unrolled recon)"
+UNIT = "slices/s"
+
+
+# --------------------------------------------------------------------------- algorithmic bytes
+def algorithmic_bytes(op: str, B, E, C, T, Y, X, mask_elems) -> int:
+    P = B * T * Y * X
+    maps = 8 * B * E * C * Y * X
+    M = 4 * mask_elems
+    if op in ("forward", "adjoint"):
+        return 8 * P * (E + C) + maps + M
+    if op == "normal":
+        return 16 * P * E + maps + M
+    if op == "dc_step":
+        return 24 * P * E + maps + M
+    raise ValueError(op)
+
+
+def algorithmic_flops(op: str, B, E, C, T, Y, X) -> float:
+    n = Y * X
+    fft = 5.0 * n * np.log2(n) * B * C * T
+    mac = 8.0 * B * T * Y * X * E * C
+    return (fft + mac) * (1 if op in ("forward", "adjoint") else 2)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- synthetic data
+def make_mask(B, T, Y, X, accel, seed):
+    """0/1 k-t mask [B,1,T,Y,X]: every accel-th ky line shifted per frame, centre lines, first quarter of kx empty."""
+    rng = np.random.default_rng(seed)
+    mask = np.zeros((B, 1, T, Y, X), dtype=np.float32)
+    for b in range(B):
+        off = int(rng.integers(0, accel))
+        for t in range(T):
+            rows = (np.arange(Y) + 5 * t + off) % accel == 0
+            centre = np.abs(np.arange(Y) - Y // 2) < max(1, Y // 32)
+            mask[b, 0, t, np.roll(rows | centre, -(Y // 2)), :] = 1.0
+    mask[..., : X // 4] = 0.0
+    return mask
+
+
+def device_problem(cfg, dev, seed):
+    """maps, mask, y = mask * A_full(x_true) generated on the device (seed 1000 + rank)."""
+    from dl_swin_gan_b200.mri import SenseModel
+    B, E, C, T, Y, X = (cfg[k] for k in "BECTYX")
+    g = torch.Generator(device=dev).manual_seed(seed)
+
+    def cn(*s):
+        return torch.view_as_complex(torch.randn(*s, 2, generator=g, device=dev)) * (0.5 ** 0.5)
+
+    maps = cn(B, E, C, 1, Y, X) / (E * C) ** 0.5
+    x_true = cn(B, E, T, Y, X)
+    mask = torch.from_numpy(make_mask(B, T, Y, X, cfg["accel"], seed)).to(dev)
+    y = SenseModel(maps, weights=mask)(x_true)
+    return maps, mask, y
+
+
+# --------------------------------------------------------------------------- CPU port arm
+def cpu_port_rate(cfg, seconds_target=12.0):
+    """slices/s of the torch-CPU port of the reference path on a bounded sample of the workload."""
+    from oracle import sense_oracle_torch as st
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    E, C, T, Y, X = (cfg[k] for k in "ECTYX")
+    g = torch.Generator().manual_seed(1000)
+
+    def cn(*s):
+        return torch.view_as_complex(torch.randn(*s, 2, generator=g)) * (0.5 ** 0.5)
+
+    nb = 1
+    maps = cn(nb, E, C, 1, Y, X) / (E * C) ** 0.5
+    mask = torch.from_numpy(make_mask(nb, T, Y, X, cfg["accel"], 1000))
+    y = mask * cn(nb, C, T, Y, X)
+    st.dc_path(y, maps, mask, 1, cfg["step"])            # warm-up (thread pool, FFT plans)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        st.dc_path(y, maps, mask, cfg["unrolls"], cfg["step"])
+        n += nb
+        el = time.perf_counter() - t0
+        if el > seconds_target or n >= 16:
+            break
+    return n / el, threads, f"{n} slice(s) of the batch through A^H y + {cfg['unrolls']} DC updates, {el:.1f} s"
+
+
+def run_reference_arm(args, rank):
+    cfg = dict(WORKLOAD)
+    if rank != 0:
+        return
+    rates = []
+    for _ in range(max(1, args.warmup)):
+        pass                                              # the port warms itself up inside cpu_port_rate
+    budget = max(2.0, min(20.0, 60.0 / max(1, args.steps)))
+    for _ in range(args.steps):
+        rate, threads, sample = cpu_port_rate(cfg, seconds_target=budget)
+        rates.append(rate)
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cfg["B"] / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (complex64)",
+        "data": "synthetic", "config": {"workload": "config_recon.yaml", **cfg},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- main arm
+def time_op(fn, iters, dev):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize(dev)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize(dev)
+    return s.elapsed_time(e) / iters   # ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=WORKLOAD["B"], help="slices per GPU (default: the config's 64)")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import __graft_entry__ as ge
+    if rank == 0 or not os.path.exists(ge.LIB):
+        ge.build()
+    from dl_swin_gan_b200 import _lib
+    from dl_swin_gan_b200.mri import SenseModel
+    from dl_swin_gan_b200.unrolled import ProximalGradientDescent
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = dict(WORKLOAD)
+    cfg["B"] = args.batch
+    B, E, C, T, Y, X = (cfg[k] for k in "BECTYX")
+    lib = _lib.load()
+
+    maps, mask, y = device_problem(cfg, dev, 1000 + rank)
+    A = SenseModel(maps, weights=mask)
+    pgd = ProximalGradientDescent(num_unrolls=cfg["unrolls"], step_init=cfg["step"]).to(dev)
+
+    def step():
+        with torch.no_grad():
+            return pgd(y, A)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    n0 = lib.dlsg_launch_count()
+    with ClockSampler(local_rank) as clocks:
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        for _ in range(args.steps):
+            out = step()
+        e_ev.record()
+        barrier()
+    launches = int(lib.dlsg_launch_count() - n0)
+    ms = torch.tensor([s_ev.elapsed_time(e_ev)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- per-op timings for the roofline (CUDA events on the launching stream, batch >> L2)
+    hbm_peak, peak_src = measured_peaks()
+    x0 = out
+    aty = A(y, adjoint=True)
+    ops = {}
+    iters = 5
+    with torch.no_grad():
+        t_ms = {
+            "forward": time_op(lambda: A(x0), iters, dev),
+            "adjoint": time_op(lambda: A(y, adjoint=True), iters, dev),
+            "normal": time_op(lambda: A.normal(x0), iters, dev),
+            "dc_step": time_op(lambda: A.dc_step(x0, aty, pgd.step_size), iters, dev),
+        }
+    for name, t in t_ms.items():
+        nbytes = algorithmic_bytes(name, B, E, C, T, Y, X, mask.numel())
+        ops[name] = {"ms": t, "algorithmic_MB_per_slice": nbytes / B / 1e6, "GBps": nbytes / (t * 1e-3) / 1e9,
+                     "frac_hbm": nbytes / (t * 1e-3) / 1e9 / hbm_peak,
+                     "TFLOPs_nominal": algorithmic_flops(name, B, E, C, T, Y, X) / (t * 1e-3) / 1e12}
+    dom = "dc_step"
+    roofline = {"bound": "hbm", "kernel": "fused DC step chain (rows_fwd + cols_normal + rows_adj)",
+                "achieved": ops[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": ops[dom]["frac_hbm"],
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algorithmic_bytes(dom, B, E, C, T, Y, X, mask.numel())}
+
+    # ---- end to end from pinned host memory through the same API
+    e2e = None
+    if not args.skip_e2e:
+        hy = torch.empty(y.shape, dtype=y.dtype, pin_memory=True).copy_(y)
+        hm = torch.empty(maps.shape, dtype=maps.dtype, pin_memory=True).copy_(maps)
+        hw = torch.empty(mask.shape, dtype=mask.dtype, pin_memory=True).copy_(mask)
+        hx = torch.empty((B, E, T, Y, X), dtype=torch.complex64, pin_memory=True)
+        h2d = hy.numel() * 8 + hm.numel() * 8 + hw.numel() * 4
+        d2h = hx.numel() * 8
+
+        def e2e_step():
+            with torch.no_grad():
+                dy = hy.to(dev, non_blocking=True)
+                dm = hm.to(dev, non_blocking=True)
+                dw = hw.to(dev, non_blocking=True)
+                res = pgd(dy, SenseModel(dm, weights=dw))
+                hx.copy_(res, non_blocking=True)
+
+        n_e2e = max(2, min(args.steps, 5))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        el = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * n_e2e / float(el.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        rate, threads, sample = cpu_port_rate(cfg)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (complex64)", "data": "synthetic",
+            "config": {"workload": "config_recon.yaml", **cfg, "slices_per_gpu": B,
+                       "l2": "working set per step (y 2.5 GB + x/maps/mask) >> 126 MB L2, no flush needed",
+                       "workspace_MB": float(os.environ.get("DLSG_WORKSPACE_MB", 64))},
+            "roofline": roofline, "ops": ops, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

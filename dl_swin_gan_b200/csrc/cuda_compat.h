@@ -19,10 +19,16 @@
     type* name = reinterpret_cast<type*>(dlsg_dyn_smem_raw)
 #define DLSG_LAUNCH_BOUNDS(...) __launch_bounds__(__VA_ARGS__)
 
+#include <atomic>
 namespace dlsg {
 using stream_t = cudaStream_t;
+inline std::atomic<unsigned long long>& launch_counter() {
+    static std::atomic<unsigned long long> n{0};   // statistics only (bench.py's gpu_launches); no behaviour depends on it
+    return n;
+}
 template <typename K, typename... A>
 inline int launch(K kernel, dim3 grid, dim3 block, size_t smem, stream_t s, A... args) {
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { (void)cudaGetLastError(); return -1; }
@@ -90,11 +96,17 @@ using std::max;
 #define DLSG_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(dlsg_emu::t_ctx->smem)
 #define DLSG_LAUNCH_BOUNDS(...)
 
+#include <atomic>
 namespace dlsg {
 using stream_t = void*;
+inline std::atomic<unsigned long long>& launch_counter() {
+    static std::atomic<unsigned long long> n{0};
+    return n;
+}
 template <typename K, typename... A>
 inline int launch(K kernel, dim3 grid, dim3 block, size_t smem, stream_t, A... args) {
     using namespace dlsg_emu;
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
     if (smem > 227 * 1024 || block.x > 1024 || block.y != 1 || block.z != 1) return -1;
     g_blockDim = block; g_gridDim = grid;
     const size_t smem_alloc = ((smem + 255) / 128) * 128;

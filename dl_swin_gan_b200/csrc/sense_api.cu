@@ -253,6 +253,8 @@ extern "C" {
 
 int dlsg_version(void) { return 100; }
 
+unsigned long long dlsg_launch_count(void) { return dlsg::launch_counter().load(std::memory_order_relaxed); }
+
 const char* dlsg_status_string(int status) {
     switch (status) {
         case DLSG_OK: return "ok";

@@ -1,0 +1,319 @@
+"""Drop-in mirror of dl_cs/mri/transforms.py (FFT, SenseModel) on the B200 kernels.
+
+Same class names, constructor arguments, call signature, attributes and assertions as the
+reference (`SenseModel(maps, weights)(data, adjoint=False)`, transforms.py:49-111;
+`FFT(ndims, norm)(data, adjoint, centered)`, transforms.py:12-46), so the unrolled solvers
+that receive the operator by dependency injection (`forward(self, y, A, x0)`,
+unrolledswin.py:91, unrolled.py:86) run unchanged.  Arithmetic happens in the hand-written
+sm_100a kernels behind the C ABI of include/dlsg_b200.h; torch is used for device memory,
+streams and autograd plumbing only.  There is no CPU path: CPU tensors raise.
+
+Beyond the reference interface the operator offers two fused entries the solvers may use
+when present (they fall back to two calls otherwise):
+    A.normal(x)              == A(A(x), adjoint=True)
+    A.dc_step(x, ATy, step)  == x + step * (A(A(x), adjoint=True) - ATy)      (unrolledswin.py:109)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+from torch import nn
+
+from .. import _lib
+
+_WORKSPACE_MB_DEFAULT = 64
+
+
+def _workspace_budget() -> int:
+    return int(float(os.environ.get("DLSG_WORKSPACE_MB", _WORKSPACE_MB_DEFAULT)) * (1 << 20))
+
+
+def _require_cuda_c64(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} is on {t.device}: dl_swin_gan_b200 runs on CUDA (sm_100a) only and has no CPU fallback")
+    if t.dtype != torch.complex64:
+        raise TypeError(f"{what} must be complex64 (got {t.dtype}); the B200 kernels compute in fp32")
+
+
+# --------------------------------------------------------------------------------------
+# low-level launcher shared by SenseModel and FFT
+# --------------------------------------------------------------------------------------
+def _launch(kind: str, data: torch.Tensor, maps5: Optional[torch.Tensor], wexp: Optional[torch.Tensor],
+            dims, ndims: int, aty: Optional[torch.Tensor] = None, step=None) -> torch.Tensor:
+    """kind in {'fwd','adj','normal','dc'}; dims = (B,E,C,T,Y,X); tensors already validated/contiguous."""
+    lib = _lib.load()
+    B, E, C, T, Y, X = dims
+    dev = data.device
+    out_shape = (B, C, T, Y, X) if kind == "fwd" else (B, E, T, Y, X)
+    out = torch.empty(out_shape, dtype=torch.complex64, device=dev)
+    if out.numel() == 0 or data.numel() == 0:
+        return out.zero_()
+    if wexp is not None:
+        wptr = wexp.data_ptr()
+        wstr = (ctypes.c_longlong * 5)(*wexp.stride())
+    else:
+        wptr, wstr = None, None
+    nbytes = lib.dlsg_sense_workspace_bytes(B, E, C, T, Y, X, ndims, _workspace_budget())
+    work = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)
+    mptr = maps5.data_ptr() if maps5 is not None else None
+    with torch.cuda.device(dev):
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        tail = (work.data_ptr(), nbytes, B, E, C, T, Y, X, ndims, stream)
+        if kind == "fwd":
+            st = lib.dlsg_sense_forward_c64(data.data_ptr(), mptr, wptr, wstr, out.data_ptr(), *tail)
+        elif kind == "adj":
+            st = lib.dlsg_sense_adjoint_c64(data.data_ptr(), mptr, wptr, wstr, out.data_ptr(), *tail)
+        elif kind == "normal":
+            st = lib.dlsg_sense_normal_c64(data.data_ptr(), mptr, wptr, wstr, out.data_ptr(), *tail)
+        elif kind == "dc":
+            if isinstance(step, torch.Tensor):
+                step_host, step_dev = 0.0, step.data_ptr()
+            else:
+                step_host, step_dev = float(step), None
+            st = lib.dlsg_sense_dc_step_c64(data.data_ptr(), aty.data_ptr(), mptr, wptr, wstr,
+                                            step_host, step_dev, out.data_ptr(), *tail)
+        else:  # pragma: no cover
+            raise AssertionError(kind)
+    _lib.check(st, f"dlsg_sense_{kind}")
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# FFT  (dl_cs/mri/transforms.py:12-46)
+# --------------------------------------------------------------------------------------
+class FFT(nn.Module):
+    """Centered-optional N-dimensional (i)FFT over the trailing `ndims` axes, norm='ortho' by default."""
+
+    def __init__(self, ndims: int, norm: Optional[str] = "ortho") -> None:
+        super().__init__()
+        self.ndims = ndims
+        self.norm = norm
+        self.fft_dims = [i for i in range(-1, -1 - ndims, -1)]
+
+    def forward(self, data: torch.Tensor, adjoint: Optional[bool] = False, centered: Optional[bool] = False):
+        assert torch.is_complex(data)  # force complex (transforms.py:33)
+        _require_cuda_c64(data, "FFT input")
+        if self.ndims == 0:
+            return data.clone()
+        if self.ndims not in (1, 2):
+            raise NotImplementedError(f"FFT over {self.ndims} trailing axes: the B200 kernels cover ndims 1 and 2")
+        if data.dim() < self.ndims:
+            raise ValueError("FFT input has fewer dimensions than ndims")
+        if centered:
+            data = torch.fft.ifftshift(data, dim=self.fft_dims)   # index permutation only
+        out = _FftFn.apply(data, self.ndims, bool(adjoint), self.norm)
+        if centered:
+            out = torch.fft.fftshift(out, dim=self.fft_dims)
+        return out
+
+
+def _fft_raw(data: torch.Tensor, ndims: int, inverse: bool) -> torch.Tensor:
+    """ortho (i)FFT of the trailing ndims axes through the SENSE entry points with unit maps."""
+    shape = data.shape
+    X = shape[-1]
+    Y = shape[-2] if ndims == 2 else 1
+    flat = data.contiguous().reshape(-1, 1, 1, Y, X)      # [B,E=1,T=1,Y,X]; C = 1
+    B = flat.shape[0]
+    out = _launch("adj" if inverse else "fwd", flat, None, None, (B, 1, 1, 1, Y, X), 2)
+    return out.reshape(shape)
+
+
+class _FftFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, ndims, inverse, norm):
+        ctx.cfg = (ndims, inverse, norm)
+        out = _fft_raw(data, ndims, inverse)
+        n = 1
+        for d in data.shape[-ndims:]:
+            n *= d
+        # kernels are ortho; other torch.fft norm modes are a scalar away
+        if norm in (None, "backward"):
+            out = out * (n ** -0.5 if inverse else n ** 0.5)
+        elif norm == "forward":
+            out = out * (n ** 0.5 if inverse else n ** -0.5)
+        elif norm != "ortho":
+            raise ValueError(f"unknown norm {norm!r}")
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        ndims, inverse, norm = ctx.cfg
+        # VJP of a DFT is the conjugate-transpose DFT; the non-ortho scalings swap roles
+        back_norm = {"ortho": "ortho", None: "forward", "backward": "forward", "forward": "backward"}[norm]
+        return _FftFn.apply(grad, ndims, not inverse, back_norm), None, None, None
+
+
+# --------------------------------------------------------------------------------------
+# SenseModel  (dl_cs/mri/transforms.py:49-111)
+# --------------------------------------------------------------------------------------
+class SenseModel(nn.Module):
+    """Forward  y = (W * F * S) x   and adjoint  x = (S^H * F^H * W) y   SENSE operations.
+
+    Args:
+        maps (torch.Tensor[complex64]): [batch, emaps, coils, 1, y, x]
+        weights (torch.Tensor, optional): real, broadcastable to [batch, coils, t, y, x]
+            (the usual sampling mask is [batch, 1, t, y, x]); None means 1.0.
+    The constructor does no device work (the training loop builds one per step,
+    scripts/train_swin.py:116); layout preparation happens on first use and is cached.
+    """
+
+    def __init__(self, maps: torch.Tensor, weights: Optional[torch.Tensor] = None) -> None:
+        super().__init__()
+        assert torch.is_complex(maps)  # force complex (transforms.py:70)
+        self.maps = maps
+        ndims = len(list(maps[0, 0, 0, ...].squeeze().shape))
+        self.fft = FFT(ndims)
+        if weights is None:
+            self.weights = 1.0
+        else:
+            self.weights = weights
+        self._maps5 = None
+        self._w32 = None
+
+    # ---- reference interface ---------------------------------------------------------
+    def forward(self, data: torch.Tensor, adjoint: Optional[bool] = False) -> torch.Tensor:
+        assert torch.is_complex(data)  # transforms.py:104
+        return _SenseFn.apply(data, self, "adj" if adjoint else "fwd")
+
+    def _adjoint_op(self, data: torch.Tensor) -> torch.Tensor:
+        return self.forward(data, adjoint=True)
+
+    def _forward_op(self, data: torch.Tensor) -> torch.Tensor:
+        return self.forward(data, adjoint=False)
+
+    # ---- fused entries ---------------------------------------------------------------
+    def normal(self, data: torch.Tensor) -> torch.Tensor:
+        """A(A(x), adjoint=True) in one fused chain (k-space stays in L2)."""
+        assert torch.is_complex(data)
+        return _SenseFn.apply(data, self, "normal")
+
+    def dc_step(self, x: torch.Tensor, aty: torch.Tensor, step) -> torch.Tensor:
+        """x + step * (A(A(x), adjoint=True) - aty)   — unrolledswin.py:109 in one fused chain."""
+        assert torch.is_complex(x) and torch.is_complex(aty)
+        if not isinstance(step, torch.Tensor):
+            step = torch.as_tensor(float(step), dtype=torch.float32)   # host scalar, no device work
+        return _DcFn.apply(x, aty, step, self)
+
+    # ---- preparation -------------------------------------------------------------------
+    def _prepared_maps(self) -> torch.Tensor:
+        if self._maps5 is None:
+            m = self.maps
+            _require_cuda_c64(m, "SenseModel maps")
+            if m.dim() != 6 or m.shape[3] != 1:
+                raise ValueError(f"maps must be [batch, emaps, coils, 1, y, x]; got {tuple(m.shape)}")
+            self._maps5 = m.detach()[:, :, :, 0].contiguous()
+        return self._maps5
+
+    def _prepared_weights(self, dims, device):
+        """-> fp32 tensor expanded (stride-0 broadcast, no copy) to [B,C,T,Y,X], or None for 1.0."""
+        w = self.weights
+        B, E, C, T, Y, X = dims
+        if not isinstance(w, torch.Tensor):
+            if float(w) == 1.0:
+                return None
+            if self._w32 is None:
+                self._w32 = torch.full((1,), float(w), dtype=torch.float32, device=device)
+            return self._w32.expand(B, C, T, Y, X)
+        if self._w32 is None:
+            if torch.is_complex(w):
+                raise TypeError("SenseModel weights must be real (the reference documents a float mask)")
+            if not w.is_cuda:
+                raise RuntimeError(f"SenseModel weights are on {w.device}; CUDA tensors only (no CPU fallback)")
+            w32 = w.detach()
+            if w32.dtype != torch.float32:
+                w32 = w32.to(torch.float32)
+            self._w32 = w32
+        w32 = self._w32
+        if w32.dim() > 5:
+            raise ValueError(f"weights must broadcast to [batch, coils, t, y, x]; got {tuple(w32.shape)}")
+        return w32.expand(B, C, T, Y, X)   # raises like torch broadcasting does when incompatible
+
+    def _dims(self, data: torch.Tensor, kind: str):
+        maps5 = self._prepared_maps()
+        Bm, E, C, Y, X = maps5.shape
+        if data.dim() != 5:
+            raise ValueError(f"SENSE data must be 5-D ([batch, emaps|coils, t, y, x]); got {tuple(data.shape)}")
+        B, ch, T, Yd, Xd = data.shape
+        want = C if kind == "adj" else E
+        if (Yd, Xd) != (Y, X) or ch != want or B != Bm:
+            raise ValueError(
+                f"SENSE {kind}: data {tuple(data.shape)} does not match maps {tuple(self.maps.shape)} "
+                f"(expected [{Bm}, {want}, T, {Y}, {X}])")
+        return (B, E, C, T, Y, X)
+
+    def _kernel_ndims(self, dims) -> int:
+        nd = self.fft.ndims
+        Y, X = dims[4], dims[5]
+        if nd == 2:
+            return 2
+        if nd == 1:
+            # reference: FFT over the last axis only.  With Y == 1 the 2-D path is identical (and faster).
+            return 2 if Y == 1 else 1
+        if nd == 0:
+            return 2   # Y == X == 1: the transform is the identity either way
+        raise NotImplementedError(
+            f"maps with a non-singleton 4th axis imply a {nd}-D FFT (transforms.py:76); the B200 kernels cover 1-D/2-D")
+
+    def _run(self, kind: str, data: torch.Tensor, aty=None, step=None) -> torch.Tensor:
+        _require_cuda_c64(data, "SENSE input")
+        dims = self._dims(data, kind)
+        maps5 = self._prepared_maps()
+        if maps5.device != data.device:
+            raise RuntimeError(f"SENSE input on {data.device} but maps on {maps5.device}")
+        wexp = self._prepared_weights(dims, data.device)
+        if wexp is not None and wexp.device != data.device:
+            raise RuntimeError(f"SENSE input on {data.device} but weights on {wexp.device}")
+        data = data.detach().contiguous()
+        if kind == "dc":
+            _require_cuda_c64(aty, "ATy")
+            if aty.shape != data.shape:
+                raise ValueError(f"ATy {tuple(aty.shape)} must have the shape of x {tuple(data.shape)}")
+            aty = aty.detach().contiguous()
+            if isinstance(step, torch.Tensor):
+                if step.is_cuda and step.dtype == torch.float32 and step.numel() == 1 and step.device == data.device:
+                    step = step.detach()
+                else:
+                    step = float(step)
+        return _launch(kind, data, maps5, wexp, dims, self._kernel_ndims(dims), aty, step)
+
+
+class _SenseFn(torch.autograd.Function):
+    """A is linear: VJP(A) = A^H, VJP(A^H) = A, VJP(A^H A) = A^H A.  maps / weights carry no gradient."""
+
+    _BACK = {"fwd": "adj", "adj": "fwd", "normal": "normal"}
+
+    @staticmethod
+    def forward(ctx, data, model, kind):
+        ctx.model, ctx.kind = model, kind
+        return model._run(kind, data)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return _SenseFn.apply(grad, ctx.model, _SenseFn._BACK[ctx.kind]), None, None
+
+
+class _DcFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, aty, step, model):
+        ctx.model = model
+        ctx.save_for_backward(x, aty, step)
+        return model._run("dc", x, aty=aty, step=step)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, aty, step = ctx.saved_tensors
+        model = ctx.model
+        s = step.to(device=grad.device, dtype=torch.float32)
+        gx = gaty = gstep = None
+        if ctx.needs_input_grad[0]:
+            gx = grad + s * _SenseFn.apply(grad, model, "normal")
+        if ctx.needs_input_grad[1]:
+            gaty = -s * grad
+        if ctx.needs_input_grad[2]:
+            resid = _SenseFn.apply(x, model, "normal") - aty
+            gstep = (resid.conj() * grad).real.sum().reshape(step.shape).to(step.device)
+        return gx, gaty, gstep, None

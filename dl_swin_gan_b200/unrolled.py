@@ -1,0 +1,43 @@
+"""Host-side mirror of the unrolled solvers' data-consistency loop.
+
+`ProximalGradientDescent.forward(y, A, x0)` of the reference (dl_cs/models/unrolledswin.py:91-122,
+dl_cs/models/unrolled.py:86-117) with the operator `A` injected exactly as there.  The per-unroll
+update `x = x + step_size * (A(A(x), adjoint=True) - ATy)` (unrolledswin.py:109) goes through the
+fused `A.dc_step` entry when the operator offers it and through two operator calls otherwise, so a
+reference `SenseModel` and the B200 `SenseModel` are interchangeable here.
+
+The denoiser list `cnn_update` is a constructor argument: the Swin / ResNet denoisers are the callers'
+business (cuDNN convolutions); with `None` the loop is the pure data-consistency path
+that bench.py measures.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import torch
+from torch import nn
+
+
+class ProximalGradientDescent(nn.Module):
+    def __init__(self, num_unrolls: int = 5, cnn_update: Optional[Sequence[Callable]] = None,
+                 fix_step_size: bool = True, step_init: float = -2.0) -> None:
+        super().__init__()
+        self.num_unrolls = num_unrolls
+        self.cnn_update = nn.ModuleList(cnn_update) if cnn_update is not None and all(
+            isinstance(m, nn.Module) for m in cnn_update) else cnn_update
+        # PGD step size (unrolledswin.py:88-89)
+        self.step_size = nn.Parameter(torch.tensor([step_init], dtype=torch.float32),
+                                      requires_grad=(not fix_step_size))
+
+    def forward(self, y, A, x0=None):
+        ATy = A(y, adjoint=True)                       # unrolledswin.py:96
+        xi = ATy if x0 is None else x0
+        fused = getattr(A, "dc_step", None)
+        for i in range(self.num_unrolls):
+            if fused is not None:
+                xi = fused(xi, ATy, self.step_size)
+            else:
+                xi = xi + self.step_size * (A(A(xi), adjoint=True) - ATy)
+            if self.cnn_update is not None:
+                xi = self.cnn_update[i](xi)
+        return xi

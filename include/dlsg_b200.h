@@ -32,6 +32,10 @@ extern "C" {
 /* Library version (major*10000 + minor*100 + patch). */
 int dlsg_version(void);
 
+/* Kernels this library has launched so far in this process (monotonic atomic counter; statistics only —
+ * bench.py reports the difference over its timed region as gpu_launches). */
+unsigned long long dlsg_launch_count(void);
+
 /* Human-readable text for a status code (static storage). */
 const char* dlsg_status_string(int status);
 

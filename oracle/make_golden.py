@@ -1,0 +1,81 @@
+"""Generate tests/golden/sense_*.npz by running the UNMODIFIED reference implementation.
+
+Run in the build container only (it imports /root/reference, which does not exist on the GPU
+box):      python oracle/make_golden.py
+Each fixture holds the outputs (inputs are regenerated from oracle/golden_inputs.py seeds) of
+    dl_cs.mri.transforms.SenseModel / FFT        (/root/reference/dl_cs/mri/transforms.py)
+    dl_cs.mri.utils.fftmod / sliding_window      (/root/reference/dl_cs/mri/utils.py)
+computed with torch on CPU in complex64 (what the reference runs) and, for an error floor,
+in complex128.  tests/test_oracle_golden.py pins oracle/sense_oracle.py to these vectors and
+tests/test_sense_gpu.py compares the CUDA path with them on the B200.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+from oracle.golden_inputs import CASES, make_inputs  # noqa: E402
+
+
+def main():
+    sys.path.insert(0, REF)
+    from dl_cs.mri.transforms import SenseModel, FFT   # the reference, unmodified
+    from dl_cs.mri import utils as ref_utils
+
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    for name, (B, E, C, T, Y, X, wkind) in CASES.items():
+        maps, x, k, aty, w = make_inputs(name, B, E, C, T, Y, X, wkind)
+        out = {"step": np.float32(-2.0)}
+        small = k.size <= 5000
+        for tag, cdt in (("c64", torch.complex64), ("c128", torch.complex128)):
+            if tag == "c128" and not small:
+                continue
+            tm = torch.from_numpy(maps).to(cdt)
+            tw = None if w is None else torch.from_numpy(w).to(torch.float32 if cdt == torch.complex64 else torch.float64)
+            A = SenseModel(tm, weights=tw)
+            tx, tk, ta = (torch.from_numpy(a).to(cdt) for a in (x, k, aty))
+            fwd = A(tx)
+            adj = A(tk, adjoint=True)
+            nrm = A(A(tx), adjoint=True)
+            dc = tx + float(out["step"]) * (nrm - ta)            # unrolledswin.py:109
+            out[f"fwd_{tag}"] = fwd.numpy()
+            out[f"adj_{tag}"] = adj.numpy()
+            out[f"normal_{tag}"] = nrm.numpy()
+            out[f"dc_{tag}"] = dc.numpy()
+            out["ndims"] = np.int32(A.fft.ndims)
+        np.savez_compressed(os.path.join(OUT, f"sense_{name}.npz"), **out)
+        print(name, {k_: v.shape for k_, v in out.items() if hasattr(v, "shape") and v.ndim > 0})
+
+    # FFT module (centered / adjoint) and the helpers either side of the operator
+    rng = np.random.default_rng(77)
+    img = ((rng.standard_normal((3, 12, 10)) + 1j * rng.standard_normal((3, 12, 10)))).astype(np.complex64)
+    img_even = ((rng.standard_normal((2, 8, 6)) + 1j * rng.standard_normal((2, 8, 6)))).astype(np.complex64)
+    series = ((rng.standard_normal((1, 2, 6, 4, 5)) + 1j * rng.standard_normal((1, 2, 6, 4, 5)))).astype(np.complex64)
+    series[:, :, ::3] = 0   # unsampled frames exercise get_mask / time_average
+    f2, f1 = FFT(2), FFT(1)
+    timg = torch.from_numpy(img)
+    misc = {
+        "img": img, "img_even": img_even, "series": series,
+        "fft2": f2(timg).numpy(), "ifft2": f2(timg, adjoint=True).numpy(),
+        "fft2_centered": f2(timg, centered=True).numpy(),
+        "ifft2_centered": f2(timg, adjoint=True, centered=True).numpy(),
+        "fft1": f1(timg).numpy(),
+        "fftmod": ref_utils.fftmod(torch.from_numpy(img_even.copy())).numpy(),
+        "sliding_window5": ref_utils.sliding_window(torch.from_numpy(series), 2, 5).numpy(),
+        "get_mask": ref_utils.get_mask(torch.from_numpy(series)).numpy(),
+    }
+    np.savez_compressed(os.path.join(OUT, "sense_misc.npz"), **misc)
+    print("misc", list(misc))
+
+
+if __name__ == "__main__":
+    main()

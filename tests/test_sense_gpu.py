@@ -1,0 +1,196 @@
+"""Parity of the CUDA SENSE path (through SenseModel -> ctypes -> C ABI -> sm_100a kernels) on a B200.
+
+Bar (BASELINE.json north_star): forward / adjoint within 1e-5 relative L2 of the reference in fp32.
+Checked three ways: against the committed outputs of the unmodified reference (tests/golden), against
+the numpy oracle on seeded inputs over the radix and direct-DFT kernels, and at BASELINE.json's full
+cine size through size-independent properties (adjointness, fused == composed, linearity, delta -> plane wave).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import sense_oracle as so
+from oracle.golden_inputs import CASES
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import __graft_entry__ as ge
+    ge.build()
+    return torch.device("cuda:0")
+
+
+def make_model(maps, w, dev):
+    from dl_swin_gan_b200.mri import SenseModel
+    tw = None if w is None else torch.from_numpy(w).to(dev)
+    return SenseModel(torch.from_numpy(maps).to(dev), weights=tw)
+
+
+def to_np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_matches_reference_golden_vectors(golden_cases, dev, name):
+    inp, ref = golden_cases[name]
+    A = make_model(inp["maps"], inp["weights"], dev)
+    assert A.fft.ndims == int(ref["ndims"])
+    x, k, aty = (torch.from_numpy(inp[n]).to(dev) for n in ("x", "k", "aty"))
+    step = float(ref["step"])
+    got = {
+        "fwd": A(x), "adj": A(k, adjoint=True), "normal": A.normal(x), "dc": A.dc_step(x, aty, step),
+        "composed": A(A(x), adjoint=True),
+    }
+    for key in ("fwd", "adj", "normal", "dc"):
+        assert rel_l2(to_np(got[key]), ref[f"{key}_c64"]) < TOL, (name, key)
+    assert rel_l2(to_np(got["composed"]), ref["normal_c64"]) < TOL
+
+
+SWEEP = [
+    # B, E, C, T, Y, X, weights
+    (2, 1, 8, 5, 192, 160, "mask"),      # cine radices (6, 5), E = 1 as config_recon.yaml
+    (1, 2, 8, 20, 192, 160, "mask"),     # one full cine slice, E = 2 (config 1 / 3)
+    (1, 2, 4, 3, 128, 128, "none"),
+    (1, 1, 3, 2, 160, 160, "full"),
+    (1, 2, 2, 2, 256, 256, "mask"),      # perfusion matrix
+    (1, 1, 2, 2, 320, 320, "mask"),
+    (1, 2, 3, 2, 96, 64, "full"),
+    (1, 3, 2, 2, 64, 32, "mask"),        # E = 3: two accumulator groups
+    (1, 2, 3, 2, 100, 90, "mask"),       # direct-DFT kernels (axes not 32*R)
+    (1, 1, 2, 2, 191, 160, "full"),      # direct columns + radix rows
+    (1, 1, 2, 2, 192, 150, "full"),      # radix-ineligible rows -> direct rows and direct columns
+    (3, 1, 2, 1, 33, 31, "none"),
+]
+
+
+@pytest.mark.parametrize("case", SWEEP)
+def test_matches_oracle_on_seeded_inputs(dev, case):
+    B, E, C, T, Y, X, wkind = case
+    rng = np.random.default_rng(11)
+    maps, x, mask = so.synthetic_problem(B, E, C, T, Y, X, seed=1000)
+    w = {"none": None, "mask": mask, "full": rng.standard_normal((B, C, T, Y, X)).astype(np.float32)}[wkind]
+    k = (rng.standard_normal((B, C, T, Y, X)) + 1j * rng.standard_normal((B, C, T, Y, X))).astype(np.complex64)
+    aty = (rng.standard_normal((B, E, T, Y, X)) + 1j * rng.standard_normal((B, E, T, Y, X))).astype(np.complex64)
+    A = make_model(maps, w, dev)
+    xd, kd, ad = (torch.from_numpy(a).to(dev) for a in (x, k, aty))
+    m128 = maps.astype(np.complex128)
+    assert rel_l2(to_np(A(xd)), so.sense_forward(x.astype(np.complex128), m128, w)) < TOL
+    assert rel_l2(to_np(A(kd, adjoint=True)), so.sense_adjoint(k.astype(np.complex128), m128, w)) < TOL
+    assert rel_l2(to_np(A.normal(xd)), so.sense_normal(x.astype(np.complex128), m128, w)) < TOL
+    ref_dc = so.dc_step(x.astype(np.complex128), aty.astype(np.complex128), m128, w, -2.0)
+    assert rel_l2(to_np(A.dc_step(xd, ad, -2.0)), ref_dc) < TOL
+
+
+def test_workspace_chunking_does_not_change_results(dev, monkeypatch):
+    B, E, C, T, Y, X = 3, 2, 4, 5, 64, 96
+    maps, x, mask = so.synthetic_problem(B, E, C, T, Y, X, seed=3)
+    A = make_model(maps, mask, dev)
+    xd = torch.from_numpy(x).to(dev)
+    monkeypatch.setenv("DLSG_WORKSPACE_MB", "4096")
+    full = [to_np(A(xd)), to_np(A.normal(xd))]
+    for mb in ("0.0001", "0.5", "1.5"):          # one (b,t) set per chunk ... a few frames ... > one slice
+        monkeypatch.setenv("DLSG_WORKSPACE_MB", mb)
+        assert np.array_equal(to_np(A(xd)), full[0])
+        assert np.array_equal(to_np(A.normal(xd)), full[1])
+
+
+def test_full_size_properties_cine_batch(dev):
+    """config_recon.yaml shape, 8 slices of the 64-slice batch: properties that need no CPU oracle run."""
+    B, E, C, T, Y, X = 8, 1, 8, 20, 192, 160
+    g = torch.Generator(device=dev).manual_seed(1000)
+
+    def cn(*s):
+        return torch.view_as_complex(torch.randn(*s, 2, generator=g, device=dev))
+
+    maps = cn(B, E, C, 1, Y, X) / (E * C) ** 0.5
+    mask = (torch.rand(B, 1, T, Y, 1, generator=g, device=dev) < 1 / 12).float().expand(B, 1, T, Y, X).contiguous()
+    from dl_swin_gan_b200.mri import SenseModel
+    A = SenseModel(maps, weights=mask)
+    x, y = cn(B, E, T, Y, X), cn(B, C, T, Y, X)
+    Ax, Ahy = A(x), A(y, adjoint=True)
+    lhs, rhs = torch.vdot(y.flatten(), Ax.flatten()), torch.vdot(Ahy.flatten(), x.flatten())
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5                              # <y, Ax> == <A^H y, x>
+    assert rel_l2(to_np(A.normal(x)), to_np(A(Ax, adjoint=True))) < 2e-6   # fused == composed
+    x2 = cn(B, E, T, Y, X)
+    lin = A(2.0 * x - 0.5j * x2)
+    assert rel_l2(to_np(lin), to_np(2.0 * Ax - 0.5j * A(x2))) < 2e-6      # linearity
+    aty = cn(B, E, T, Y, X)
+    dc = A.dc_step(x, aty, -2.0)
+    assert rel_l2(to_np(dc), to_np(x - 2.0 * (A(Ax, adjoint=True) - aty))) < 2e-6
+    # unmasked operator with unit maps: a delta at (y0, x0) becomes a plane wave of modulus 1/sqrt(YX)
+    ones = torch.ones(1, 1, 1, 1, Y, X, dtype=torch.complex64, device=dev)
+    F = SenseModel(ones)
+    d = torch.zeros(1, 1, 1, Y, X, dtype=torch.complex64, device=dev)
+    d[0, 0, 0, 5, 7] = 1
+    kd = F(d)[0, 0, 0]
+    ky, kx = torch.meshgrid(torch.arange(Y, device=dev), torch.arange(X, device=dev), indexing="ij")
+    wave = torch.exp(-2j * torch.pi * (5 * ky / Y + 7 * kx / X)) / (Y * X) ** 0.5
+    assert rel_l2(to_np(kd), to_np(wave)) < 2e-6
+    # parseval: ortho transform with unit maps preserves energy
+    z = cn(1, 1, 1, Y, X)
+    assert abs(torch.linalg.norm(F(z)) / torch.linalg.norm(z) - 1) < 1e-5
+
+
+def test_autograd_vjp_is_the_adjoint(dev):
+    B, E, C, T, Y, X = 1, 2, 3, 2, 64, 32
+    maps, x, mask = so.synthetic_problem(B, E, C, T, Y, X, seed=5)
+    A = make_model(maps, mask, dev)
+    xd = torch.from_numpy(x).to(dev).requires_grad_()
+    g = torch.from_numpy(so.synthetic_problem(B, C, 1, T, Y, X, seed=6)[1]).to(dev)   # [B,C,T,Y,X]
+    (gx,) = torch.autograd.grad(A(xd), xd, grad_outputs=g)
+    assert rel_l2(to_np(gx), to_np(A(g, adjoint=True))) < 1e-6
+    kd = g.clone().requires_grad_()
+    gi = torch.from_numpy(x).to(dev)
+    (gk,) = torch.autograd.grad(A(kd, adjoint=True), kd, grad_outputs=gi)
+    assert rel_l2(to_np(gk), to_np(A(gi))) < 1e-6
+    # fused DC step: gradients w.r.t. x, ATy and a learnable CUDA step (FIX_STEP_SIZE False)
+    step = torch.tensor([-2.0], device=dev, requires_grad=True)
+    aty = torch.from_numpy(so.synthetic_problem(B, E, 1, T, Y, X, seed=8)[1]).to(dev).requires_grad_()
+    x1 = torch.from_numpy(x).to(dev).requires_grad_()
+    out = A.dc_step(x1, aty, step)
+    x2 = torch.from_numpy(x).to(dev).requires_grad_()
+    aty2 = aty.detach().clone().requires_grad_()
+    step2 = step.detach().clone().requires_grad_()
+    ref = x2 + step2 * (A(A(x2), adjoint=True) - aty2)              # the reference's expression, our operator
+    go = torch.randn_like(out)
+    got = torch.autograd.grad(out, (x1, aty, step), grad_outputs=go)
+    want = torch.autograd.grad(ref, (x2, aty2, step2), grad_outputs=go)
+    for a, b in zip(got, want):
+        assert rel_l2(to_np(a), to_np(b)) < 1e-5
+
+
+def test_fft_module_matches_reference_vectors(dev):
+    import os
+    from conftest import GOLDEN
+    from dl_swin_gan_b200.mri import FFT
+    ref = np.load(os.path.join(GOLDEN, "sense_misc.npz"))
+    img = torch.from_numpy(ref["img"]).to(dev)
+    f2, f1 = FFT(2), FFT(1)
+    assert rel_l2(to_np(f2(img)), ref["fft2"]) < TOL
+    assert rel_l2(to_np(f2(img, adjoint=True)), ref["ifft2"]) < TOL
+    assert rel_l2(to_np(f2(img, centered=True)), ref["fft2_centered"]) < TOL
+    assert rel_l2(to_np(f2(img, adjoint=True, centered=True)), ref["ifft2_centered"]) < TOL
+    assert rel_l2(to_np(f1(img)), ref["fft1"]) < TOL
+    big = torch.view_as_complex(torch.randn(3, 2, 192, 160, 2, device=dev))
+    assert rel_l2(to_np(f2(big)), to_np(torch.fft.fftn(big, dim=(-2, -1), norm="ortho"))) < TOL
+
+
+def test_error_behaviour(dev):
+    from dl_swin_gan_b200.mri import SenseModel
+    maps = torch.view_as_complex(torch.randn(1, 2, 3, 1, 16, 16, 2, device=dev))
+    A = SenseModel(maps)
+    with pytest.raises(AssertionError):
+        A(torch.randn(1, 2, 2, 16, 16, device=dev))                                 # not complex (transforms.py:104)
+    with pytest.raises(ValueError):
+        A(torch.view_as_complex(torch.randn(1, 3, 2, 16, 16, 2, device=dev)))       # wrong emaps count
+    with pytest.raises(TypeError):
+        A(torch.view_as_complex(torch.randn(1, 2, 2, 16, 16, 2, device=dev, dtype=torch.float64)))
+    with pytest.raises(AssertionError):
+        SenseModel(torch.randn(1, 2, 3, 1, 16, 16, device=dev))                    # transforms.py:70
+    empty = torch.zeros(1, 2, 0, 16, 16, dtype=torch.complex64, device=dev)
+    assert A(empty).shape == (1, 3, 0, 16, 16)

@@ -1,0 +1,96 @@
+"""The product's SENSE kernels + C-ABI dispatch, built by g++ under the thread-per-CUDA-thread
+emulation of csrc/cuda_compat.h (TEST ONLY), against the oracle.  Debugs the index math,
+shared-memory layouts and chunk walk without a GPU; the GPU parity tests are in test_sense_gpu.py."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+from oracle import sense_oracle as so
+
+vp = ctypes.c_void_p
+
+
+@pytest.fixture(scope="module")
+def lib(sense_emu_lib):
+    lib = ctypes.CDLL(sense_emu_lib)
+    tail = [vp, ctypes.c_size_t] + [ctypes.c_int] * 7 + [vp]
+    for name in ("forward", "adjoint", "normal"):
+        getattr(lib, f"dlsg_sense_{name}_c64").argtypes = [vp] * 5 + tail
+    lib.dlsg_sense_dc_step_c64.argtypes = [vp] * 5 + [ctypes.c_float, vp, vp] + tail
+    lib.dlsg_sense_workspace_bytes.restype = ctypes.c_size_t
+    lib.dlsg_sense_workspace_bytes.argtypes = [ctypes.c_int] * 7 + [ctypes.c_size_t]
+    return lib
+
+
+def ptr(a):
+    return a.ctypes.data_as(vp)
+
+
+def run_all(lib, B, E, C, T, Y, X, wkind, budget=0, ndims=2, seed=7):
+    rng = np.random.default_rng(seed)
+    maps, x, mask = so.synthetic_problem(B, E, C, T, Y, X, seed=seed)
+    w = {"none": None, "mask": mask,
+         "full": rng.standard_normal((B, C, T, Y, X)).astype(np.float32)}[wkind]
+    k = (rng.standard_normal((B, C, T, Y, X)) + 1j * rng.standard_normal((B, C, T, Y, X))).astype(np.complex64)
+    aty = (rng.standard_normal((B, E, T, Y, X)) + 1j * rng.standard_normal((B, E, T, Y, X))).astype(np.complex64)
+    m5 = np.ascontiguousarray(maps[:, :, :, 0])
+    if w is not None:
+        wb = np.broadcast_to(w, (B, C, T, Y, X))
+        ws, wp = (ctypes.c_longlong * 5)(*[s // 4 for s in wb.strides]), ptr(w)
+    else:
+        ws, wp = None, None
+    nbytes = lib.dlsg_sense_workspace_bytes(B, E, C, T, Y, X, ndims, budget)
+    work = np.zeros(nbytes // 8 + 1, np.complex64)
+    tail = (ptr(work), nbytes, B, E, C, T, Y, X, ndims, None)
+    m128, x128, k128, a128 = (a.astype(np.complex128) for a in (maps, x, k, aty))
+    err = {}
+    out = np.full((B, C, T, Y, X), np.nan, np.complex64)
+    assert lib.dlsg_sense_forward_c64(ptr(x), ptr(m5), wp, ws, ptr(out), *tail) == 0
+    err["fwd"] = rel_l2(out, so.sense_forward(x128, m128, w))
+    out = np.full((B, E, T, Y, X), np.nan, np.complex64)
+    assert lib.dlsg_sense_adjoint_c64(ptr(k), ptr(m5), wp, ws, ptr(out), *tail) == 0
+    err["adj"] = rel_l2(out, so.sense_adjoint(k128, m128, w))
+    out = np.full((B, E, T, Y, X), np.nan, np.complex64)
+    assert lib.dlsg_sense_normal_c64(ptr(x), ptr(m5), wp, ws, ptr(out), *tail) == 0
+    err["normal"] = rel_l2(out, so.sense_normal(x128, m128, w))
+    out = np.full((B, E, T, Y, X), np.nan, np.complex64)
+    assert lib.dlsg_sense_dc_step_c64(ptr(x), ptr(aty), ptr(m5), wp, ws, -2.0, None, ptr(out), *tail) == 0
+    err["dc"] = rel_l2(out, so.dc_step(x128, a128, m128, w, -2.0))
+    return err
+
+
+# (B, E, C, T, Y, X, weights, kwargs) — radix kernels (32*R axes), direct kernels (odd axes), mixes, chunking
+CASES = [
+    ((1, 1, 2, 2, 32, 32, "mask"), {}),
+    ((1, 2, 3, 2, 64, 96, "none"), {}),
+    ((1, 2, 2, 1, 12, 10, "mask"), {}),
+    ((1, 1, 2, 2, 7, 32, "full"), {}),
+    ((1, 3, 2, 2, 32, 15, "full"), {}),
+    ((2, 3, 2, 2, 64, 64, "full"), {"budget": 1}),          # one (slice, frame) per chunk, E > 2 groups
+    ((1, 2, 2, 2, 1, 64, "mask"), {"ndims": 1}),
+]
+
+
+@pytest.mark.parametrize("case,kw", CASES)
+def test_emulated_kernels_match_oracle(lib, case, kw):
+    err = run_all(lib, *case, **kw)
+    for key, e in err.items():
+        assert e < 1e-5, (case, key, e)      # north_star tolerance: 1e-5 relative L2 in fp32
+
+
+@pytest.mark.slow
+def test_emulated_cine_radices_192x160(lib):
+    err = run_all(lib, 1, 1, 2, 2, 192, 160, "mask")
+    assert max(err.values()) < 1e-5
+
+
+def test_status_codes(lib):
+    z = np.zeros(16, np.complex64)
+    tail = (ptr(z), 128, 1, 1, 1, 1, 4, 4, 2, None)
+    assert lib.dlsg_sense_forward_c64(None, ptr(z), None, None, ptr(z), *tail) == -1
+    assert lib.dlsg_sense_forward_c64(ptr(z), ptr(z), None, None, ptr(z), ptr(z), 8, 1, 1, 1, 1, 4, 4, 2, None) == -2
+    assert lib.dlsg_sense_forward_c64(ptr(z), ptr(z), None, None, ptr(z), ptr(z), 128, 1, 1, 1, 1, 4, 4, 3, None) == -1
+    assert lib.dlsg_sense_forward_c64(ptr(z), ptr(z), None, None, ptr(z), ptr(z), 128, 1, 1, 1, 1, 4, 5000, 2, None) == -3
+    assert lib.dlsg_sense_forward_c64(ptr(z), ptr(z), ptr(z), None, ptr(z), *tail) == -1   # weights without strides
