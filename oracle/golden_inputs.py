@@ -38,3 +38,33 @@ def make_inputs(name, B, E, C, T, Y, X, wkind):
     return maps, x, k, aty, w
 
 
+
+
+# ------------------------------------------------------------------ shifted-window attention fixtures
+# name: (B, D, H, W, dim, heads, window, shift)
+SWIN_CASES = {
+    "small_shift": (2, 4, 8, 8, 16, 2, (2, 4, 4), (1, 2, 2)),
+    "small_pad_noshift": (1, 3, 6, 5, 16, 2, (2, 4, 4), (0, 0, 0)),
+    "small_pad_shift": (1, 5, 7, 9, 24, 3, (2, 4, 4), (1, 2, 2)),
+    "clamped_depth": (1, 2, 8, 8, 16, 4, (4, 4, 4), (2, 2, 2)),          # D <= window: window and shift clamp (:72-85)
+    "cine_cfg_shift": (1, 7, 16, 16, 160, 8, (7, 8, 8), (3, 4, 4)),       # hard-coded Swin config (swin3D.py:315), 4 windows
+    "cine_cfg_noshift": (1, 7, 8, 16, 160, 8, (7, 8, 8), (0, 0, 0)),
+}
+
+
+def swin_case(name):
+    B, D, H, W, dim, heads, window, shift = SWIN_CASES[name]
+    rng = np.random.default_rng(2000 + sum(ord(ch) for ch in name))
+    f32 = np.float32
+    ntab = (2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1)
+    params = {
+        "norm1.weight": (1 + 0.1 * rng.standard_normal(dim)).astype(f32),
+        "norm1.bias": (0.1 * rng.standard_normal(dim)).astype(f32),
+        "attn.relative_position_bias_table": (0.5 * rng.standard_normal((ntab, heads))).astype(f32),
+        "attn.qkv.weight": (rng.standard_normal((3 * dim, dim)) / np.sqrt(dim)).astype(f32),
+        "attn.qkv.bias": (0.1 * rng.standard_normal(3 * dim)).astype(f32),
+        "attn.proj.weight": (rng.standard_normal((dim, dim)) / np.sqrt(dim)).astype(f32),
+        "attn.proj.bias": (0.1 * rng.standard_normal(dim)).astype(f32),
+    }
+    x = rng.standard_normal((B, D, H, W, dim)).astype(f32)
+    return dict(x=x, params=params, dim=dim, heads=heads, window=window, shift=shift)

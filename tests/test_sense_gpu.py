@@ -130,7 +130,7 @@ def test_full_size_properties_cine_batch(dev):
     kd = F(d)[0, 0, 0]
     ky, kx = torch.meshgrid(torch.arange(Y, device=dev), torch.arange(X, device=dev), indexing="ij")
     wave = torch.exp(-2j * torch.pi * (5 * ky / Y + 7 * kx / X)) / (Y * X) ** 0.5
-    assert rel_l2(to_np(kd), to_np(wave)) < 2e-6
+    assert rel_l2(to_np(kd), to_np(wave)) < TOL   # the fp32 torch plane wave itself carries ~1e-6
     # parseval: ortho transform with unit maps preserves energy
     z = cn(1, 1, 1, Y, X)
     assert abs(torch.linalg.norm(F(z)) / torch.linalg.norm(z) - 1) < 1e-5
