@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdlsg_b200.so")
+LIB_PATH = os.environ.get("DLSG_LIB_PATH") or os.path.join(_HERE, "csrc", "libdlsg_b200.so")   # override: tuning variants only
 
 DLSG_OK = 0
 DLSG_EINVAL = -1

@@ -19,6 +19,17 @@
     type* name = reinterpret_cast<type*>(dlsg_dyn_smem_raw)
 #define DLSG_LAUNCH_BOUNDS(...) __launch_bounds__(__VA_ARGS__)
 
+// 16-byte asynchronous global -> shared copy (LDGSTS), L1 bypassed; both addresses 16-byte aligned
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_group0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 #include <atomic>
 namespace dlsg {
 using stream_t = cudaStream_t;
@@ -88,6 +99,10 @@ static inline void sincospif(float a, float* s, float* c) {
     *s = (float)std::sin(pi * (double)a); *c = (float)std::cos(pi * (double)a);
 }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline void cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
+static inline void cp_async_wait_all() {}
+static inline void cp_async_commit() {}
+static inline void cp_async_wait_group0() {}
 using std::min;
 using std::max;
 

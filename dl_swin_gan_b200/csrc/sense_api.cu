@@ -11,7 +11,7 @@ namespace {
 
 constexpr int kMaxDirectX = 4096;
 constexpr int kMaxDirectY = 1536;
-constexpr long long kTargetWarps = 148LL * 32;     // row pass: >= 2 waves of 16 warps/SM
+constexpr long long kTargetRowCtas = 148LL * 8;    // row pass: about two waves of 4-5 CTAs per SM
 constexpr long long kTargetColCtas = 148LL * 4;
 
 inline int radix_of(int n) {   // R if n == 32*R with a compiled radix, else 0
@@ -32,20 +32,39 @@ struct Problem {          // what stays fixed over the chunk walk
 
 #define DLSG_TRY(expr) do { if ((expr) != 0) return DLSG_ELAUNCH; } while (0)
 
+// ---- row pass: work split ----------------------------------------------------------------
+// One CTA (4 warps) per (slice, image row, frame chunk).  The frame chunk is a multiple of 4 so that
+// every warp owns whole frames; coil groups are sized so that the staged map rows stay <= 24 KB.
+RowPlan make_row_plan(const SenseDims& d, int e_staged) {
+    RowPlan p;
+    const long long base = (long long)d.B * d.Y;
+    long long want = (kTargetRowCtas + base - 1) / base;
+    const long long max_chunks = (d.t_count + 3) / 4;
+    if (want > max_chunks) want = max_chunks;
+    if (want < 1) want = 1;
+    int tchunk = (int)((d.t_count + want - 1) / want);
+    if (d.t_count >= 4) tchunk = ((tchunk + 3) / 4) * 4;
+    p.tchunk = tchunk;
+    p.nchunks = (d.t_count + tchunk - 1) / tchunk;
+    long long cg = 24576 / ((long long)e_staged * d.X * (long long)sizeof(float2));
+    if (cg < 1) cg = 1;
+    if (cg > d.C) cg = d.C;
+    p.cgroup = (int)cg;
+    return p;
+}
+
 // ---- row pass, forward --------------------------------------------------------------
 template <int RX>
 int launch_rows_fwd(const float2* x, const float2* maps, float2* tmp, const SenseDims& d, stream_t s) {
     using Cfg = RowCfg<RX>;
-    const long long base = (long long)d.B * d.Y;
-    long long want = (kTargetWarps + base - 1) / base;
-    if (want < 1) want = 1;
-    if (want > d.t_count) want = d.t_count;
-    const int tchunk = (int)((d.t_count + want - 1) / want);
-    const int nchunks = (d.t_count + tchunk - 1) / tchunk;
-    const long long warps = base * nchunks;
-    const unsigned grid = (unsigned)((warps + Cfg::WARPS - 1) / Cfg::WARPS);
-    return launch(sense_rows_fwd_kernel<RX>, dim3(grid), dim3(32 * Cfg::WARPS), Cfg::SMEM, s,
-                  x, maps, tmp, d, tchunk, nchunks);
+    const RowPlan plan = make_row_plan(d, d.E);
+    const unsigned grid = (unsigned)((long long)d.B * d.Y * plan.nchunks);
+    const size_t smem = Cfg::smem_bytes(d.E, plan.cgroup, false);
+    if (d.E == 1)
+        return launch(sense_rows_fwd_kernel<RX, 1>, dim3(grid), dim3(32 * Cfg::WARPS), smem, s, x, maps, tmp, d, plan);
+    if (d.E == 2)
+        return launch(sense_rows_fwd_kernel<RX, 2>, dim3(grid), dim3(32 * Cfg::WARPS), smem, s, x, maps, tmp, d, plan);
+    return launch(sense_rows_fwd_kernel<RX, 0>, dim3(grid), dim3(32 * Cfg::WARPS), smem, s, x, maps, tmp, d, plan);
 }
 
 int rows_fwd(const Problem& p, const float2* x, const float2* maps, const float* w, float2* k,
@@ -74,16 +93,11 @@ template <int RX, int EMAX>
 int launch_rows_adj(const float2* maps, float2* out, const float2* xin, const float2* aty,
                     const Problem& p, const SenseDims& d, int e0) {
     using Cfg = RowCfg<RX>;
-    const long long base = (long long)d.B * d.Y;
-    long long want = (kTargetWarps + base - 1) / base;
-    if (want < 1) want = 1;
-    if (want > d.t_count) want = d.t_count;
-    const int tchunk = (int)((d.t_count + want - 1) / want);
-    const int nchunks = (d.t_count + tchunk - 1) / tchunk;
-    const long long warps = base * nchunks;
-    const unsigned grid = (unsigned)((warps + Cfg::WARPS - 1) / Cfg::WARPS);
-    return launch(sense_rows_adj_kernel<RX, EMAX>, dim3(grid), dim3(32 * Cfg::WARPS), Cfg::SMEM, p.stream,
-                  (const float2*)p.tmp, maps, out, xin, aty, p.step, p.step_dev, p.epi, d, tchunk, nchunks, e0);
+    const RowPlan plan = make_row_plan(d, EMAX);
+    const unsigned grid = (unsigned)((long long)d.B * d.Y * plan.nchunks);
+    const size_t smem = Cfg::smem_bytes(EMAX, plan.cgroup, true);
+    return launch(sense_rows_adj_kernel<RX, EMAX>, dim3(grid), dim3(32 * Cfg::WARPS), smem, p.stream,
+                  (const float2*)p.tmp, maps, out, xin, aty, p.step, p.step_dev, p.epi, d, plan, e0);
 }
 
 template <int RX>
@@ -121,7 +135,7 @@ int rows_adj(const Problem& p, const float2* src_k, const float2* maps, const fl
 template <int RY, int MODE>
 int launch_cols(const float2* src, float2* dst, const float* w, const Problem& p, const SenseDims& d, float scale) {
     using Cfg = ColCfg<RY>;
-    const long long base = (long long)(d.X / 32) * d.t_count * d.B;
+    const long long base = (long long)(d.X / Cfg::SW) * d.t_count * d.B;
     long long want = (kTargetColCtas + base - 1) / base;
     if (want < 1) want = 1;
     if (want > d.C) want = d.C;

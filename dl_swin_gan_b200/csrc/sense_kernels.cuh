@@ -31,6 +31,20 @@
 #include "cuda_compat.h"
 #include "fft_radix.cuh"
 
+// Occupancy knobs (resident CTAs per SM the register allocator must allow); tuned on the B200, see DESIGN.md.
+#ifndef DLSG_ROWS_MINB
+#define DLSG_ROWS_MINB 3
+#endif
+#ifndef DLSG_COLS_TARGET_THREADS
+#define DLSG_COLS_TARGET_THREADS 448
+#endif
+// DLSG_PIN_LOADS: keep the compiler from hoisting the next batch's global loads above the radix-32 phase
+#ifdef DLSG_PIN_LOADS
+#define DLSG_LOAD_FENCE() asm volatile("" ::: "memory")
+#else
+#define DLSG_LOAD_FENCE() ((void)0)
+#endif
+
 namespace dlsg {
 
 struct SenseDims {
@@ -60,6 +74,15 @@ DLSG_DEVICE float load_w(const float* w, const WeightStrides& ws, int b, int c, 
 
 // ============================================================================
 // Row pass (axis X), fast path: X = 32*RX.
+//
+// One CTA (4 warps) owns (slice b, image row y, a chunk of frames).  The coil-sensitivity
+// rows maps[b, :, c-group, y, :] are staged once per CTA in shared memory (cp.async) and
+// reused for every frame.  Each warp owns a contiguous sub-range of frames and walks the
+// flattened (frame, coil) items, coil fastest, in batches of NB = 32/RX rows, so that the
+// radix-32 stage has one transform per lane:
+//   phase A  lane = x mod 32: radix-RX DFT over x = lane + 32 j, twiddle, to view 1
+//   phase B  lane = (row, k2): radix-32 DFT over the 32 lanes' values, to view 2 (natural kx order)
+//   phase C  coalesced copy-out (forward) / conj-map multiply-accumulate over coils (adjoint)
 // ============================================================================
 template <int RX>
 struct RowCfg {
@@ -69,8 +92,12 @@ struct RowCfg {
     static constexpr int S2 = 33 * RX;          // view 2: [row][x] natural order, stride = RX mod 16
     static constexpr int BUF = 32 * 34;         // complex elements of smem per warp
     static constexpr int WARPS = 4;
-    static constexpr size_t SMEM = (size_t)WARPS * BUF * sizeof(float2);
+    static size_t smem_bytes(int E, int cgroup, bool staging) {
+        return ((size_t)WARPS * (BUF + (staging ? NB * X : 0)) + (size_t)E * cgroup * X) * sizeof(float2);
+    }
 };
+
+struct RowPlan { int tchunk, nchunks, cgroup; };
 
 // lane twiddles exp(DIR*2*pi*i*lane*k2/X), k2 = 0..RX-1
 template <int RX, int DIR>
@@ -85,7 +112,7 @@ DLSG_DEVICE void lane_twiddles(int lane, float2* tw) {
     }
 }
 
-// Phases B of the row pass: radix-32 across the batch, view 1 -> view 2.
+// Phase B of the row pass: radix-32 across the batch, view 1 -> view 2.
 template <int RX, int DIR>
 DLSG_DEVICE void row_radix32(float2* buf, int lane, int nrows) {
     using Cfg = RowCfg<RX>;
@@ -111,64 +138,123 @@ DLSG_DEVICE void row_radix32(float2* buf, int lane, int nrows) {
     __syncwarp();
 }
 
-// Forward rows:  tmp[b,c,t,y,:] = DFT_X( sum_e maps[b,e,c,y,:] * x[b,e,t,y,:] )   (unnormalised)
-// One warp owns (b, y, frame-chunk) and walks the flattened (t, c) items, c fastest.
+// Stage maps[b, 0..E, cg0..cg0+cgn, y, :] into shared memory as [e][cl][X]; all threads of the CTA call it.
 template <int RX>
-DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(128)
+DLSG_DEVICE void stage_maps(float2* ms, const float2* __restrict__ maps, const SenseDims& d,
+                            int b, int y, int cg0, int cgn, int cgroup) {
+    constexpr int X = 32 * RX;
+    constexpr int CH = X / 2;                    // 16-byte chunks per row
+    const int total = d.E * cgn * CH;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int ch = i % CH, rc = i / CH;
+        const int cl = rc % cgn, e = rc / cgn;
+        cp_async16(ms + ((size_t)(e * cgroup + cl) * X + 2 * ch),
+                   maps + idx_maps(d, b, e, cg0 + cl, y) + 2 * ch);
+    }
+    cp_async_wait_all();
+}
+
+// Forward rows:  tmp[b,c,t,y,:] = DFT_X( sum_e maps[b,e,c,y,:] * x[b,e,t,y,:] )   (unnormalised)
+// EREG: number of map sets whose x row is cached in registers (1 or 2); 0 = any E, x re-read per row.
+template <int RX, int EREG>
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(128, DLSG_ROWS_MINB)
 sense_rows_fwd_kernel(const float2* __restrict__ x, const float2* __restrict__ maps,
-                      float2* __restrict__ tmp, SenseDims d, int tchunk, int nchunks) {
+                      float2* __restrict__ tmp, SenseDims d, RowPlan plan) {
     using Cfg = RowCfg<RX>;
+    constexpr int X = Cfg::X, NB = Cfg::NB;
     DLSG_DYN_SMEM(float2, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* buf = smem + warp * Cfg::BUF;
-    const long long unit = (long long)blockIdx.x * Cfg::WARPS + warp;
-    const long long total = (long long)d.B * d.Y * nchunks;
-    if (unit >= total) return;                  // whole warp leaves; only __syncwarp is used below
-    const int chunk = (int)(unit % nchunks);
-    const long long by = unit / nchunks;
-    const int y = (int)(by % d.Y), b = (int)(by / d.Y);
-    const int t0 = d.t_begin + chunk * tchunk;
-    const int t1 = min(d.t_begin + d.t_count, t0 + tchunk);
-    const int nitems = (t1 - t0) * d.C;
+    float2* ms = smem + Cfg::WARPS * Cfg::BUF;   // [e][cl][X]
+    long long unit = blockIdx.x;
+    const int chunk = (int)(unit % plan.nchunks); unit /= plan.nchunks;
+    const int y = (int)(unit % d.Y), b = (int)(unit / d.Y);
+    const int t0 = d.t_begin + chunk * plan.tchunk;
+    const int t1 = min(d.t_begin + d.t_count, t0 + plan.tchunk);
+    const int per_warp = (t1 - t0 + Cfg::WARPS - 1) / Cfg::WARPS;
+    const int tw0 = min(t1, t0 + warp * per_warp), tw1 = min(t1, tw0 + per_warp);
 
     float2 tw[RX];
     lane_twiddles<RX, -1>(lane, tw);
+    constexpr int ER = EREG > 0 ? EREG : 1;
+    float2 xr[ER][RX], xn[ER][RX];
 
-    for (int it0 = 0; it0 < nitems; it0 += Cfg::NB) {
-        const int nrows = min(Cfg::NB, nitems - it0);
-        for (int r = 0; r < nrows; ++r) {
-            const int item = it0 + r;
-            const int t = t0 + item / d.C, c = item % d.C;
-            float2 v[RX];
+    auto load_x = [&](float2 (&dst)[ER][RX], int t) {
 #pragma unroll
-            for (int j = 0; j < RX; ++j) v[j] = make_float2(0.f, 0.f);
-            for (int e = 0; e < d.E; ++e) {
-                const float2* xs = x + idx_x(d, b, e, t, y) + lane;
-                if (maps) {
-                    const float2* ms = maps + idx_maps(d, b, e, c, y) + lane;
+        for (int e = 0; e < ER; ++e) {
+            const float2* xs = x + idx_x(d, b, e, t, y) + lane;
 #pragma unroll
-                    for (int j = 0; j < RX; ++j) v[j] = cfma(__ldg(ms + 32 * j), __ldg(xs + 32 * j), v[j]);
-                } else {                         // maps == NULL: unit sensitivities (plain FFT entry point)
+            for (int j = 0; j < RX; ++j) dst[e][j] = __ldg(xs + 32 * j);
+        }
+    };
+
+    for (int cg0 = 0; cg0 < d.C; cg0 += plan.cgroup) {
+        const int cgn = min(plan.cgroup, d.C - cg0);
+        if (maps) {
+            __syncthreads();                     // previous group's rows are no longer read
+            stage_maps<RX>(ms, maps, d, b, y, cg0, cgn, plan.cgroup);
+            __syncthreads();
+        }
+        const int nitems = (tw1 - tw0) * cgn;
+        int cur_t = -1;
+        if (EREG > 0 && nitems > 0) load_x(xn, tw0);
+        for (int it0 = 0; it0 < nitems; it0 += NB) {
+            const int nrows = min(NB, nitems - it0);
+            int tl = it0 / cgn, cl = it0 - tl * cgn;
+            for (int r = 0; r < nrows; ++r) {
+                const int t = tw0 + tl;
+                if (EREG > 0 && t != cur_t) {    // new frame: take the prefetched row, prefetch the next one
 #pragma unroll
-                    for (int j = 0; j < RX; ++j) v[j] = cadd(v[j], __ldg(xs + 32 * j));
+                    for (int e = 0; e < ER; ++e)
+#pragma unroll
+                        for (int j = 0; j < RX; ++j) xr[e][j] = xn[e][j];
+                    cur_t = t;
+                    if (t + 1 < tw1) load_x(xn, t + 1);
                 }
+                float2 v[RX];
+#pragma unroll
+                for (int j = 0; j < RX; ++j) v[j] = make_float2(0.f, 0.f);
+                if (EREG > 0) {
+#pragma unroll
+                    for (int e = 0; e < ER; ++e) {
+                        if (maps) {
+                            const float2* m = ms + (size_t)(e * plan.cgroup + cl) * X + lane;
+#pragma unroll
+                            for (int j = 0; j < RX; ++j) v[j] = cfma(m[32 * j], xr[e][j], v[j]);
+                        } else {                 // maps == NULL: unit sensitivities (plain FFT entry point)
+#pragma unroll
+                            for (int j = 0; j < RX; ++j) v[j] = cadd(v[j], xr[e][j]);
+                        }
+                    }
+                } else {
+                    for (int e = 0; e < d.E; ++e) {
+                        const float2* xs = x + idx_x(d, b, e, t, y) + lane;
+                        const float2* m = ms + (size_t)(e * plan.cgroup + cl) * X + lane;
+#pragma unroll
+                        for (int j = 0; j < RX; ++j) {
+                            const float2 xv = __ldg(xs + 32 * j);
+                            v[j] = maps ? cfma(m[32 * j], xv, v[j]) : cadd(v[j], xv);
+                        }
+                    }
+                }
+                Dft<RX, -1>::run(v);
+                float2* o = buf + (r * RX) * Cfg::S1 + lane;
+#pragma unroll
+                for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmul(v[k2], tw[k2]);
+                if (++cl == cgn) { cl = 0; ++tl; }
             }
-            Dft<RX, -1>::run(v);
-            float2* o = buf + (r * RX) * Cfg::S1 + lane;
+            __syncwarp();
+            row_radix32<RX, -1>(buf, lane, nrows);
+            tl = it0 / cgn; cl = it0 - tl * cgn;
+            for (int r = 0; r < nrows; ++r) {
+                float2* dst = tmp + idx_tmp(d, b, cg0 + cl, tw0 + tl, y) + lane;
+                const float2* sv = buf + r * Cfg::S2 + lane;
 #pragma unroll
-            for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmul(v[k2], tw[k2]);
+                for (int j = 0; j < RX; ++j) dst[32 * j] = sv[32 * j];
+                if (++cl == cgn) { cl = 0; ++tl; }
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        row_radix32<RX, -1>(buf, lane, nrows);
-        for (int r = 0; r < nrows; ++r) {
-            const int item = it0 + r;
-            const int t = t0 + item / d.C, c = item % d.C;
-            float2* dst = tmp + idx_tmp(d, b, c, t, y) + lane;
-            const float2* s = buf + r * Cfg::S2 + lane;
-#pragma unroll
-            for (int j = 0; j < RX; ++j) dst[32 * j] = s[32 * j];
-        }
-        __syncwarp();
     }
 }
 
@@ -176,25 +262,27 @@ sense_rows_fwd_kernel(const float2* __restrict__ x, const float2* __restrict__ m
 //   EPI_PLAIN: out = acc
 //   EPI_DC   : out = xin + step * (acc - aty)          (unrolledswin.py:109)
 // EMAX accumulators live in registers; E > EMAX is handled by e-groups (e0 .. e0+EMAX).
+// With several coil groups the partial sums go through `out` (each element is owned by one lane).
 template <int RX, int EMAX>
-DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(128)
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(128, DLSG_ROWS_MINB)
 sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__ maps,
-                      float2* __restrict__ out, const float2* __restrict__ xin,
+                      float2* out, const float2* __restrict__ xin,
                       const float2* __restrict__ aty, float step_host, const float* __restrict__ step_dev,
-                      int epi, SenseDims d, int tchunk, int nchunks, int e0) {
+                      int epi, SenseDims d, RowPlan plan, int e0) {
     using Cfg = RowCfg<RX>;
+    constexpr int X = Cfg::X, NB = Cfg::NB;
     DLSG_DYN_SMEM(float2, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* buf = smem + warp * Cfg::BUF;
-    const long long unit = (long long)blockIdx.x * Cfg::WARPS + warp;
-    const long long total = (long long)d.B * d.Y * nchunks;
-    if (unit >= total) return;
-    const int chunk = (int)(unit % nchunks);
-    const long long by = unit / nchunks;
-    const int y = (int)(by % d.Y), b = (int)(by / d.Y);
-    const int t0 = d.t_begin + chunk * tchunk;
-    const int t1 = min(d.t_begin + d.t_count, t0 + tchunk);
-    const int nitems = (t1 - t0) * d.C;
+    float2* stg = smem + Cfg::WARPS * Cfg::BUF + warp * (NB * X);     // [r][X] raw rows of the next batch
+    float2* ms = smem + Cfg::WARPS * (Cfg::BUF + NB * X);             // [e][cl][X], e relative to e0
+    long long unit = blockIdx.x;
+    const int chunk = (int)(unit % plan.nchunks); unit /= plan.nchunks;
+    const int y = (int)(unit % d.Y), b = (int)(unit / d.Y);
+    const int t0 = d.t_begin + chunk * plan.tchunk;
+    const int t1 = min(d.t_begin + d.t_count, t0 + plan.tchunk);
+    const int per_warp = (t1 - t0 + Cfg::WARPS - 1) / Cfg::WARPS;
+    const int tw0 = min(t1, t0 + warp * per_warp), tw1 = min(t1, tw0 + per_warp);
     const int ne = min(EMAX, d.E - e0);
     const float step = step_dev ? __ldg(step_dev) : step_host;
 
@@ -206,68 +294,113 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
     for (int e = 0; e < EMAX; ++e)
 #pragma unroll
         for (int j = 0; j < RX; ++j) acc[e][j] = make_float2(0.f, 0.f);
-    int cur_t = t0;
 
-    auto flush = [&](int t) {
-#pragma unroll
-        for (int e = 0; e < EMAX; ++e) {
-            if (e < ne) {
-                const size_t base = idx_x(d, b, e0 + e, t, y) + lane;
-#pragma unroll
-                for (int j = 0; j < RX; ++j) {
-                    float2 r = acc[e][j];
-                    if (epi == EPI_DC) {
-                        const float2 xv = __ldg(xin + base + 32 * j), av = __ldg(aty + base + 32 * j);
-                        r = make_float2(fmaf(step, r.x - av.x, xv.x), fmaf(step, r.y - av.y, xv.y));
-                    }
-                    out[base + 32 * j] = r;
-                    acc[e][j] = make_float2(0.f, 0.f);
-                }
+    for (int cg0 = 0; cg0 < d.C; cg0 += plan.cgroup) {
+        const int cgn = min(plan.cgroup, d.C - cg0);
+        const bool first_group = (cg0 == 0), last_group = (cg0 + cgn >= d.C);
+        if (maps) {
+            __syncthreads();
+            SenseDims de = d;                    // stage only this kernel's map sets: shift e by e0
+            constexpr int CH = X / 2;
+            const int total = ne * cgn * CH;
+            for (int i = threadIdx.x; i < total; i += blockDim.x) {
+                const int ch = i % CH, rc = i / CH;
+                const int cl = rc % cgn, e = rc / cgn;
+                cp_async16(ms + ((size_t)(e * plan.cgroup + cl) * X + 2 * ch),
+                           maps + idx_maps(de, b, e0 + e, cg0 + cl, y) + 2 * ch);
             }
+            cp_async_wait_all();
+            __syncthreads();
         }
-    };
 
-    for (int it0 = 0; it0 < nitems; it0 += Cfg::NB) {
-        const int nrows = min(Cfg::NB, nitems - it0);
-        for (int r = 0; r < nrows; ++r) {
-            const int item = it0 + r;
-            const int t = t0 + item / d.C, c = item % d.C;
-            const float2* src = tmp + idx_tmp(d, b, c, t, y) + lane;
-            float2 v[RX];
-#pragma unroll
-            for (int j = 0; j < RX; ++j) v[j] = __ldg(src + 32 * j);
-            Dft<RX, +1>::run(v);
-            float2* o = buf + (r * RX) * Cfg::S1 + lane;
-#pragma unroll
-            for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmul(v[k2], tw[k2]);
-        }
-        __syncwarp();
-        row_radix32<RX, +1>(buf, lane, nrows);
-        for (int r = 0; r < nrows; ++r) {
-            const int item = it0 + r;
-            const int t = t0 + item / d.C, c = item % d.C;
-            if (t != cur_t) { flush(cur_t); cur_t = t; }
-            const float2* s = buf + r * Cfg::S2 + lane;
-            float2 v[RX];
-#pragma unroll
-            for (int j = 0; j < RX; ++j) v[j] = s[32 * j];
+        auto flush = [&](int t) {
 #pragma unroll
             for (int e = 0; e < EMAX; ++e) {
                 if (e < ne) {
-                    if (maps) {
-                        const float2* ms = maps + idx_maps(d, b, e0 + e, c, y) + lane;
+                    const size_t base = idx_x(d, b, e0 + e, t, y) + lane;
 #pragma unroll
-                        for (int j = 0; j < RX; ++j) acc[e][j] = cfmac(v[j], __ldg(ms + 32 * j), acc[e][j]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < RX; ++j) acc[e][j] = cadd(acc[e][j], v[j]);
+                    for (int j = 0; j < RX; ++j) {
+                        float2 r = acc[e][j];
+                        if (!first_group) r = cadd(r, out[base + 32 * j]);
+                        if (last_group && epi == EPI_DC) {
+                            const float2 xv = __ldg(xin + base + 32 * j), av = __ldg(aty + base + 32 * j);
+                            r = make_float2(fmaf(step, r.x - av.x, xv.x), fmaf(step, r.y - av.y, xv.y));
+                        }
+                        out[base + 32 * j] = r;
+                        acc[e][j] = make_float2(0.f, 0.f);
                     }
                 }
             }
+        };
+
+        const int nitems = (tw1 - tw0) * cgn;
+        int cur_t = tw0;
+        // asynchronous staging of one batch of tmp rows (natural order, [r][X]) into this warp's buffer
+        auto stage_batch = [&](int it0) {
+            const int nrows = min(NB, nitems - it0);
+            int tl = it0 / cgn, cl = it0 - tl * cgn;
+            for (int r = 0; r < nrows; ++r) {
+                const float2* src = tmp + idx_tmp(d, b, cg0 + cl, tw0 + tl, y);
+                float2* dstp = stg + r * X;
+                for (int q = lane; q < X / 2; q += 32) cp_async16(dstp + 2 * q, src + 2 * q);
+                if (++cl == cgn) { cl = 0; ++tl; }
+            }
+            cp_async_commit();
+        };
+        if (nitems > 0) stage_batch(0);
+        for (int it0 = 0; it0 < nitems; it0 += NB) {
+            const int nrows = min(NB, nitems - it0);
+            const int tl0 = it0 / cgn, cl0 = it0 - tl0 * cgn;
+            cp_async_wait_group0();
+            __syncwarp();
+            float2 in[NB][RX];
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {
+                if (r < nrows) {
+#pragma unroll
+                    for (int j = 0; j < RX; ++j) in[r][j] = stg[r * X + lane + 32 * j];
+                }
+            }
+            __syncwarp();                        // staging buffer is free again
+            if (it0 + NB < nitems) stage_batch(it0 + NB);
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {
+                if (r < nrows) {
+                    Dft<RX, +1>::run(in[r]);
+                    float2* o = buf + (r * RX) * Cfg::S1 + lane;
+#pragma unroll
+                    for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? in[r][0] : cmul(in[r][k2], tw[k2]);
+                }
+            }
+            __syncwarp();
+            row_radix32<RX, +1>(buf, lane, nrows);
+            int tl = tl0, cl = cl0;
+            for (int r = 0; r < nrows; ++r) {
+                const int t = tw0 + tl;
+                if (t != cur_t) { flush(cur_t); cur_t = t; }
+                const float2* sv = buf + r * Cfg::S2 + lane;
+                float2 v[RX];
+#pragma unroll
+                for (int j = 0; j < RX; ++j) v[j] = sv[32 * j];
+#pragma unroll
+                for (int e = 0; e < EMAX; ++e) {
+                    if (e < ne) {
+                        if (maps) {
+                            const float2* m = ms + (size_t)(e * plan.cgroup + cl) * X + lane;
+#pragma unroll
+                            for (int j = 0; j < RX; ++j) acc[e][j] = cfmac(v[j], m[32 * j], acc[e][j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < RX; ++j) acc[e][j] = cadd(acc[e][j], v[j]);
+                        }
+                    }
+                }
+                if (++cl == cgn) { cl = 0; ++tl; }
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        if (nitems > 0) flush(cur_t);
     }
-    if (nitems > 0) flush(cur_t);
 }
 
 // ============================================================================
@@ -279,92 +412,113 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
 template <int RY>
 struct ColCfg {
     static constexpr int Y = 32 * RY;
-    static constexpr int NT = 32 * RY;          // threads per CTA = radix-32 transforms per slab
-    static constexpr size_t SMEM = (size_t)(Y * 32 + Y) * sizeof(float2);   // slab + twiddle table
+    static constexpr int SW = (RY <= 6) ? 32 : 16;      // slab width in columns
+    static constexpr int NT = SW * RY;                  // threads per CTA = radix-32 transforms per slab
+    static constexpr int ITEMS = (32 + RY - 1) / RY;    // phase-A (l, column) items per thread
+    static constexpr int MINB = (DLSG_COLS_TARGET_THREADS / NT) > 0 ? (DLSG_COLS_TARGET_THREADS / NT) : 1;
+    static constexpr size_t SMEM = (size_t)(2 * Y * SW + Y) * sizeof(float2);   // two slabs + twiddle table
 };
 
+// One CTA owns an SW-column slab of the images (b, c0..c1, t).  The raw slab of the next coil is
+// fetched with cp.async while the current one is transformed; phase A works in place on the slab.
 template <int RY, int MODE>
-DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(32 * RY)
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(ColCfg<RY>::NT, ColCfg<RY>::MINB)
 sense_cols_kernel(const float2* __restrict__ src, float2* __restrict__ dst,
                   const float* __restrict__ w, WeightStrides ws, float scale,
                   SenseDims d, int cchunk, int ncchunks) {
     using Cfg = ColCfg<RY>;
     constexpr int DIR = (MODE == MODE_ADJ) ? +1 : -1;
+    constexpr int ITEMS = Cfg::ITEMS, NT = Cfg::NT, SW = Cfg::SW, Y = Cfg::Y;
     DLSG_DYN_SMEM(float2, smem);
-    float2* slab = smem;                         // [k2*32 + l][col]
-    float2* twy = smem + Cfg::Y * 32;            // [l*RY + k2] = exp(-2*pi*i*l*k2/Y)  (forward sign)
-    const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;   // grp = k2 of this thread's radix-32
+    float2* twy = smem + 2 * Y * SW;             // [l*RY + k2] = exp(-2*pi*i*l*k2/Y)  (forward sign)
+    const int tid = threadIdx.x, col = tid % SW, grp = tid / SW;   // grp = k2 of this thread's radix-32
 
-    const int ncolblk = d.X / 32;
+    const int ncolblk = d.X / SW;
     long long u = blockIdx.x;
     const int colblk = (int)(u % ncolblk); u /= ncolblk;
     const int cc = (int)(u % ncchunks); u /= ncchunks;
     const int tl = (int)(u % d.t_count);
     const int b = (int)(u / d.t_count);
     const int t = d.t_begin + tl;
-    const int kx = colblk * 32 + lane;
+    const int kx0 = colblk * SW, kx = kx0 + col;
     const int c0 = cc * cchunk, c1 = min(d.C, c0 + cchunk);
+    const int Xs = d.X;
 
-    for (int i = tid; i < Cfg::Y; i += Cfg::NT) {
+    auto prefetch = [&](int c, float2* slab) {
+        const float2* in = src + ((MODE == MODE_ADJ) ? idx_k(d, b, c, t, 0) : idx_tmp(d, b, c, t, 0)) + kx0;
+        for (int q = tid; q < Y * (SW / 2); q += NT) {
+            const int yy = q / (SW / 2), ch = q - yy * (SW / 2);
+            cp_async16(slab + yy * SW + 2 * ch, in + (size_t)yy * Xs + 2 * ch);
+        }
+        cp_async_commit();
+    };
+
+    if (c0 < c1) prefetch(c0, smem);
+    for (int i = tid; i < Y; i += NT) {
         const int l = i / RY, k2 = i - l * RY;
-        int m = (l * k2) % Cfg::Y;
-        if (2 * m > Cfg::Y) m -= Cfg::Y;
-        float s, c;
-        sincospif((float)(2 * m) / (float)Cfg::Y, &s, &c);
-        twy[i] = make_float2(c, -s);
+        int m = (l * k2) % Y;
+        if (2 * m > Y) m -= Y;
+        float sn, cs;
+        sincospif((float)(2 * m) / (float)Y, &sn, &cs);
+        twy[i] = make_float2(cs, -sn);
     }
-    __syncthreads();
 
     for (int c = c0; c < c1; ++c) {
-        const size_t img_in = (MODE == MODE_ADJ) ? idx_k(d, b, c, t, 0) : idx_tmp(d, b, c, t, 0);
-        const size_t img_out = (MODE == MODE_FWD) ? idx_k(d, b, c, t, 0) : idx_tmp(d, b, c, t, 0);
-        // ---- phase A: radix-RY over y = l + 32*j, twiddle, to the slab
-        for (int it = tid; it < 1024; it += Cfg::NT) {
-            const int l = it >> 5;               // lane == it & 31 because NT is a multiple of 32
-            float2 v[RY];
+        float2* slab = smem + ((c - c0) & 1) * (Y * SW);          // [k2*32 + l][col] after phase A
+        float2* other = smem + (((c - c0) & 1) ^ 1) * (Y * SW);
+        float2* outp = dst + ((MODE == MODE_FWD) ? idx_k(d, b, c, t, 0) : idx_tmp(d, b, c, t, 0)) + kx;
+        const float* wp = w ? w + (b * ws.b + c * ws.c + t * ws.t + kx * ws.x) : nullptr;
+        cp_async_wait_group0();
+        __syncthreads();                         // this coil's slab has landed; the other slab is no longer read
+        if (c + 1 < c1) prefetch(c + 1, other);
+        // ---- phase A (in place): radix-RY over y = l + 32*j, twiddle
 #pragma unroll
-            for (int j = 0; j < RY; ++j) {
-                const int yy = l + 32 * j;
-                float2 a = __ldg(src + img_in + (size_t)yy * d.X + kx);
-                if (MODE == MODE_ADJ) a = cscale(a, scale * load_w(w, ws, b, c, t, yy, kx));
-                v[j] = a;
-            }
-            Dft<RY, DIR>::run(v);
+        for (int i = 0; i < ITEMS; ++i) {
+            const int l = grp + i * RY;          // item = tid + i*NT  ->  l = item / SW
+            if (l < 32) {
+                float2 v[RY];
 #pragma unroll
-            for (int k2 = 0; k2 < RY; ++k2) {
-                float2 q = v[k2];
-                if (k2 > 0) {
-                    const float2 tq = twy[l * RY + k2];
-                    q = (DIR < 0) ? cmul(q, tq) : cmulc(q, tq);
+                for (int j = 0; j < RY; ++j) {
+                    const int yy = l + 32 * j;
+                    float2 a = slab[yy * SW + col];
+                    if (MODE == MODE_ADJ) a = cscale(a, wp ? scale * __ldg(wp + yy * ws.y) : scale);
+                    v[j] = a;
                 }
-                slab[(k2 * 32 + l) * 32 + lane] = q;
+                Dft<RY, DIR>::run(v);
+#pragma unroll
+                for (int k2 = 0; k2 < RY; ++k2) {
+                    float2 q = v[k2];
+                    if (k2 > 0) {
+                        const float2 tq = twy[l * RY + k2];
+                        q = (DIR < 0) ? cmul(q, tq) : cmulc(q, tq);
+                    }
+                    slab[(k2 * 32 + l) * SW + col] = q;
+                }
             }
         }
         __syncthreads();
-        // ---- phase B: radix-32 over l for (k2 = grp, column = lane); ky = RY*k1 + k2
+        // ---- phase B: radix-32 over l for (k2 = grp, column = col); ky = RY*k1 + k2
         float2 r[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = slab[(grp * 32 + i) * 32 + lane];
+        for (int i = 0; i < 32; ++i) r[i] = slab[(grp * 32 + i) * SW + col];
         Dft<32, DIR>::run(r);
         if (MODE == MODE_FWD) {
 #pragma unroll
             for (int k1 = 0; k1 < 32; ++k1) {
                 const int ky = RY * k1 + grp;
-                const float wv = scale * load_w(w, ws, b, c, t, ky, kx);
-                dst[img_out + (size_t)ky * d.X + kx] = cscale(r[k1], wv);
+                const float wv = wp ? scale * __ldg(wp + ky * ws.y) : scale;
+                outp[ky * Xs] = cscale(r[k1], wv);
             }
-            __syncthreads();                     // slab is rewritten by the next coil
         } else if (MODE == MODE_ADJ) {
 #pragma unroll
-            for (int k1 = 0; k1 < 32; ++k1) dst[img_out + (size_t)(RY * k1 + grp) * d.X + kx] = r[k1];
-            __syncthreads();
+            for (int k1 = 0; k1 < 32; ++k1) outp[(RY * k1 + grp) * Xs] = r[k1];
         } else {
             // weights squared, then the way back with the "32-first" split:
             // thread holds ky = RY*n1 + n2 (n2 = grp): radix-32 over n1 -> k1', twiddle
             // exp(+2*pi*i*n2*k1'/Y), exchange, radix-RY over n2 -> y = k1' + 32*k2'.
 #pragma unroll
             for (int k1 = 0; k1 < 32; ++k1) {
-                const float wv = scale * load_w(w, ws, b, c, t, RY * k1 + grp, kx);
+                const float wv = wp ? scale * __ldg(wp + (RY * k1 + grp) * ws.y) : scale;
                 r[k1] = cscale(r[k1], wv * wv);
             }
             Dft<32, +1>::run(r);
@@ -373,19 +527,21 @@ sense_cols_kernel(const float2* __restrict__ src, float2* __restrict__ dst,
             for (int k1 = 0; k1 < 32; ++k1) {
                 float2 q = r[k1];
                 if (grp > 0) q = cmulc(q, twy[k1 * RY + grp]);
-                slab[(grp * 32 + k1) * 32 + lane] = q;
+                slab[(grp * 32 + k1) * SW + col] = q;
             }
             __syncthreads();
-            for (int it = tid; it < 1024; it += Cfg::NT) {
-                const int k1 = it >> 5;
-                float2 g[RY];
 #pragma unroll
-                for (int n2 = 0; n2 < RY; ++n2) g[n2] = slab[(n2 * 32 + k1) * 32 + lane];
-                Dft<RY, +1>::run(g);
+            for (int i = 0; i < ITEMS; ++i) {
+                const int k1 = grp + i * RY;
+                if (k1 < 32) {
+                    float2 g[RY];
 #pragma unroll
-                for (int k2 = 0; k2 < RY; ++k2) dst[img_out + (size_t)(k1 + 32 * k2) * d.X + kx] = g[k2];
+                    for (int n2 = 0; n2 < RY; ++n2) g[n2] = slab[(n2 * 32 + k1) * SW + col];
+                    Dft<RY, +1>::run(g);
+#pragma unroll
+                    for (int k2 = 0; k2 < RY; ++k2) outp[(k1 + 32 * k2) * Xs] = g[k2];
+                }
             }
-            __syncthreads();
         }
     }
 }

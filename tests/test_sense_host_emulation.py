@@ -70,6 +70,8 @@ CASES = [
     ((1, 3, 2, 2, 32, 15, "full"), {}),
     ((2, 3, 2, 2, 64, 64, "full"), {"budget": 1}),          # one (slice, frame) per chunk, E > 2 groups
     ((1, 2, 2, 2, 1, 64, "mask"), {"ndims": 1}),
+    ((1, 2, 6, 2, 32, 320, "mask"), {}),                    # two coil groups: partial sums through `out`
+    ((1, 1, 3, 5, 32, 64, "full"), {}),                     # frame chunk shared by 4 warps, ragged batches
 ]
 
 

@@ -14,12 +14,13 @@ from dl_swin_gan_b200.mri import SenseModel
 dev = torch.device("cuda:0")
 cfg = dict(bench.WORKLOAD)
 cfg["B"] = int(os.environ.get("SWEEP_B", 64))
+cfg["E"] = int(os.environ.get("SWEEP_E", 1))
 maps, mask, y = bench.device_problem(cfg, dev, 1000)
 A = SenseModel(maps, weights=mask)
 x = A(y, adjoint=True)
 B, E, C, T, Y, X = (cfg[k] for k in "BECTYX")
 rows = []
-for mb in [8, 20, 40, 64, 80, 120, 200, 400, 8192]:
+for mb in [int(v) for v in os.environ.get("SWEEP_MB", "8,20,40,64,80,120,200,400,8192").split(",")]:
     os.environ["DLSG_WORKSPACE_MB"] = str(mb)
     r = {"workspace_MB": mb}
     with torch.no_grad():
