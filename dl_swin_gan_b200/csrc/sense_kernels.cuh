@@ -92,8 +92,9 @@ struct RowCfg {
     static constexpr int S2 = 33 * RX;          // view 2: [row][x] natural order, stride = RX mod 16
     static constexpr int BUF = 32 * 34;         // complex elements of smem per warp
     static constexpr int WARPS = 4;
+    // forward: exchange buffers + staged maps;  adjoint (staging): + raw-row staging and DC-row buffers per warp
     static size_t smem_bytes(int E, int cgroup, bool staging) {
-        return ((size_t)WARPS * (BUF + (staging ? NB * X : 0)) + (size_t)E * cgroup * X) * sizeof(float2);
+        return ((size_t)WARPS * (BUF + (staging ? NB * X + 2 * E * X : 0)) + (size_t)E * cgroup * X) * sizeof(float2);
     }
 };
 
@@ -275,7 +276,8 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* buf = smem + warp * Cfg::BUF;
     float2* stg = smem + Cfg::WARPS * Cfg::BUF + warp * (NB * X);     // [r][X] raw rows of the next batch
-    float2* ms = smem + Cfg::WARPS * (Cfg::BUF + NB * X);             // [e][cl][X], e relative to e0
+    float2* dcb = smem + Cfg::WARPS * (Cfg::BUF + NB * X) + warp * (2 * EMAX * X);   // [xin|aty][e][X] of the frame being summed
+    float2* ms = smem + Cfg::WARPS * (Cfg::BUF + NB * X + 2 * EMAX * X);             // [e][cl][X], e relative to e0
     long long unit = blockIdx.x;
     const int chunk = (int)(unit % plan.nchunks); unit /= plan.nchunks;
     const int y = (int)(unit % d.Y), b = (int)(unit / d.Y);
@@ -313,7 +315,22 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
             __syncthreads();
         }
 
+        // x and A^H y rows of frame t for the DC epilogue, fetched asynchronously when the frame is started
+        auto stage_dc = [&](int t) {
+            if (last_group && epi == EPI_DC) {
+                __syncwarp();                    // the previous frame's epilogue has read the buffer
+                for (int e = 0; e < ne; ++e) {
+                    const size_t base = idx_x(d, b, e0 + e, t, y);
+                    for (int q = lane; q < X / 2; q += 32) {
+                        cp_async16(dcb + e * X + 2 * q, xin + base + 2 * q);
+                        cp_async16(dcb + (EMAX + e) * X + 2 * q, aty + base + 2 * q);
+                    }
+                }
+                cp_async_commit();
+            }
+        };
         auto flush = [&](int t) {
+            if (last_group && epi == EPI_DC) { cp_async_wait_group0(); __syncwarp(); }
 #pragma unroll
             for (int e = 0; e < EMAX; ++e) {
                 if (e < ne) {
@@ -323,7 +340,7 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
                         float2 r = acc[e][j];
                         if (!first_group) r = cadd(r, out[base + 32 * j]);
                         if (last_group && epi == EPI_DC) {
-                            const float2 xv = __ldg(xin + base + 32 * j), av = __ldg(aty + base + 32 * j);
+                            const float2 xv = dcb[e * X + lane + 32 * j], av = dcb[(EMAX + e) * X + lane + 32 * j];
                             r = make_float2(fmaf(step, r.x - av.x, xv.x), fmaf(step, r.y - av.y, xv.y));
                         }
                         out[base + 32 * j] = r;
@@ -347,37 +364,28 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
             }
             cp_async_commit();
         };
-        if (nitems > 0) stage_batch(0);
+        if (nitems > 0) { stage_dc(tw0); stage_batch(0); }
         for (int it0 = 0; it0 < nitems; it0 += NB) {
             const int nrows = min(NB, nitems - it0);
             const int tl0 = it0 / cgn, cl0 = it0 - tl0 * cgn;
             cp_async_wait_group0();
             __syncwarp();
-            float2 in[NB][RX];
+            for (int r = 0; r < nrows; ++r) {
+                float2 v[RX];
 #pragma unroll
-            for (int r = 0; r < NB; ++r) {
-                if (r < nrows) {
+                for (int j = 0; j < RX; ++j) v[j] = stg[r * X + lane + 32 * j];
+                Dft<RX, +1>::run(v);
+                float2* o = buf + (r * RX) * Cfg::S1 + lane;
 #pragma unroll
-                    for (int j = 0; j < RX; ++j) in[r][j] = stg[r * X + lane + 32 * j];
-                }
+                for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmul(v[k2], tw[k2]);
             }
-            __syncwarp();                        // staging buffer is free again
-            if (it0 + NB < nitems) stage_batch(it0 + NB);
-#pragma unroll
-            for (int r = 0; r < NB; ++r) {
-                if (r < nrows) {
-                    Dft<RX, +1>::run(in[r]);
-                    float2* o = buf + (r * RX) * Cfg::S1 + lane;
-#pragma unroll
-                    for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? in[r][0] : cmul(in[r][k2], tw[k2]);
-                }
-            }
-            __syncwarp();
+            __syncwarp();                        // staging buffer consumed, view 1 complete
+            if (it0 + NB < nitems) stage_batch(it0 + NB);   // lands while phases B and C run
             row_radix32<RX, +1>(buf, lane, nrows);
             int tl = tl0, cl = cl0;
             for (int r = 0; r < nrows; ++r) {
                 const int t = tw0 + tl;
-                if (t != cur_t) { flush(cur_t); cur_t = t; }
+                if (t != cur_t) { flush(cur_t); cur_t = t; stage_dc(t); }
                 const float2* sv = buf + r * Cfg::S2 + lane;
                 float2 v[RX];
 #pragma unroll
@@ -463,11 +471,37 @@ sense_cols_kernel(const float2* __restrict__ src, float2* __restrict__ dst,
         twy[i] = make_float2(cs, -sn);
     }
 
+    // k-space weights of this thread's elements live in registers: ADJ needs them at its phase-A elements
+    // (y = l + 32 j), FWD / NORMAL at its phase-B outputs (ky = RY k1 + grp).  Loaded before the wait on the
+    // slab so that the latency overlaps; only once per CTA when the weights are coil-broadcast (ws.c == 0).
+    constexpr int NW = (MODE == MODE_ADJ) ? ITEMS * RY : 32;
+    float wreg[NW];
+    auto load_weights = [&](int c) {
+        const float* wp = w + (b * ws.b + c * ws.c + t * ws.t + kx * ws.x);
+        if (MODE == MODE_ADJ) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const int l = grp + i * RY;
+#pragma unroll
+                for (int j = 0; j < RY; ++j) wreg[i * RY + j] = (l < 32) ? scale * __ldg(wp + (l + 32 * j) * ws.y) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) wreg[k1] = scale * __ldg(wp + (RY * k1 + grp) * ws.y);
+        }
+    };
+    if (!w) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) wreg[i] = scale;
+    } else if (ws.c == 0 && c0 < c1) {
+        load_weights(c0);
+    }
+
     for (int c = c0; c < c1; ++c) {
         float2* slab = smem + ((c - c0) & 1) * (Y * SW);          // [k2*32 + l][col] after phase A
         float2* other = smem + (((c - c0) & 1) ^ 1) * (Y * SW);
         float2* outp = dst + ((MODE == MODE_FWD) ? idx_k(d, b, c, t, 0) : idx_tmp(d, b, c, t, 0)) + kx;
-        const float* wp = w ? w + (b * ws.b + c * ws.c + t * ws.t + kx * ws.x) : nullptr;
+        if (w && ws.c != 0) load_weights(c);
         cp_async_wait_group0();
         __syncthreads();                         // this coil's slab has landed; the other slab is no longer read
         if (c + 1 < c1) prefetch(c + 1, other);
@@ -481,7 +515,7 @@ sense_cols_kernel(const float2* __restrict__ src, float2* __restrict__ dst,
                 for (int j = 0; j < RY; ++j) {
                     const int yy = l + 32 * j;
                     float2 a = slab[yy * SW + col];
-                    if (MODE == MODE_ADJ) a = cscale(a, wp ? scale * __ldg(wp + yy * ws.y) : scale);
+                    if (MODE == MODE_ADJ) a = cscale(a, wreg[i * RY + j]);
                     v[j] = a;
                 }
                 Dft<RY, DIR>::run(v);
@@ -505,9 +539,7 @@ sense_cols_kernel(const float2* __restrict__ src, float2* __restrict__ dst,
         if (MODE == MODE_FWD) {
 #pragma unroll
             for (int k1 = 0; k1 < 32; ++k1) {
-                const int ky = RY * k1 + grp;
-                const float wv = wp ? scale * __ldg(wp + ky * ws.y) : scale;
-                outp[ky * Xs] = cscale(r[k1], wv);
+                outp[(RY * k1 + grp) * Xs] = cscale(r[k1], wreg[k1]);
             }
         } else if (MODE == MODE_ADJ) {
 #pragma unroll
@@ -517,10 +549,7 @@ sense_cols_kernel(const float2* __restrict__ src, float2* __restrict__ dst,
             // thread holds ky = RY*n1 + n2 (n2 = grp): radix-32 over n1 -> k1', twiddle
             // exp(+2*pi*i*n2*k1'/Y), exchange, radix-RY over n2 -> y = k1' + 32*k2'.
 #pragma unroll
-            for (int k1 = 0; k1 < 32; ++k1) {
-                const float wv = wp ? scale * __ldg(wp + (RY * k1 + grp) * ws.y) : scale;
-                r[k1] = cscale(r[k1], wv * wv);
-            }
+            for (int k1 = 0; k1 < 32; ++k1) r[k1] = cscale(r[k1], wreg[k1] * wreg[k1]);
             Dft<32, +1>::run(r);
             __syncthreads();                     // every phase-B read of the slab is done
 #pragma unroll
