@@ -357,7 +357,7 @@ def main():
             "vs_baseline": None, "dtype": "f32 (complex64)", "data": "synthetic",
             "config": {"workload": "config_recon.yaml", **cfg, "slices_per_gpu": B,
                        "l2": "working set per step (y 2.5 GB + x/maps/mask) >> 126 MB L2, no flush needed",
-                       "workspace_MB": float(os.environ.get("DLSG_WORKSPACE_MB", 64))},
+                       "workspace_MB": float(os.environ.get("DLSG_WORKSPACE_MB", 4096))},
             "roofline": roofline, "ops": ops, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks.summary(),
         }

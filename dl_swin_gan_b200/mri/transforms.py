@@ -24,7 +24,7 @@ from torch import nn
 
 from .. import _lib
 
-_WORKSPACE_MB_DEFAULT = 64
+_WORKSPACE_MB_DEFAULT = 4096   # measured: an unchunked intermediate beats L2-sized chunks (profiles/r1a_workspace_sweep.log)
 
 
 def _workspace_budget() -> int:
