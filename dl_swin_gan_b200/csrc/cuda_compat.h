@@ -30,6 +30,24 @@ __device__ __forceinline__ void cp_async_wait_all() {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_group0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+#include <cuda_fp16.h>
+typedef __half half_t;
+// 2^x on the SFU (MUFU.EX2), flush-to-zero: exp2(-inf) = 0
+__device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ half_t f2h(float v) { return __float2half_rn(v); }
+// two floats -> packed fp16 pair (first argument in the low half)
+__device__ __forceinline__ unsigned pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const unsigned*>(&h);
+}
+__device__ __forceinline__ unsigned lds_u32(const half_t* p) { return *reinterpret_cast<const unsigned*>(p); }
+// D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col); fragment layouts per PTX ISA "mma.m16n8k16"
+__device__ __forceinline__ void mma_m16n8k16_f16(float* c, const unsigned* a, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 #include <atomic>
 namespace dlsg {
 using stream_t = cudaStream_t;
@@ -81,7 +99,8 @@ private:
     std::mutex m_;
     std::condition_variable cv_;
 };
-struct BlockCtx { Barrier* block_bar; std::vector<Barrier*> warp_bars; unsigned char* smem; };
+struct WarpScratch { unsigned a[32][4]; unsigned b[32][2]; float f[32]; };
+struct BlockCtx { Barrier* block_bar; std::vector<Barrier*> warp_bars; unsigned char* smem; WarpScratch* scratch; };
 extern thread_local dim3 t_threadIdx;
 extern thread_local dim3 t_blockIdx;
 extern thread_local BlockCtx* t_ctx;
@@ -99,6 +118,44 @@ static inline void sincospif(float a, float* s, float* c) {
     *s = (float)std::sin(pi * (double)a); *c = (float)std::cos(pi * (double)a);
 }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+typedef _Float16 half_t;
+static inline float fast_exp2(float x) { return std::exp2(x); }
+static inline half_t f2h(float v) { return (half_t)v; }
+static inline unsigned pack_h2(float lo, float hi) {
+    half_t h[2] = {(half_t)lo, (half_t)hi};
+    unsigned u; std::memcpy(&u, h, 4); return u;
+}
+static inline unsigned lds_u32(const half_t* p) { unsigned u; std::memcpy(&u, p, 4); return u; }
+static inline float emu_half_of(unsigned u, int hi) { half_t h[2]; std::memcpy(h, &u, 4); return (float)h[hi]; }
+static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+    auto* ws = &dlsg_emu::t_ctx->scratch[dlsg_emu::t_threadIdx.x >> 5];
+    const int lane = dlsg_emu::t_threadIdx.x & 31;
+    ws->f[lane] = v;
+    __syncwarp();
+    const float r = ws->f[lane ^ lane_mask];
+    __syncwarp();
+    return r;
+}
+// emulation of mma.sync.m16n8k16 (f16 x f16 -> f32) with the PTX ISA fragment layouts
+static inline void mma_m16n8k16_f16(float* c, const unsigned* a, unsigned b0, unsigned b1) {
+    auto* ws = &dlsg_emu::t_ctx->scratch[dlsg_emu::t_threadIdx.x >> 5];
+    const int lane = dlsg_emu::t_threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    for (int i = 0; i < 4; ++i) ws->a[lane][i] = a[i];
+    ws->b[lane][0] = b0; ws->b[lane][1] = b1;
+    __syncwarp();
+    auto A = [&](int row, int k) { return emu_half_of(ws->a[(row % 8) * 4 + (k % 8) / 2][(row >= 8 ? 1 : 0) + (k >= 8 ? 2 : 0)], k % 2); };
+    auto B = [&](int k, int n) { return emu_half_of(ws->b[n * 4 + (k % 8) / 2][k >= 8 ? 1 : 0], k % 2); };
+    for (int i = 0; i < 4; ++i) {
+        const int row = g + (i >= 2 ? 8 : 0), col = 2 * t4 + (i & 1);
+        float acc = c[i];
+        for (int k = 0; k < 16; ++k) acc += A(row, k) * B(k, col);
+        c[i] = acc;
+    }
+    __syncwarp();
+}
+
+
+
 static inline void cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
 static inline void cp_async_wait_all() {}
 static inline void cp_async_commit() {}
@@ -136,7 +193,8 @@ inline int launch(K kernel, dim3 grid, dim3 block, size_t smem, stream_t, A... a
             unsigned lanes = (w + 1) * 32 <= block.x ? 32 : block.x - w * 32;
             wb.push_back(new Barrier((int)lanes));
         }
-        BlockCtx ctx{&block_bar, wb, smem_buf};
+        std::vector<WarpScratch> scratch(nwarps);
+        BlockCtx ctx{&block_bar, wb, smem_buf, scratch.data()};
         std::memset(smem_buf, 0xCD, smem_alloc);   // poison: catches reads of unwritten smem
         std::vector<std::thread> th;
         for (unsigned t = 0; t < block.x; ++t) {

@@ -90,6 +90,37 @@ int dlsg_sense_dc_step_c64(const void* x, const void* aty, const void* maps, con
                            void* workspace, size_t workspace_bytes,
                            int B, int E, int C, int T, int Y, int X, int ndims, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Shifted-window attention of the Swin denoiser block
+ * (dl_cs/models/video_swin_transformer_mri_downsample.py).  All tensors fp32, contiguous.
+ * `window` / `shift` are the values actually used for this volume, i.e. after get_window_size (:72-85).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* LayerNorm (norm1) + zero pad to window multiples + cyclic shift + window_partition, the first half of
+ * SwinTransformerBlock3D.forward_part1 (:215-236) in one pass:
+ *   x [B,D,H,W,C]  ->  xw [B*nW, wd*wh*ww, C];  gamma / beta may be NULL (1 / 0);  padded tokens are exact zeros
+ *   (the reference pads after the norm, :219-225). */
+int dlsg_swin_ln_partition_f32(const float* x, const float* gamma, const float* beta, float eps, float* xw,
+                               int B, int D, int H, int W, int C, const int* window, const int* shift, void* stream);
+
+/* window_reverse + reverse cyclic shift + crop, the tail of forward_part1 (:238-248):
+ *   yw [B*nW, N, C]  ->  y [B,D,H,W,C] */
+int dlsg_swin_window_reverse_f32(const float* yw, float* y, int B, int D, int H, int W, int C,
+                                 const int* window, const int* shift, void* stream);
+
+/* Attention core of WindowAttention3D.forward (:148-167), between the qkv and proj Linear layers:
+ *   out[b_, i, h*hd + d] = sum_j softmax_j( scale * q_i . k_j + table[index[i,j], h] + mask[b_ % nW, i, j] ) * v_j[d]
+ *   qkv        [B_, N, 3, heads, head_dim]  exactly the output of the qkv Linear (:146), no permute
+ *   bias_table [(2Wd-1)(2Wh-1)(2Ww-1), heads] the module parameter; index[i,j] is regenerated in the kernel
+ *              from module_window = (Wd, Wh, Ww) (:115-129); N may be smaller than Wd*Wh*Ww (index[:N,:N], :152)
+ *   mask_mode  0 none; 1 `mask` = region ids, uint8 [nW, N]: additive -100 where ids differ (what compute_mask
+ *              :342-355 encodes); 2 `mask` = dense additive fp32 [nW, N, N] (any mask a caller passes)
+ *   out        [B_, N, heads*head_dim]  == (attn @ v).transpose(1, 2).reshape(B_, N, C)  (:167)
+ * head_dim <= 32.  fp16 tensor-core operands, fp32 softmax and accumulation. */
+int dlsg_swin_window_attention_f32(const float* qkv, const float* bias_table, float* out,
+                                   int B_, int N, int heads, int head_dim, const int* module_window, float scale,
+                                   int mask_mode, const void* mask, int nW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

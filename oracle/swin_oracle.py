@@ -132,7 +132,8 @@ def block_part1(x, p, num_heads, window_size, shift_size, mask_matrix=None):
         mask = None
     xw = window_partition(x, ws)
     ap = {k[len("attn."):]: v for k, v in p.items() if k.startswith("attn.")}
-    aw = window_attention(xw, ap, num_heads, ws, mask)
+    # the bias index is the MODULE's (un-clamped) window index sliced to [:N, :N] (:152), even when the window was clamped
+    aw = window_attention(xw, ap, num_heads, window_size, mask)
     aw = aw.reshape((-1,) + tuple(ws) + (C,))
     x = window_reverse(aw, ws, B, Dp, Hp, Wp)
     if shifted:

@@ -95,3 +95,51 @@ def test_torch_port_matches_reference_outputs(golden_cases, name):
     got = st.dc_path(k, maps, w, 1, float(ref["step"]), x0=x)
     assert rel_l2(got.numpy(), one.numpy()) < 1e-6
     assert rel_l2(st.adjoint(st.forward(x, maps, w), maps, w).numpy(), ref["normal_c64"]) < 2e-6
+
+
+# ----------------------------------------------------------------------------- shifted-window attention oracle
+from oracle import swin_oracle as sw  # noqa: E402
+from oracle.golden_inputs import SWIN_CASES, swin_case  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(SWIN_CASES))
+def test_swin_oracle_matches_reference_outputs(name):
+    c = swin_case(name)
+    ref = np.load(os.path.join(GOLDEN, f"swin_{name}.npz"))
+    x, p = c["x"].astype(np.float64), c["params"]
+    B, D, H, W, C = x.shape
+    ws, ss = sw.get_window_size((D, H, W), c["window"], c["shift"])
+    assert tuple(ref["ws"]) == ws and tuple(ref["ss"]) == ss
+    Dp, Hp, Wp = (int(np.ceil(n / w)) * w for n, w in zip((D, H, W), ws))
+    mask = sw.compute_mask(Dp, Hp, Wp, ws, ss)
+    assert np.array_equal(mask.astype(np.float32), ref["mask"])
+    assert np.array_equal(sw.relative_position_index(c["window"]), ref["relative_position_index"])
+    assert rel_l2(sw.block_part1(x, p, c["heads"], c["window"], c["shift"], mask), ref["part1"]) < 5e-6
+    xp = np.pad(x, ((0, 0), (0, Dp - D), (0, Hp - H), (0, Wp - W), (0, 0)))
+    xw = sw.window_partition(xp, ws)
+    ap = {k[5:]: v for k, v in p.items() if k.startswith("attn.")}
+    assert rel_l2(sw.window_attention(xw, ap, c["heads"], c["window"], None), ref["attn_nomask"]) < 5e-6
+    assert rel_l2(sw.window_attention(xw, ap, c["heads"], c["window"], mask), ref["attn_mask"]) < 5e-6
+
+
+def test_swin_host_helpers_match_oracle():
+    """The product's host-side helpers (pure torch indexing, CPU-runnable) against the oracle."""
+    import torch
+    from dl_swin_gan_b200.swin import window_attention as wa
+    for (D, H, W, ws, ss) in [(4, 8, 8, (2, 4, 4), (1, 2, 2)), (7, 16, 16, (7, 8, 8), (0, 4, 4)), (6, 8, 12, (2, 4, 4), (0, 0, 0))]:
+        m = wa.compute_mask(D, H, W, ws, ss, torch.device("cpu"))
+        assert np.array_equal(m.numpy(), sw.compute_mask(D, H, W, ws, ss).astype(np.float32))
+        assert wa.compute_mask(D, H, W, ws, ss, torch.device("cpu")) is m          # cached like the reference's lru_cache
+        rid = wa._region_ids_for(m, D, H, W, ws, ss, torch.device("cpu")).numpy().astype(np.int64)
+        assert np.array_equal(np.where(rid[:, None, :] != rid[:, :, None], -100.0, 0.0), m.numpy())
+    x = torch.arange(2 * 4 * 8 * 8 * 3, dtype=torch.float32).view(2, 4, 8, 8, 3)
+    xw = wa.window_partition(x, (2, 4, 4))
+    assert np.array_equal(xw.numpy(), sw.window_partition(x.numpy(), (2, 4, 4)))
+    back = wa.window_reverse(xw.view(-1, 2, 4, 4, 3), (2, 4, 4), 2, 4, 8, 8)
+    assert torch.equal(back, x)
+    assert wa.get_window_size((2, 8, 8), (4, 4, 4), (2, 2, 2)) == sw.get_window_size((2, 8, 8), (4, 4, 4), (2, 2, 2))
+    mod = wa.WindowAttention3D(160, (7, 8, 8), 8, qkv_bias=True)
+    shapes = {k: tuple(v.shape) for k, v in mod.state_dict().items()}
+    assert shapes == {"relative_position_bias_table": (2925, 8), "relative_position_index": (448, 448),
+                      "qkv.weight": (480, 160), "qkv.bias": (480,), "proj.weight": (160, 160), "proj.bias": (160,)}
+    assert np.array_equal(mod.relative_position_index.numpy(), sw.relative_position_index((7, 8, 8)))
