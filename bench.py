@@ -244,6 +244,7 @@ def main():
     from dl_swin_gan_b200 import _lib
     from dl_swin_gan_b200.mri import SenseModel
     from dl_swin_gan_b200.unrolled import ProximalGradientDescent
+    from dl_swin_gan_b200.sharding import max_over_ranks
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
     dev = torch.device("cuda", local_rank)
@@ -284,10 +285,7 @@ def main():
         e_ev.record()
         barrier()
     launches = int(lib.dlsg_launch_count() - n0)
-    ms = torch.tensor([s_ev.elapsed_time(e_ev)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms.item()) / args.steps
+    ms_per_step = max_over_ranks(s_ev.elapsed_time(e_ev), dev) / args.steps      # device-timed, max over ranks
     value = world * B / (ms_per_step * 1e-3)
 
     # ---- per-op timings for the roofline (CUDA events on the launching stream, batch >> L2)
@@ -339,10 +337,8 @@ def main():
         for _ in range(n_e2e):
             e2e_step()
         barrier()
-        el = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * n_e2e / float(el.item()), "unit": UNIT,
+        el = max_over_ranks(time.perf_counter() - t0, dev)
+        e2e = {"value": world * B * n_e2e / el, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e}
 
     cpu = None
