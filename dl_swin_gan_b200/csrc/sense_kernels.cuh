@@ -202,7 +202,9 @@ sense_rows_fwd_kernel(const float2* __restrict__ x, const float2* __restrict__ m
         for (int it0 = 0; it0 < nitems; it0 += NB) {
             const int nrows = min(NB, nitems - it0);
             int tl = it0 / cgn, cl = it0 - tl * cgn;
-            for (int r = 0; r < nrows; ++r) {
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {
+                if (r >= nrows) break;
                 const int t = tw0 + tl;
                 if (EREG > 0 && t != cur_t) {    // new frame: take the prefetched row, prefetch the next one
 #pragma unroll
@@ -247,7 +249,9 @@ sense_rows_fwd_kernel(const float2* __restrict__ x, const float2* __restrict__ m
             __syncwarp();
             row_radix32<RX, -1>(buf, lane, nrows);
             tl = it0 / cgn; cl = it0 - tl * cgn;
-            for (int r = 0; r < nrows; ++r) {
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {
+                if (r >= nrows) break;
                 float2* dst = tmp + idx_tmp(d, b, cg0 + cl, tw0 + tl, y) + lane;
                 const float2* sv = buf + r * Cfg::S2 + lane;
 #pragma unroll
@@ -321,9 +325,13 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
                 __syncwarp();                    // the previous frame's epilogue has read the buffer
                 for (int e = 0; e < ne; ++e) {
                     const size_t base = idx_x(d, b, e0 + e, t, y);
-                    for (int q = lane; q < X / 2; q += 32) {
-                        cp_async16(dcb + e * X + 2 * q, xin + base + 2 * q);
-                        cp_async16(dcb + (EMAX + e) * X + 2 * q, aty + base + 2 * q);
+#pragma unroll
+                    for (int m = 0; m < (X / 2 + 31) / 32; ++m) {
+                        const int q = lane + 32 * m;
+                        if ((X / 2) % 32 == 0 || q < X / 2) {
+                            cp_async16(dcb + e * X + 2 * q, xin + base + 2 * q);
+                            cp_async16(dcb + (EMAX + e) * X + 2 * q, aty + base + 2 * q);
+                        }
                     }
                 }
                 cp_async_commit();
@@ -359,7 +367,11 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
             for (int r = 0; r < nrows; ++r) {
                 const float2* src = tmp + idx_tmp(d, b, cg0 + cl, tw0 + tl, y);
                 float2* dstp = stg + r * X;
-                for (int q = lane; q < X / 2; q += 32) cp_async16(dstp + 2 * q, src + 2 * q);
+#pragma unroll
+                for (int m = 0; m < (X / 2 + 31) / 32; ++m) {
+                    const int q = lane + 32 * m;
+                    if ((X / 2) % 32 == 0 || q < X / 2) cp_async16(dstp + 2 * q, src + 2 * q);
+                }
                 if (++cl == cgn) { cl = 0; ++tl; }
             }
             cp_async_commit();
@@ -370,23 +382,28 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
             const int tl0 = it0 / cgn, cl0 = it0 - tl0 * cgn;
             cp_async_wait_group0();
             __syncwarp();
-            for (int r = 0; r < nrows; ++r) {
-                float2 v[RX];
 #pragma unroll
-                for (int j = 0; j < RX; ++j) v[j] = stg[r * X + lane + 32 * j];
-                Dft<RX, +1>::run(v);
-                float2* o = buf + (r * RX) * Cfg::S1 + lane;
+            for (int r = 0; r < NB; ++r) {       // rows are independent: unrolled so that their chains interleave
+                if (r < nrows) {
+                    float2 v[RX];
 #pragma unroll
-                for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmul(v[k2], tw[k2]);
+                    for (int j = 0; j < RX; ++j) v[j] = stg[r * X + lane + 32 * j];
+                    Dft<RX, +1>::run(v);
+                    float2* o = buf + (r * RX) * Cfg::S1 + lane;
+#pragma unroll
+                    for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmul(v[k2], tw[k2]);
+                }
             }
             __syncwarp();                        // staging buffer consumed, view 1 complete
             if (it0 + NB < nitems) stage_batch(it0 + NB);   // lands while phases B and C run
             row_radix32<RX, +1>(buf, lane, nrows);
             int tl = tl0, cl = cl0;
-            for (int r = 0; r < nrows; ++r) {
+            const float2* sv = buf + lane;
+            const float2* mrow = ms + cl0 * X + lane;
+            const int estride = plan.cgroup * X;
+            for (int r = 0; r < nrows; ++r, sv += Cfg::S2) {
                 const int t = tw0 + tl;
                 if (t != cur_t) { flush(cur_t); cur_t = t; stage_dc(t); }
-                const float2* sv = buf + r * Cfg::S2 + lane;
                 float2 v[RX];
 #pragma unroll
                 for (int j = 0; j < RX; ++j) v[j] = sv[32 * j];
@@ -394,7 +411,7 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
                 for (int e = 0; e < EMAX; ++e) {
                     if (e < ne) {
                         if (maps) {
-                            const float2* m = ms + (size_t)(e * plan.cgroup + cl) * X + lane;
+                            const float2* m = mrow + e * estride;
 #pragma unroll
                             for (int j = 0; j < RX; ++j) acc[e][j] = cfmac(v[j], m[32 * j], acc[e][j]);
                         } else {
@@ -403,7 +420,8 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
                         }
                     }
                 }
-                if (++cl == cgn) { cl = 0; ++tl; }
+                mrow += X;
+                if (++cl == cgn) { cl = 0; ++tl; mrow = ms + lane; }
             }
             __syncwarp();
         }
