@@ -37,6 +37,7 @@ SIGNATURES = {
     "dlsg_swin_ln_partition_f32": (_i, [_vp, _vp, _vp, _f, _vp] + [_i] * 5 + [_vp, _vp, _vp]),
     "dlsg_swin_window_reverse_f32": (_i, [_vp, _vp] + [_i] * 5 + [_vp, _vp, _vp]),
     "dlsg_swin_window_attention_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _f, _i, _vp, _i, _vp]),
+    "dlsg_swin_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

@@ -1,6 +1,7 @@
 // C-ABI entry points of the shifted-window attention path (declared in include/dlsg_b200.h).
 #include "../../include/dlsg_b200.h"
 #include "swin_kernels.cuh"
+#include "swin_linear_tc.cuh"
 
 namespace dlsg {
 namespace {
@@ -82,6 +83,29 @@ int dlsg_swin_window_attention_f32(const float* qkv, const float* bias_table, fl
     else if (mask_mode == SWIN_MASK_REGION) rc = launch(swin_attn_core_kernel<SWIN_MASK_REGION>, grid, block, smem, (stream_t)stream, p);
     else                                    rc = launch(swin_attn_core_kernel<SWIN_MASK_DENSE>, grid, block, smem, (stream_t)stream, p);
     return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
+}
+
+int dlsg_swin_linear_f32(const float* x, const float* weight, const float* bias, float* y,
+                         int M, int N, int K, void* stream) {
+#if defined(__CUDACC__)
+    using namespace dlsg;
+    if (!x || !weight || !y || M <= 0 || N <= 0 || K <= 0) return DLSG_EINVAL;
+    if (K % 16 != 0 || N % 32 != 0 || N > 512 || (N > 256 && (N / 2) % 16 != 0)) return DLSG_EUNSUPPORTED;
+    if ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(weight)) % 16 != 0) return DLSG_EUNSUPPORTED;
+    const size_t smem = linear_smem_bytes(N, K);
+    if (smem > 227 * 1024) return DLSG_EUNSUPPORTED;
+    LinearParams p{x, weight, bias, y, M, N, K, 32};
+    while (p.tmem_cols < N) p.tmem_cols *= 2;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = (M + kLinTileM - 1) / kLinTileM;
+    const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+    return launch(swin_linear_tc_kernel, dim3(grid), dim3(kLinThreads), smem, (stream_t)stream, p) == 0 ? DLSG_OK : DLSG_ELAUNCH;
+#else
+    (void)x; (void)weight; (void)bias; (void)y; (void)M; (void)N; (void)K; (void)stream;
+    return DLSG_EUNSUPPORTED;      // tcgen05 / TMEM have no host emulation
+#endif
 }
 
 }  // extern "C"

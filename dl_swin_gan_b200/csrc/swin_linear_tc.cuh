@@ -1,0 +1,177 @@
+// Linear layers of the window-attention block (qkv :146, proj :168 of
+// dl_cs/models/video_swin_transformer_mri_downsample.py) on the 5th-generation tensor cores:
+//     Y[M, N] = X[M, K] * W[N, K]^T + bias[N]        fp32 in / out, fp16 operands, fp32 accumulation in TMEM.
+//
+// One persistent CTA per SM (128 threads).  W is converted to fp16 once per CTA and kept in shared memory in
+// the canonical no-swizzle K-major UMMA layout ([k/8][n/8][8 rows][8 halves]: core matrices of 8 x 16 bytes,
+// SBO = 128 B between row groups, LBO = (rows/8)*128 B between k chunks).  Per 128-row tile: the X rows are
+// converted and laid out the same way, one elected thread issues the tcgen05.mma chain (K/16 steps per N half,
+// N <= 256 per instruction), tcgen05.commit signals an mbarrier, and the four warps drain their 32 TMEM lanes
+// with tcgen05.ld, add the bias and store coalesced rows through a shared-memory transpose.
+// CUDA-only (no host emulation: tcgen05 / TMEM have no software model here); validated on the B200 against
+// torch.nn.functional.linear in tests/test_swin_gpu.py.
+#pragma once
+
+#include "cuda_compat.h"
+
+#if defined(__CUDACC__)
+namespace dlsg {
+
+constexpr int kLinThreads = 128;
+constexpr int kLinTileM = 128;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor, version 1 = sm_100)
+__device__ __forceinline__ unsigned long long umma_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((saddr >> 4) & 0x3fff);
+    d |= (unsigned long long)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (unsigned long long)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= 1ull << 46;                 // descriptor version
+    return d;                        // layout_type (bits 61-63) = 0: SWIZZLE_NONE
+}
+
+// instruction descriptor for kind::f16: A = B = F16 (0), D = F32 (1), both K-major, dense
+__device__ __forceinline__ unsigned umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                         unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float* v) {
+    unsigned* r = reinterpret_cast<unsigned*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+struct LinearParams {
+    const float* x;      // [M, K]
+    const float* w;      // [N, K]
+    const float* bias;   // [N] or NULL
+    float* y;            // [M, N]
+    int M, N, K;
+    int tmem_cols;       // power of two >= N, >= 32
+};
+
+// dynamic smem: W fp16 [K/8][N/8][8][8] | A fp16 [K/8][16][8][8] (reused as the epilogue transpose) | bias fp32 [N] | ctrl
+__host__ __device__ inline size_t linear_a_region_bytes(int K) {      // A tile, reused as 4 x [32][33] fp32 transpose buffers
+    const size_t a = (size_t)kLinTileM * K * 2, st = (size_t)(kLinThreads / 32) * 32 * 33 * 4;
+    return ((a > st ? a : st) + 127) / 128 * 128;
+}
+inline size_t linear_smem_bytes(int N, int K) {
+    return (size_t)N * K * 2 + linear_a_region_bytes(K) + (size_t)N * 4 + 64;
+}
+
+__global__ void __launch_bounds__(kLinThreads, 1) swin_linear_tc_kernel(LinearParams p) {
+    extern __shared__ __align__(128) unsigned char lin_smem[];
+    const int N = p.N, K = p.K, KC = K / 8;
+    half_t* sW = reinterpret_cast<half_t*>(lin_smem);
+    half_t* sA = sW + (size_t)N * K;
+    float* sBias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sA) + linear_a_region_bytes(K));
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sBias + N);
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(mbar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned lboW = (unsigned)(N / 8) * 128u, lboA = (unsigned)(kLinTileM / 8) * 128u;
+
+    // ---- one-time setup: TMEM allocation, mbarrier, weights and bias
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(smem_u32(mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = tid; i < N * KC; i += kLinThreads) {          // item = (k chunk, row n): consecutive threads -> consecutive n
+        const int kc = i / N, n = i - kc * N;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * K + 8 * kc));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * K + 8 * kc + 4));
+        uint4 h;
+        h.x = pack_h2(a.x, a.y); h.y = pack_h2(a.z, a.w); h.z = pack_h2(b.x, b.y); h.w = pack_h2(b.z, b.w);
+        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(sW) + (size_t)kc * lboW + (size_t)(n >> 3) * 128 + (n & 7) * 16) = h;
+    }
+    for (int i = tid; i < N; i += kLinThreads) sBias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+
+    const int ntiles = (p.M + kLinTileM - 1) / kLinTileM;
+    unsigned phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- A tile: thread = row; fp32 -> fp16, canonical layout (rows beyond M are zero)
+        const int row = tile * kLinTileM + tid;
+        const float* xr = p.x + (size_t)row * K;
+        for (int kc = 0; kc < KC; ++kc) {
+            uint4 h = make_uint4(0u, 0u, 0u, 0u);
+            if (row < p.M) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc + 4));
+                h.x = pack_h2(a.x, a.y); h.y = pack_h2(a.z, a.w); h.z = pack_h2(b.x, b.y); h.w = pack_h2(b.z, b.w);
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(sA) + (size_t)kc * lboA + (size_t)(tid >> 3) * 128 + (tid & 7) * 16) = h;
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
+        __syncthreads();
+        // ---- MMA chain: D[128, N] = A[128, K] * W[N, K]^T, N split into halves of <= 256 columns
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const int nh = (N > 256) ? N / 2 : N;
+            const unsigned idesc = umma_idesc_f16(kLinTileM, nh);
+            for (int n0 = 0; n0 < N; n0 += nh) {
+                for (int ks = 0; ks < K / 16; ++ks) {
+                    const unsigned long long ad = umma_desc(smem_u32(sA) + (unsigned)(2 * ks) * lboA, lboA, 128u);
+                    const unsigned long long bd = umma_desc(smem_u32(sW) + (unsigned)(2 * ks) * lboW + (unsigned)(n0 / 8) * 128u, lboW, 128u);
+                    umma_f16(tmem_base + (unsigned)n0, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(mbar)) : "memory");
+        }
+        // ---- wait for the accumulator (bounded spin: a broken pipeline traps instead of hanging the GPU)
+        {
+            unsigned done = 0;
+            for (long long spin = 0; !done; ++spin) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                             : "=r"(done) : "r"(smem_u32(mbar)), "r"(phase) : "memory");
+                if (spin > (1ll << 26)) __trap();
+            }
+            phase ^= 1u;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 (= tile rows); 32 columns at a time through a smem transpose
+        float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);
+        const int row0 = tile * kLinTileM + warp * 32;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j] + sBias[c0 + j];
+            __syncwarp();
+            for (int r = 0; r < 32; ++r) {
+                if (row0 + r < p.M) p.y[(size_t)(row0 + r) * N + c0 + lane] = stage[r * 33 + lane];
+            }
+            __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();                                      // TMEM drained and the A / stage region free for the next tile
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+}  // namespace dlsg
+#endif

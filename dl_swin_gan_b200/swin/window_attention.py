@@ -112,6 +112,26 @@ def _region_ids_for(mask_matrix, D, H, W, window_size, shift_size, device):
     return None
 
 
+# ----------------------------------------------------------------------------- tensor-core linear (tcgen05 + TMEM)
+def linear_tc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """torch.nn.functional.linear on the tcgen05 kernel: fp16 operands, fp32 accumulation.  x [..., K] fp32 CUDA."""
+    _require_cuda_f32(x, "linear_tc input")
+    lib = _lib.load()
+    K = x.shape[-1]
+    N = weight.shape[0]
+    x2 = x.contiguous().view(-1, K)
+    y = torch.empty((x2.shape[0], N), dtype=torch.float32, device=x.device)
+    if y.numel() == 0:
+        return y.view(*x.shape[:-1], N)
+    w = weight.detach().contiguous()
+    b = bias.detach().contiguous() if bias is not None else None
+    with torch.cuda.device(x.device):
+        st = lib.dlsg_swin_linear_f32(x2.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None,
+                                      y.data_ptr(), x2.shape[0], N, K, _stream())
+    _lib.check(st, "dlsg_swin_linear")
+    return y.view(*x.shape[:-1], N)
+
+
 # ----------------------------------------------------------------------------- attention core
 def _attention_core_raw(qkv, table, num_heads, module_window, scale, mask_mode, mask, nW):
     lib = _lib.load()
@@ -209,7 +229,7 @@ class WindowAttention3D(nn.Module):
         _require_cuda_f32(x, "WindowAttention3D input")
         if self.training and self.attn_drop.p > 0:
             raise NotImplementedError("attn_drop > 0 in training is not supported by the fused attention core")
-        qkv = self.qkv(x)                                   # (B_, N, 3C): the kernel reads q/k/v in place
+        qkv = self._linear(self.qkv, x)                     # (B_, N, 3C): the kernel reads q/k/v in place
         if _region_ids is not None:
             mode, m, dense = MASK_REGION, _region_ids, mask
         elif mask is not None:
@@ -219,8 +239,18 @@ class WindowAttention3D(nn.Module):
             mode, m, dense = MASK_NONE, None, None
         out = _AttnCoreFn.apply(qkv, self.relative_position_bias_table, self.relative_position_index,
                                 self.num_heads, tuple(self.window_size), self.scale, mode, m, dense)
-        out = self.proj(out)
+        out = self._linear(self.proj, out)
         return self.proj_drop(out)
+
+    tc_linear = True    # qkv / proj on the tcgen05 kernel when no gradient is needed (fp16 operands, fp32 accumulate)
+
+    def _linear(self, layer: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or layer.weight.requires_grad)
+        K, N = layer.in_features, layer.out_features
+        if (self.tc_linear and not needs_grad and K % 16 == 0 and N % 32 == 0 and N <= 512
+                and (N <= 256 or (N // 2) % 16 == 0) and N * K * 2 + max(256 * K, 16896) + 4 * N + 192 <= 227 * 1024):
+            return linear_tc(x, layer.weight, layer.bias)
+        return layer(x)
 
 
 # ----------------------------------------------------------------------------- fused first half of the block

@@ -121,6 +121,13 @@ int dlsg_swin_window_attention_f32(const float* qkv, const float* bias_table, fl
                                    int B_, int N, int heads, int head_dim, const int* module_window, float scale,
                                    int mask_mode, const void* mask, int nW, void* stream);
 
+/* Linear layer on the tcgen05 tensor cores (qkv :146 and proj :168 of WindowAttention3D):
+ *     y[M, N] = x[M, K] @ weight[N, K]^T + bias[N]       (torch.nn.functional.linear semantics)
+ * fp32 in/out, fp16 operands, fp32 accumulation in tensor memory.  K % 16 == 0, N % 32 == 0, N <= 512,
+ * N*K*2 + 128*K*2 + 4N + 64 bytes of shared memory must fit 227 KB; x and weight 16-byte aligned. */
+int dlsg_swin_linear_f32(const float* x, const float* weight, const float* bias, float* y,
+                         int M, int N, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

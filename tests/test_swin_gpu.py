@@ -141,6 +141,22 @@ def test_basic_layer_runs_and_matches_blockwise_oracle(dev):
     assert rel_l2(got.cpu().numpy(), want) < TOL
 
 
+def test_tcgen05_linear_matches_torch(dev):
+    from dl_swin_gan_b200.swin import window_attention as wa
+    torch.manual_seed(3)
+    for (M, N, K) in [(128, 32, 16), (1, 160, 160), (300, 480, 160), (13440, 480, 160), (13440, 160, 160), (257, 512, 64)]:
+        x = torch.randn(M, K, device=dev)
+        w = torch.randn(N, K, device=dev) / K ** 0.5
+        b = torch.randn(N, device=dev)
+        want = torch.nn.functional.linear(x.double(), w.double(), b.double())
+        got = wa.linear_tc(x, w, b)
+        assert rel_l2(got.cpu().numpy(), want.cpu().numpy()) < 5e-4, (M, N, K)       # fp16 operand rounding ~2e-4
+        got_nb = wa.linear_tc(x, w, None)
+        assert rel_l2(got_nb.cpu().numpy(), (want - b.double()).cpu().numpy()) < 5e-4
+    with pytest.raises(ValueError):
+        wa.linear_tc(torch.randn(8, 24, device=dev), torch.randn(32, 24, device=dev), None)       # K % 16 != 0
+
+
 def test_error_behaviour(dev):
     from dl_swin_gan_b200.swin import window_attention as wa
     mod = wa.WindowAttention3D(16, (2, 4, 4), 2).to(dev)
