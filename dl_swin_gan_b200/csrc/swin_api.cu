@@ -4,7 +4,6 @@
 #include "swin_linear_tc.cuh"
 
 namespace dlsg {
-namespace {
 
 int make_geom(SwinGeom& g, int B, int D, int H, int W, int C, const int* window, const int* shift) {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0 || !window || !shift) return DLSG_EINVAL;
@@ -23,8 +22,76 @@ long long geom_tokens(const SwinGeom& g) {
     return (long long)g.B * (g.Dp / g.wd) * (g.Hp / g.wh) * (g.Wp / g.ww) * g.wd * g.wh * g.ww;
 }
 
-}  // namespace
 }  // namespace dlsg
+
+static int attention_common(const float* qkv, const void* q16, const void* k16, const void* vt16,
+                            const float* bias_table, float* out,
+                            int B_, int N, int heads, int head_dim, const int* module_window, float scale,
+                            int mask_mode, const void* mask, int nW, void* stream) {
+    using namespace dlsg;
+    const bool in16 = (qkv == nullptr);
+    if (in16 ? (!q16 || !k16 || !vt16) : false) return DLSG_EINVAL;
+    if (!bias_table || !out || !module_window) return DLSG_EINVAL;
+    if (B_ <= 0 || N <= 0 || heads <= 0 || head_dim <= 0) return DLSG_EINVAL;
+    if (mask_mode < SWIN_MASK_NONE || mask_mode > SWIN_MASK_DENSE) return DLSG_EINVAL;
+    if (mask_mode != SWIN_MASK_NONE && (!mask || nW <= 0 || B_ % nW != 0)) return DLSG_EINVAL;
+    const int mwd = module_window[0], mwh = module_window[1], mww = module_window[2];
+    if (mwd <= 0 || mwh <= 0 || mww <= 0 || N > mwd * mwh * mww) return DLSG_EINVAL;
+    const long long table_len = (long long)(2 * mwd - 1) * (2 * mwh - 1) * (2 * mww - 1);
+    if (head_dim > kAttnHdPad || table_len > 65535 || N > 4096) return DLSG_EUNSUPPORTED;
+    if (in16 && N % 8 != 0) return DLSG_EUNSUPPORTED;
+
+    AttnParams p{};
+    p.qkv = qkv; p.q16 = static_cast<const half_t*>(q16); p.k16 = static_cast<const half_t*>(k16);
+    p.vt16 = static_cast<const half_t*>(vt16);
+    p.table = bias_table; p.out = out;
+    p.region = (mask_mode == SWIN_MASK_REGION) ? static_cast<const unsigned char*>(mask) : nullptr;
+    p.mask = (mask_mode == SWIN_MASK_DENSE) ? static_cast<const float*>(mask) : nullptr;
+    p.B_ = B_; p.N = N; p.heads = heads; p.hd = head_dim; p.nW = (mask_mode == SWIN_MASK_NONE) ? 1 : nW;
+    p.mwd = mwd; p.mwh = mwh; p.mww = mww;
+    p.scale = scale;
+    p.npad = (N + kAttnKB - 1) / kAttnKB * kAttnKB;
+    p.vstride = p.npad + 8;
+    p.table_len = (int)table_len;
+    const size_t smem = attn_smem_bytes(p.npad, p.vstride, p.table_len);
+    if (smem > 227 * 1024) return DLSG_EUNSUPPORTED;
+    const dim3 grid(heads, B_), block(32 * kAttnWarps);
+    stream_t st = (stream_t)stream;
+    int rc;
+    if (in16) {
+        if (mask_mode == SWIN_MASK_NONE)        rc = launch(swin_attn_core_kernel<SWIN_MASK_NONE, true>, grid, block, smem, st, p);
+        else if (mask_mode == SWIN_MASK_REGION) rc = launch(swin_attn_core_kernel<SWIN_MASK_REGION, true>, grid, block, smem, st, p);
+        else                                    rc = launch(swin_attn_core_kernel<SWIN_MASK_DENSE, true>, grid, block, smem, st, p);
+    } else {
+        if (mask_mode == SWIN_MASK_NONE)        rc = launch(swin_attn_core_kernel<SWIN_MASK_NONE, false>, grid, block, smem, st, p);
+        else if (mask_mode == SWIN_MASK_REGION) rc = launch(swin_attn_core_kernel<SWIN_MASK_REGION, false>, grid, block, smem, st, p);
+        else                                    rc = launch(swin_attn_core_kernel<SWIN_MASK_DENSE, false>, grid, block, smem, st, p);
+    }
+    return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
+}
+
+#if defined(__CUDACC__)
+static int linear_check(int M, int N, int K, const void* a, const void* w) {
+    if (M <= 0 || N <= 0 || K <= 0 || !a || !w) return DLSG_EINVAL;
+    if (K % 16 != 0 || N % 32 != 0 || N > 512 || (N > 256 && (N / 2) % 16 != 0)) return DLSG_EUNSUPPORTED;
+    if ((reinterpret_cast<size_t>(a) | reinterpret_cast<size_t>(w)) % 16 != 0) return DLSG_EUNSUPPORTED;
+    if (dlsg::linear_smem_bytes(N, K) > 227 * 1024) return DLSG_EUNSUPPORTED;
+    return DLSG_OK;
+}
+template <int AMODE, int EMODE>
+static int linear_launch(dlsg::LinearParams& p, void* stream) {
+    using namespace dlsg;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.N) p.tmem_cols *= 2;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = (p.M + kLinTileM - 1) / kLinTileM;
+    const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+    return launch(swin_linear_tc_kernel<AMODE, EMODE>, dim3(grid), dim3(kLinThreads), linear_smem_bytes(p.N, p.K),
+                  (stream_t)stream, p) == 0 ? DLSG_OK : DLSG_ELAUNCH;
+}
+#endif
 
 extern "C" {
 
@@ -55,56 +122,77 @@ int dlsg_swin_window_reverse_f32(const float* yw, float* y, int B, int D, int H,
 int dlsg_swin_window_attention_f32(const float* qkv, const float* bias_table, float* out,
                                    int B_, int N, int heads, int head_dim, const int* module_window, float scale,
                                    int mask_mode, const void* mask, int nW, void* stream) {
-    using namespace dlsg;
-    if (!qkv || !bias_table || !out || !module_window) return DLSG_EINVAL;
-    if (B_ <= 0 || N <= 0 || heads <= 0 || head_dim <= 0) return DLSG_EINVAL;
-    if (mask_mode < SWIN_MASK_NONE || mask_mode > SWIN_MASK_DENSE) return DLSG_EINVAL;
-    if (mask_mode != SWIN_MASK_NONE && (!mask || nW <= 0 || B_ % nW != 0)) return DLSG_EINVAL;
-    const int mwd = module_window[0], mwh = module_window[1], mww = module_window[2];
-    if (mwd <= 0 || mwh <= 0 || mww <= 0 || N > mwd * mwh * mww) return DLSG_EINVAL;
-    const long long table_len = (long long)(2 * mwd - 1) * (2 * mwh - 1) * (2 * mww - 1);
-    if (head_dim > kAttnHdPad || table_len > 65535 || N > 4096) return DLSG_EUNSUPPORTED;
+    if (!qkv) return DLSG_EINVAL;
+    return attention_common(qkv, nullptr, nullptr, nullptr, bias_table, out, B_, N, heads, head_dim, module_window, scale,
+                            mask_mode, mask, nW, stream);
+}
 
-    AttnParams p{};
-    p.qkv = qkv; p.table = bias_table; p.out = out;
-    p.region = (mask_mode == SWIN_MASK_REGION) ? static_cast<const unsigned char*>(mask) : nullptr;
-    p.mask = (mask_mode == SWIN_MASK_DENSE) ? static_cast<const float*>(mask) : nullptr;
-    p.B_ = B_; p.N = N; p.heads = heads; p.hd = head_dim; p.nW = (mask_mode == SWIN_MASK_NONE) ? 1 : nW;
-    p.mwd = mwd; p.mwh = mwh; p.mww = mww;
-    p.scale = scale;
-    p.npad = (N + kAttnKB - 1) / kAttnKB * kAttnKB;
-    p.vstride = p.npad + 8;
-    p.table_len = (int)table_len;
-    const size_t smem = attn_smem_bytes(p.npad, p.vstride, p.table_len);
-    if (smem > 227 * 1024) return DLSG_EUNSUPPORTED;
-    const dim3 grid(heads, B_), block(32 * kAttnWarps);
-    int rc;
-    if (mask_mode == SWIN_MASK_NONE)        rc = launch(swin_attn_core_kernel<SWIN_MASK_NONE>, grid, block, smem, (stream_t)stream, p);
-    else if (mask_mode == SWIN_MASK_REGION) rc = launch(swin_attn_core_kernel<SWIN_MASK_REGION>, grid, block, smem, (stream_t)stream, p);
-    else                                    rc = launch(swin_attn_core_kernel<SWIN_MASK_DENSE>, grid, block, smem, (stream_t)stream, p);
-    return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
+int dlsg_swin_window_attention_f16(const void* q16, const void* k16, const void* vt16, const float* bias_table, float* out,
+                                   int B_, int N, int heads, int head_dim, const int* module_window,
+                                   int mask_mode, const void* mask, int nW, void* stream) {
+    return attention_common(nullptr, q16, k16, vt16, bias_table, out, B_, N, heads, head_dim, module_window, 1.0f,
+                            mask_mode, mask, nW, stream);
 }
 
 int dlsg_swin_linear_f32(const float* x, const float* weight, const float* bias, float* y,
                          int M, int N, int K, void* stream) {
 #if defined(__CUDACC__)
-    using namespace dlsg;
-    if (!x || !weight || !y || M <= 0 || N <= 0 || K <= 0) return DLSG_EINVAL;
-    if (K % 16 != 0 || N % 32 != 0 || N > 512 || (N > 256 && (N / 2) % 16 != 0)) return DLSG_EUNSUPPORTED;
-    if ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(weight)) % 16 != 0) return DLSG_EUNSUPPORTED;
-    const size_t smem = linear_smem_bytes(N, K);
-    if (smem > 227 * 1024) return DLSG_EUNSUPPORTED;
-    LinearParams p{x, weight, bias, y, M, N, K, 32};
-    while (p.tmem_cols < N) p.tmem_cols *= 2;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int ntiles = (M + kLinTileM - 1) / kLinTileM;
-    const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-    return launch(swin_linear_tc_kernel, dim3(grid), dim3(kLinThreads), smem, (stream_t)stream, p) == 0 ? DLSG_OK : DLSG_ELAUNCH;
+    const int st = linear_check(M, N, K, x, weight);
+    if (st != DLSG_OK) return st;
+    if (!y) return DLSG_EINVAL;
+    dlsg::LinearParams p{};
+    p.x = x; p.w = weight; p.bias = bias; p.y = y; p.M = M; p.N = N; p.K = K;
+    return linear_launch<dlsg::A_PLAIN, dlsg::E_PLAIN>(p, stream);
 #else
     (void)x; (void)weight; (void)bias; (void)y; (void)M; (void)N; (void)K; (void)stream;
     return DLSG_EUNSUPPORTED;      // tcgen05 / TMEM have no host emulation
+#endif
+}
+
+int dlsg_swin_qkv_fused_f32(const float* x, const float* gamma, const float* beta, float eps,
+                            const float* weight, const float* bias, void* q16, void* k16, void* vt16,
+                            int B, int D, int H, int W, int C, const int* window, const int* shift,
+                            int heads, float scale, void* stream) {
+#if defined(__CUDACC__)
+    dlsg::LinearParams p{};
+    int st = dlsg::make_geom(p.g, B, D, H, W, C, window, shift);
+    if (st != DLSG_OK) return st;
+    if (heads <= 0 || C % heads != 0 || !q16 || !k16 || !vt16) return DLSG_EINVAL;
+    const int hd = C / heads, ntok = window[0] * window[1] * window[2];
+    if (hd > 32 || hd % 4 != 0 || ntok % 8 != 0) return DLSG_EUNSUPPORTED;
+    const long long M = dlsg::geom_tokens(p.g);
+    if (M > 0x7fffffffLL) return DLSG_EUNSUPPORTED;
+    st = linear_check((int)M, 3 * C, C, x, weight);
+    if (st != DLSG_OK) return st;
+    p.x = x; p.w = weight; p.bias = bias; p.y = nullptr; p.M = (int)M; p.N = 3 * C; p.K = C;
+    p.gamma = gamma; p.beta = beta; p.eps = eps;
+    p.q16 = static_cast<half_t*>(q16); p.k16 = static_cast<half_t*>(k16); p.vt16 = static_cast<half_t*>(vt16);
+    p.heads = heads; p.hd = hd; p.ntok = ntok; p.qscale = scale * dlsg::kLog2e;
+    return linear_launch<dlsg::A_LN_GATHER, dlsg::E_QKV16>(p, stream);
+#else
+    (void)x; (void)gamma; (void)beta; (void)eps; (void)weight; (void)bias; (void)q16; (void)k16; (void)vt16;
+    (void)B; (void)D; (void)H; (void)W; (void)C; (void)window; (void)shift; (void)heads; (void)scale; (void)stream;
+    return DLSG_EUNSUPPORTED;
+#endif
+}
+
+int dlsg_swin_proj_scatter_f32(const float* attn_out, const float* weight, const float* bias, float* y,
+                               int B, int D, int H, int W, int C, const int* window, const int* shift, void* stream) {
+#if defined(__CUDACC__)
+    dlsg::LinearParams p{};
+    int st = dlsg::make_geom(p.g, B, D, H, W, C, window, shift);
+    if (st != DLSG_OK) return st;
+    const long long M = dlsg::geom_tokens(p.g);
+    if (M > 0x7fffffffLL) return DLSG_EUNSUPPORTED;
+    st = linear_check((int)M, C, C, attn_out, weight);
+    if (st != DLSG_OK) return st;
+    if (!y) return DLSG_EINVAL;
+    p.x = attn_out; p.w = weight; p.bias = bias; p.y = y; p.M = (int)M; p.N = C; p.K = C;
+    return linear_launch<dlsg::A_PLAIN, dlsg::E_SCATTER>(p, stream);
+#else
+    (void)attn_out; (void)weight; (void)bias; (void)y; (void)B; (void)D; (void)H; (void)W; (void)C;
+    (void)window; (void)shift; (void)stream;
+    return DLSG_EUNSUPPORTED;
 #endif
 }
 

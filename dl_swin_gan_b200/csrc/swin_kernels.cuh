@@ -118,7 +118,10 @@ constexpr float kLog2e = 1.4426950408889634f;
 enum : int { SWIN_MASK_NONE = 0, SWIN_MASK_REGION = 1, SWIN_MASK_DENSE = 2 };
 
 struct AttnParams {
-    const float* qkv;        // [B_, N, 3, heads, hd] fp32 (output of the qkv Linear, untouched)
+    const float* qkv;        // [B_, N, 3, heads, hd] fp32 (output of the qkv Linear, untouched); NULL when the fp16 triple is given
+    const half_t* q16;       // [B_, heads, N, 32] fp16, already multiplied by scale*log2(e)   (written by the fused qkv GEMM)
+    const half_t* k16;       // [B_, heads, N, 32] fp16
+    const half_t* vt16;      // [B_, heads, 32, N] fp16
     const float* table;      // relative_position_bias_table [(2Wd-1)(2Wh-1)(2Ww-1), heads] fp32
     const unsigned char* region;   // [nW, N] region ids (SWIN_MASK_REGION)
     const float* mask;       // [nW, N, N] additive mask (SWIN_MASK_DENSE)
@@ -135,7 +138,7 @@ inline size_t attn_smem_bytes(int npad, int vstride, int table_len) {   // host-
     return (size_t)npad * kAttnKStride * 2 + (size_t)kAttnHdPad * vstride * 2 + (size_t)table_len * 4 + (size_t)npad * 4;
 }
 
-template <int MASK_MODE>
+template <int MASK_MODE, bool IN16>
 DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(32 * kAttnWarps, 2)
 swin_attn_core_kernel(AttnParams p) {
     DLSG_DYN_SMEM(unsigned char, smem_raw);
@@ -154,6 +157,26 @@ swin_attn_core_kernel(AttnParams p) {
 
     // ---- stage K [tok][hd] and V^T [d][tok] as fp16 (zero padded), the head's bias column, the token table.
     // Lanes run over tokens (conflict-free V^T stores); each item is 4 consecutive head dims.
+    const size_t bh = (size_t)bwin * p.heads + head;
+    if (IN16) {
+        // fp16 q / k / v^T straight from the fused qkv GEMM: plain 16-byte asynchronous copies (N % 8 == 0)
+        const half_t* kg = p.k16 + bh * (size_t)N * 32;
+        const half_t* vg = p.vt16 + bh * 32 * (size_t)N;
+        for (int i = tid; i < N * 4; i += blockDim.x) {
+            const int tok = i >> 2, ch = i & 3;
+            cp_async16(sK + (size_t)tok * kAttnKStride + 8 * ch, kg + (size_t)tok * 32 + 8 * ch);
+        }
+        const int vch = N / 8;
+        for (int i = tid; i < kAttnHdPad * vch; i += blockDim.x) {
+            const int dd = i / vch, ch = i - dd * vch;
+            cp_async16(sVt + (size_t)dd * p.vstride + 8 * ch, vg + (size_t)dd * N + 8 * ch);
+        }
+        for (int i = tid; i < (p.npad - N) * kAttnHdPad; i += blockDim.x) {          // padded keys: zero rows / columns
+            const int tok = N + i / kAttnHdPad, dd = i % kAttnHdPad;
+            sK[(size_t)tok * kAttnKStride + dd] = f2h(0.f);
+            sVt[(size_t)dd * p.vstride + tok] = f2h(0.f);
+        }
+    } else {
     const bool vec4 = (hd % 4 == 0) && (((size_t)C3 * 4) % 16 == 0) && ((((size_t)head * hd + koff) * 4) % 16 == 0) &&
                       ((((size_t)head * hd + voff) * 4) % 16 == 0) && ((reinterpret_cast<size_t>(p.qkv) % 16) == 0) &&
                       ((((size_t)N * C3) * 4) % 16 == 0);
@@ -179,6 +202,7 @@ swin_attn_core_kernel(AttnParams p) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) sVt[(size_t)(dd + e) * p.vstride + tok] = f2h(vv[e]);
     }
+    }
     for (int i = tid; i < p.table_len; i += blockDim.x) sTab[i] = __ldg(p.table + (size_t)i * p.heads + head) * kLog2e;
     const int c_h = 2 * p.mww - 1, c_d = (2 * p.mwh - 1) * c_h;
     for (int tok = tid; tok < p.npad; tok += blockDim.x) {
@@ -188,6 +212,7 @@ swin_attn_core_kernel(AttnParams p) {
         if (MASK_MODE == SWIN_MASK_REGION && tok < N) r = p.region[(size_t)win * N + tok];
         sTok[tok] = a | (r << 16);
     }
+    if (IN16) cp_async_wait_all();
     __syncthreads();
 
     // each warp walks the query tiles of this (window, head): rows warp*16 + k*112
@@ -202,6 +227,10 @@ swin_attn_core_kernel(AttnParams p) {
         for (int half_i = 0; half_i < 4; ++half_i) {
             const int r = (half_i & 1) ? r_hi : r_lo;
             const int c = ks * 16 + 2 * t4 + ((half_i & 2) ? 8 : 0);
+            if (IN16) {
+                qa[ks][half_i] = (r < N) ? __ldg(reinterpret_cast<const unsigned*>(p.q16 + (bh * (size_t)N + r) * 32 + c)) : 0u;
+                continue;
+            }
             float v0 = 0.f, v1 = 0.f;
             if (r < N) {
                 if (c < hd) v0 = __ldg(base + (size_t)r * C3 + c) * qs;

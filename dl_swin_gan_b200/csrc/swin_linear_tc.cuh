@@ -1,24 +1,35 @@
 // Linear layers of the window-attention block (qkv :146, proj :168 of
 // dl_cs/models/video_swin_transformer_mri_downsample.py) on the 5th-generation tensor cores:
-//     Y[M, N] = X[M, K] * W[N, K]^T + bias[N]        fp32 in / out, fp16 operands, fp32 accumulation in TMEM.
+//     Y[M, N] = X[M, K] * W[N, K]^T + bias[N]        fp16 operands, fp32 accumulation in TMEM.
 //
 // One persistent CTA per SM (128 threads).  W is converted to fp16 once per CTA and kept in shared memory in
 // the canonical no-swizzle K-major UMMA layout ([k/8][n/8][8 rows][8 halves]: core matrices of 8 x 16 bytes,
 // SBO = 128 B between row groups, LBO = (rows/8)*128 B between k chunks).  Per 128-row tile: the X rows are
 // converted and laid out the same way, one elected thread issues the tcgen05.mma chain (K/16 steps per N half,
 // N <= 256 per instruction), tcgen05.commit signals an mbarrier, and the four warps drain their 32 TMEM lanes
-// with tcgen05.ld, add the bias and store coalesced rows through a shared-memory transpose.
+// with tcgen05.ld.
+//
+// Fusions around the GEMM (template modes):
+//   A_LN_GATHER  rows are window tokens gathered from the feature volume [B,D,H,W,C] through the cyclic shift,
+//                LayerNorm'ed on the fly (norm1 + pad + roll + window_partition, :218-236); padded tokens are zero rows
+//   E_QKV16      the epilogue splits the 3C outputs into q (pre-scaled by scale*log2e), k [B_,heads,N,32] and
+//                v^T [B_,heads,32,N] as fp16, the layouts the attention core stages with plain 16-byte copies
+//   E_SCATTER    the epilogue writes each row to its place in [B,D,H,W,C] (window_reverse + roll back + crop, :238-248)
 // CUDA-only (no host emulation: tcgen05 / TMEM have no software model here); validated on the B200 against
-// torch.nn.functional.linear in tests/test_swin_gpu.py.
+// torch in tests/test_swin_gpu.py.
 #pragma once
 
 #include "cuda_compat.h"
+#include "swin_kernels.cuh"
 
 #if defined(__CUDACC__)
 namespace dlsg {
 
 constexpr int kLinThreads = 128;
 constexpr int kLinTileM = 128;
+
+enum : int { A_PLAIN = 0, A_LN_GATHER = 1 };
+enum : int { E_PLAIN = 0, E_QKV16 = 1, E_SCATTER = 2 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -56,32 +67,47 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float* v) {
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld4(unsigned taddr, float* v) {
+    unsigned* r = reinterpret_cast<unsigned*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 struct LinearParams {
-    const float* x;      // [M, K]
+    const float* x;      // A_PLAIN: [M, K];  A_LN_GATHER: feature volume [B, D, H, W, C = K]
     const float* w;      // [N, K]
     const float* bias;   // [N] or NULL
-    float* y;            // [M, N]
+    float* y;            // E_PLAIN: [M, N];  E_SCATTER: feature volume [B, D, H, W, N]
     int M, N, K;
     int tmem_cols;       // power of two >= N, >= 32
+    // A_LN_GATHER / E_SCATTER: rows are window tokens of this geometry (M = B*nW*tokens)
+    SwinGeom g;
+    const float* gamma; const float* beta; float eps;
+    // E_QKV16
+    half_t* q16; half_t* k16; half_t* vt16;     // [B_,heads,Ntok,32], [B_,heads,Ntok,32], [B_,heads,32,Ntok]
+    int heads, hd, ntok;
+    float qscale;        // scale * log2(e), folded into q
 };
 
-// dynamic smem: W fp16 [K/8][N/8][8][8] | A fp16 [K/8][16][8][8] (reused as the epilogue transpose) | bias fp32 [N] | ctrl
 __host__ __device__ inline size_t linear_a_region_bytes(int K) {      // A tile, reused as 4 x [32][33] fp32 transpose buffers
     const size_t a = (size_t)kLinTileM * K * 2, st = (size_t)(kLinThreads / 32) * 32 * 33 * 4;
     return ((a > st ? a : st) + 127) / 128 * 128;
 }
+// dynamic smem: W fp16 | A fp16 (reused by the epilogue) | bias fp32 [N] | row offsets int64 [128] | ctrl
 inline size_t linear_smem_bytes(int N, int K) {
-    return (size_t)N * K * 2 + linear_a_region_bytes(K) + (size_t)N * 4 + 64;
+    return (size_t)N * K * 2 + linear_a_region_bytes(K) + (size_t)N * 4 + (size_t)kLinTileM * 8 + 64;
 }
 
+template <int AMODE, int EMODE>
 __global__ void __launch_bounds__(kLinThreads, 1) swin_linear_tc_kernel(LinearParams p) {
     extern __shared__ __align__(128) unsigned char lin_smem[];
     const int N = p.N, K = p.K, KC = K / 8;
     half_t* sW = reinterpret_cast<half_t*>(lin_smem);
     half_t* sA = sW + (size_t)N * K;
     float* sBias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sA) + linear_a_region_bytes(K));
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sBias + N);
+    long long* sRowOff = reinterpret_cast<long long*>(sBias + N);           // destination offset of each tile row, -1 = dropped
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sRowOff + kLinTileM);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(mbar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned lboW = (unsigned)(N / 8) * 128u, lboA = (unsigned)(kLinTileM / 8) * 128u;
@@ -109,17 +135,59 @@ __global__ void __launch_bounds__(kLinThreads, 1) swin_linear_tc_kernel(LinearPa
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const unsigned tmem_base = *tmem_slot;
 
+    const int ntok = swin_tokens(p.g), nwin = swin_windows(p.g);   // only meaningful for the gather / scatter modes
     const int ntiles = (p.M + kLinTileM - 1) / kLinTileM;
     unsigned phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // ---- A tile: thread = row; fp32 -> fp16, canonical layout (rows beyond M are zero)
         const int row = tile * kLinTileM + tid;
-        const float* xr = p.x + (size_t)row * K;
+        const float* xr = nullptr;
+        float mu = 0.f, rstd = 1.f;
+        if (AMODE == A_PLAIN) {
+            if (row < p.M) xr = p.x + (size_t)row * K;
+        }
+        if (AMODE == A_LN_GATHER || EMODE == E_SCATTER) {
+            long long off = -1;
+            if (row < p.M) {
+                const int tok = row % ntok;
+                const int bw = row / ntok;
+                const int win = bw % nwin, b = bw / nwin;
+                int d, h, w;
+                if (swin_token_coords(p.g, win, tok, d, h, w))
+                    off = (((long long)b * p.g.D + d) * p.g.H + h) * p.g.W + w;          // token index in [B, D, H, W]
+            }
+            if (EMODE == E_SCATTER) sRowOff[tid] = off;
+            if (AMODE == A_LN_GATHER && off >= 0) {
+                xr = p.x + (size_t)off * K;
+                float s = 0.f, ss = 0.f;
+                for (int kc = 0; kc < K / 4; ++kc) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(xr) + kc);
+                    s += (a.x + a.y) + (a.z + a.w);
+                }
+                mu = s / (float)K;
+                for (int kc = 0; kc < K / 4; ++kc) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(xr) + kc);
+                    const float d0 = a.x - mu, d1 = a.y - mu, d2 = a.z - mu, d3 = a.w - mu;
+                    ss += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+                }
+                rstd = 1.0f / sqrtf(ss / (float)K + p.eps);
+            }
+        }
         for (int kc = 0; kc < KC; ++kc) {
             uint4 h = make_uint4(0u, 0u, 0u, 0u);
-            if (row < p.M) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc + 4));
+            if (xr) {
+                float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc));
+                float4 b = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc + 4));
+                if (AMODE == A_LN_GATHER) {
+                    const float4 g0 = p.gamma ? __ldg(reinterpret_cast<const float4*>(p.gamma + 8 * kc)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 g1 = p.gamma ? __ldg(reinterpret_cast<const float4*>(p.gamma + 8 * kc + 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 b0 = p.beta ? __ldg(reinterpret_cast<const float4*>(p.beta + 8 * kc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 b1 = p.beta ? __ldg(reinterpret_cast<const float4*>(p.beta + 8 * kc + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    a.x = fmaf((a.x - mu) * rstd, g0.x, b0.x); a.y = fmaf((a.y - mu) * rstd, g0.y, b0.y);
+                    a.z = fmaf((a.z - mu) * rstd, g0.z, b0.z); a.w = fmaf((a.w - mu) * rstd, g0.w, b0.w);
+                    b.x = fmaf((b.x - mu) * rstd, g1.x, b1.x); b.y = fmaf((b.y - mu) * rstd, g1.y, b1.y);
+                    b.z = fmaf((b.z - mu) * rstd, g1.z, b1.z); b.w = fmaf((b.w - mu) * rstd, g1.w, b1.w);
+                }
                 h.x = pack_h2(a.x, a.y); h.y = pack_h2(a.z, a.w); h.z = pack_h2(b.x, b.y); h.w = pack_h2(b.z, b.w);
             }
             *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(sA) + (size_t)kc * lboA + (size_t)(tid >> 3) * 128 + (tid & 7) * 16) = h;
@@ -151,19 +219,59 @@ __global__ void __launch_bounds__(kLinThreads, 1) swin_linear_tc_kernel(LinearPa
             phase ^= 1u;
         }
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 (= tile rows); 32 columns at a time through a smem transpose
-        float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);
-        const int row0 = tile * kLinTileM + warp * 32;
-        for (int c0 = 0; c0 < N; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)c0, v);
+        const unsigned tlane = tmem_base + ((unsigned)(warp * 32) << 16);    // warp w owns TMEM lanes 32w..32w+31 (= tile rows)
+        if (EMODE == E_QKV16) {
+            // thread = token row; per (q|k|v, head) group of hd columns: fp16 rows of 32 for q / k, columns of v^T
+            const int C = p.heads * p.hd;
+            const bool live = row < p.M;                      // tcgen05.ld is warp-collective: only the stores are predicated
+            const int tok = live ? row % p.ntok : 0, bw = live ? row / p.ntok : 0;
+            for (int which = 0; which < 3; ++which) {
+                for (int head = 0; head < p.heads; ++head) {
+                    const int c0 = which * C + head * p.hd;
+                    float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j] + sBias[c0 + j];
-            __syncwarp();
-            for (int r = 0; r < 32; ++r) {
-                if (row0 + r < p.M) p.y[(size_t)(row0 + r) * N + c0 + lane] = stage[r * 33 + lane];
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        if (4 * j4 < p.hd) tmem_ld4(tlane + (unsigned)(c0 + 4 * j4), v + 4 * j4);
+                    tmem_ld_wait();
+                    const float sc = (which == 0) ? p.qscale : 1.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (j < p.hd) ? (v[j] + sBias[c0 + (j < p.hd ? j : 0)]) * sc : 0.f;
+                    const size_t bh = (size_t)bw * p.heads + head;
+                    if (live && which < 2) {
+                        uint4* dst = reinterpret_cast<uint4*>((which == 0 ? p.q16 : p.k16) + (bh * p.ntok + tok) * 32);
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            dst[q4] = make_uint4(pack_h2(v[8 * q4], v[8 * q4 + 1]), pack_h2(v[8 * q4 + 2], v[8 * q4 + 3]),
+                                                 pack_h2(v[8 * q4 + 4], v[8 * q4 + 5]), pack_h2(v[8 * q4 + 6], v[8 * q4 + 7]));
+                    } else if (live) {
+                        half_t* dst = p.vt16 + bh * 32 * (size_t)p.ntok + tok;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dst[(size_t)j * p.ntok] = f2h(v[j]);
+                    }
+                }
             }
-            __syncwarp();
+        } else {
+            // 32 columns at a time through a shared-memory transpose so that rows are written contiguously
+            float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);
+            const int row0 = tile * kLinTileM + warp * 32;
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                float v[32];
+                tmem_ld32(tlane + (unsigned)c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j] + sBias[c0 + j];
+                __syncwarp();
+                for (int r = 0; r < 32; ++r) {
+                    if (EMODE == E_SCATTER) {
+                        const long long off = sRowOff[warp * 32 + r];
+                        if (off >= 0) p.y[(size_t)off * N + c0 + lane] = stage[r * 33 + lane];
+                    } else {
+                        if (row0 + r < p.M) p.y[(size_t)(row0 + r) * N + c0 + lane] = stage[r * 33 + lane];
+                    }
+                }
+                __syncwarp();
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncthreads();                                      // TMEM drained and the A / stage region free for the next tile

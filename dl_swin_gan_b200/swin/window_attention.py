@@ -335,9 +335,14 @@ class SwinTransformerBlock3D(nn.Module):
         shifted = any(i > 0 for i in shift_size)
         Dp, Hp, Wp = (-(-n // w) * w for n, w in zip((D, H, W), window_size))
         fused = (isinstance(self.norm1, nn.LayerNorm) and not (torch.is_grad_enabled() and (
-            x.requires_grad or any(p.requires_grad for p in self.norm1.parameters()))))
+            x.requires_grad or any(p.requires_grad for p in self.parameters()))))
         if fused:
             _require_cuda_f32(x, "SwinTransformerBlock3D input")
+            rid = _region_ids_for(mask_matrix, Dp, Hp, Wp, window_size, shift_size, x.device) if shifted else None
+            y = self._part1_tensor_core(x.contiguous(), window_size, shift_size,
+                                        mask_matrix if shifted else None, rid)
+            if y is not None:
+                return y
             x_windows = _ln_partition(x.contiguous(), self.norm1, window_size, shift_size)
         else:                                                  # differentiable route: same ops as the reference
             xn = self.norm1(x)
@@ -357,6 +362,56 @@ class SwinTransformerBlock3D(nn.Module):
         if shifted:
             shifted_x = torch.roll(shifted_x, shifts=(shift_size[0], shift_size[1], shift_size[2]), dims=(1, 2, 3))
         return shifted_x[:, :D, :H, :W, :].contiguous()
+
+    def _part1_tensor_core(self, x, window_size, shift_size, mask, rid):
+        """Three launches for the whole of forward_part1 (inference):
+        [LN + pad + roll + partition + qkv] tcgen05 GEMM -> attention core on fp16 q/k/v^T -> [proj + reverse + roll + crop]
+        tcgen05 GEMM.  Returns None when the shape is outside what those kernels cover (the caller then takes the
+        un-fused kernels)."""
+        attn = self.attn
+        B, D, H, W, C = x.shape
+        heads = attn.num_heads
+        hd = C // heads
+        N = window_size[0] * window_size[1] * window_size[2]
+        smem_ok = lambda n_out: n_out * C * 2 + max(256 * C, 16896) + 4 * n_out + 1088 + 64 <= 227 * 1024
+        if not (attn.tc_linear and C % 16 == 0 and C % 32 == 0 and 3 * C <= 512 and ((3 * C) // 2) % 16 == 0
+                and hd <= 32 and hd % 4 == 0 and N % 8 == 0 and smem_ok(3 * C) and smem_ok(C)
+                and attn.qkv.in_features == C and attn.proj.out_features == C):
+            return None
+        if mask is not None and rid is None:
+            _require_cuda_f32(mask, "attention mask")
+        lib = _lib.load()
+        Dp, Hp, Wp = (-(-n // w) * w for n, w in zip((D, H, W), window_size))
+        nW = (Dp // window_size[0]) * (Hp // window_size[1]) * (Wp // window_size[2])
+        B_ = B * nW
+        dev = x.device
+        q16 = torch.empty((B_, heads, N, 32), dtype=torch.float16, device=dev)
+        k16 = torch.empty_like(q16)
+        vt16 = torch.empty((B_, heads, 32, N), dtype=torch.float16, device=dev)
+        core = torch.empty((B_, N, C), dtype=torch.float32, device=dev)
+        y = torch.empty((B, D, H, W, C), dtype=torch.float32, device=dev)
+        n1 = self.norm1
+        opt = lambda t: t.detach().contiguous().data_ptr() if t is not None else None
+        with torch.cuda.device(dev):
+            st = lib.dlsg_swin_qkv_fused_f32(
+                x.data_ptr(), opt(n1.weight), opt(n1.bias), float(n1.eps), opt(attn.qkv.weight), opt(attn.qkv.bias),
+                q16.data_ptr(), k16.data_ptr(), vt16.data_ptr(), B, D, H, W, C, _i3(window_size), _i3(shift_size),
+                heads, float(attn.scale), _stream())
+            _lib.check(st, "dlsg_swin_qkv_fused")
+            if rid is not None:
+                mode, mptr = MASK_REGION, rid.data_ptr()
+            elif mask is not None:
+                mode, mptr = MASK_DENSE, mask.contiguous().data_ptr()
+            else:
+                mode, mptr = MASK_NONE, None
+            st = lib.dlsg_swin_window_attention_f16(
+                q16.data_ptr(), k16.data_ptr(), vt16.data_ptr(), opt(attn.relative_position_bias_table), core.data_ptr(),
+                B_, N, heads, hd, _i3(attn.window_size), mode, mptr, nW, _stream())
+            _lib.check(st, "dlsg_swin_window_attention_f16")
+            st = lib.dlsg_swin_proj_scatter_f32(core.data_ptr(), opt(attn.proj.weight), opt(attn.proj.bias), y.data_ptr(),
+                                                B, D, H, W, C, _i3(window_size), _i3(shift_size), _stream())
+            _lib.check(st, "dlsg_swin_proj_scatter")
+        return y
 
     def forward_part2(self, x):
         return self.drop_path(self.mlp(self.norm2(x)))

@@ -121,6 +121,27 @@ int dlsg_swin_window_attention_f32(const float* qkv, const float* bias_table, fl
                                    int B_, int N, int heads, int head_dim, const int* module_window, float scale,
                                    int mask_mode, const void* mask, int nW, void* stream);
 
+/* Attention core on fp16 q / k / v^T as written by dlsg_swin_qkv_fused_f32:
+ *   q16 [B_, heads, N, 32] (already multiplied by scale*log2(e)), k16 [B_, heads, N, 32], vt16 [B_, heads, 32, N]; N % 8 == 0.
+ * Everything else as dlsg_swin_window_attention_f32. */
+int dlsg_swin_window_attention_f16(const void* q16, const void* k16, const void* vt16, const float* bias_table, float* out,
+                                   int B_, int N, int heads, int head_dim, const int* module_window,
+                                   int mask_mode, const void* mask, int nW, void* stream);
+
+/* norm1 + pad + roll + window_partition + qkv Linear (:218-236 and :146) as ONE tcgen05 GEMM: the A rows are window tokens
+ * gathered from x [B,D,H,W,C] through the cyclic shift and LayerNorm'ed on the fly; the epilogue writes the fp16 triple above
+ * (q pre-scaled by scale*log2(e)).  weight [3C, C], bias [3C] or NULL, gamma / beta [C] or NULL.  head_dim = C/heads <= 32,
+ * head_dim % 4 == 0, tokens per window % 8 == 0, C % 16 == 0. */
+int dlsg_swin_qkv_fused_f32(const float* x, const float* gamma, const float* beta, float eps,
+                            const float* weight, const float* bias, void* q16, void* k16, void* vt16,
+                            int B, int D, int H, int W, int C, const int* window, const int* shift,
+                            int heads, float scale, void* stream);
+
+/* proj Linear (:168) + window_reverse + reverse shift + crop (:238-248) as ONE tcgen05 GEMM: rows of attn_out [B*nW*N, C]
+ * are projected and written to their place in y [B,D,H,W,C]; rows of padded tokens are dropped. */
+int dlsg_swin_proj_scatter_f32(const float* attn_out, const float* weight, const float* bias, float* y,
+                               int B, int D, int H, int W, int C, const int* window, const int* shift, void* stream);
+
 /* Linear layer on the tcgen05 tensor cores (qkv :146 and proj :168 of WindowAttention3D):
  *     y[M, N] = x[M, K] @ weight[N, K]^T + bias[N]       (torch.nn.functional.linear semantics)
  * fp32 in/out, fp16 operands, fp32 accumulation in tensor memory.  K % 16 == 0, N % 32 == 0, N <= 512,

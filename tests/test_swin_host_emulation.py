@@ -19,6 +19,7 @@ def lib(sense_emu_lib):
     lib.dlsg_swin_ln_partition_f32.argtypes = [vp, vp, vp, cf, vp] + [ci] * 5 + [vp, vp, vp]
     lib.dlsg_swin_window_reverse_f32.argtypes = [vp, vp] + [ci] * 5 + [vp, vp, vp]
     lib.dlsg_swin_window_attention_f32.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, cf, ci, vp, ci, vp]
+    lib.dlsg_swin_window_attention_f16.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, vp]
     return lib
 
 
@@ -102,6 +103,39 @@ def test_attention_core(lib, name, mode):
                                             hd ** -0.5, *args, None)
     assert st == 0
     assert rel_l2(out, ref) < 1e-3          # north_star: 1e-3 relative for the tensor-core attention
+
+
+@pytest.mark.parametrize("name", ["small_shift", "small_pad_shift"])
+def test_attention_core_fp16_inputs(lib, name):
+    """The layout the fused qkv GEMM writes: q16 (pre-scaled by scale*log2e) / k16 [B_,heads,N,32], v^T [B_,heads,32,N]."""
+    c = swin_case(name)
+    x, p = c["x"], c["params"]
+    B, D, H, W, C = x.shape
+    heads, hd = c["heads"], C // c["heads"]
+    ws, ss = sw.get_window_size((D, H, W), c["window"], c["shift"])
+    Dp, Hp, Wp = (int(np.ceil(n / w)) * w for n, w in zip((D, H, W), ws))
+    nW, N = (Dp // ws[0]) * (Hp // ws[1]) * (Wp // ws[2]), ws[0] * ws[1] * ws[2]
+    rng = np.random.default_rng(6)
+    xw = rng.standard_normal((B * nW, N, C)).astype(np.float32)
+    qkv = (xw @ p["attn.qkv.weight"].T + p["attn.qkv.bias"]).astype(np.float32).reshape(B * nW, N, 3, heads, hd)
+    scale = hd ** -0.5
+    q16 = np.zeros((B * nW, heads, N, 32), np.float16)
+    k16 = np.zeros((B * nW, heads, N, 32), np.float16)
+    vt16 = np.zeros((B * nW, heads, 32, N), np.float16)
+    q16[..., :hd] = (qkv[:, :, 0].transpose(0, 2, 1, 3) * scale * np.log2(np.e)).astype(np.float16)
+    k16[..., :hd] = qkv[:, :, 1].transpose(0, 2, 1, 3).astype(np.float16)
+    vt16[:, :, :hd, :] = qkv[:, :, 2].transpose(0, 2, 3, 1).astype(np.float16)
+    mask = sw.compute_mask(Dp, Hp, Wp, ws, ss).astype(np.float32)
+    rid = np.ascontiguousarray(region_ids(Dp, Hp, Wp, ws, ss))
+    ap = {k[5:]: v for k, v in p.items() if k.startswith("attn.")}
+    ap["proj.weight"], ap["proj.bias"] = np.eye(C), np.zeros(C)
+    ref = sw.window_attention(xw.astype(np.float64), ap, heads, c["window"], mask)
+    out = np.full((B * nW, N, C), np.nan, np.float32)
+    table = np.ascontiguousarray(p["attn.relative_position_bias_table"])
+    st = lib.dlsg_swin_window_attention_f16(ptr(q16), ptr(k16), ptr(vt16), ptr(table), ptr(out), B * nW, N, heads, hd,
+                                            i3(c["window"]), 1, ptr(rid), nW, None)
+    assert st == 0
+    assert rel_l2(out, ref) < 1e-3
 
 
 def test_status_codes(lib):
