@@ -70,6 +70,7 @@ inline int launch(K kernel, dim3 grid, dim3 block, size_t smem, stream_t s, A...
 #else  // ---------------------------------------------------------------- host emulation
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -113,6 +114,16 @@ extern dim3 g_blockDim, g_gridDim;
 #define gridDim (dlsg_emu::g_gridDim)
 static inline void __syncthreads() { dlsg_emu::t_ctx->block_bar->wait(); }
 static inline void __syncwarp() { dlsg_emu::t_ctx->warp_bars[dlsg_emu::t_threadIdx.x >> 5]->wait(); }
+static inline int __syncthreads_or(int pred) {
+    static std::atomic<int> acc{0};              // blocks run one at a time in the emulation
+    if (pred) acc.store(1);
+    __syncthreads();
+    const int r = acc.load();
+    __syncthreads();
+    if (dlsg_emu::t_threadIdx.x == 0) acc.store(0);
+    __syncthreads();
+    return r;
+}
 static inline void sincospif(float a, float* s, float* c) {
     const double pi = 3.14159265358979323846;
     *s = (float)std::sin(pi * (double)a); *c = (float)std::cos(pi * (double)a);

@@ -87,7 +87,11 @@ static int linear_launch(dlsg::LinearParams& p, void* stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = (p.M + kLinTileM - 1) / kLinTileM;
-    const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+    // two co-resident CTAs per SM (each with its own <= 256 TMEM columns) when shared memory allows: one CTA's
+    // A-load / epilogue then overlaps the other's MMA
+    const int per_sm = (linear_smem_bytes(p.N, p.K) + 1024 <= (227 * 1024) / 2 && p.tmem_cols <= 256) ? 2 : 1;
+    const int slots = sms * per_sm;
+    const unsigned grid = (unsigned)(ntiles < slots ? ntiles : slots);
     return launch(swin_linear_tc_kernel<AMODE, EMODE>, dim3(grid), dim3(kLinThreads), linear_smem_bytes(p.N, p.K),
                   (stream_t)stream, p) == 0 ? DLSG_OK : DLSG_ELAUNCH;
 }

@@ -205,15 +205,19 @@ swin_attn_core_kernel(AttnParams p) {
     }
     for (int i = tid; i < p.table_len; i += blockDim.x) sTab[i] = __ldg(p.table + (size_t)i * p.heads + head) * kLog2e;
     const int c_h = 2 * p.mww - 1, c_d = (2 * p.mwh - 1) * c_h;
+    int mixed_local = 0;
     for (int tok = tid; tok < p.npad; tok += blockDim.x) {
         const int tw = tok % p.mww, th = (tok / p.mww) % p.mwh, td = tok / (p.mww * p.mwh);
         const int a = (tok < N) ? td * c_d + th * c_h + tw : 0;   // padded tokens stay inside the table
         int r = 0;
         if (MASK_MODE == SWIN_MASK_REGION && tok < N) r = p.region[(size_t)win * N + tok];
         sTok[tok] = a | (r << 16);
+        if (MASK_MODE == SWIN_MASK_REGION && tok < N && r != (int)p.region[(size_t)win * N]) mixed_local = 1;
     }
     if (IN16) cp_async_wait_all();
-    __syncthreads();
+    // interior windows of a shifted block hold a single region: their mask is all zero and the test is skipped
+    const bool masked = (MASK_MODE == SWIN_MASK_REGION) ? (__syncthreads_or(mixed_local) != 0) : (MASK_MODE == SWIN_MASK_DENSE);
+    if (MASK_MODE != SWIN_MASK_REGION) __syncthreads();
 
     // each warp walks the query tiles of this (window, head): rows warp*16 + k*112
     for (int row0 = warp * 16; row0 < N; row0 += kAttnRows) {
@@ -259,6 +263,7 @@ swin_attn_core_kernel(AttnParams p) {
     const float kMasked = -100.0f * kLog2e;
 
     for (int kb = 0; kb < p.npad; kb += kAttnKB) {
+        const bool ragged = kb + kAttnKB > N;               // only the last key block can hold padded keys
         // ---- S = Q K^T for 64 keys: 8 n8 tiles, 2 k16 steps
         float s[8][4];
 #pragma unroll
@@ -284,13 +289,15 @@ swin_attn_core_kernel(AttnParams p) {
                 float v_lo = s[nt][e] + sTab[a_lo - aj];
                 float v_hi = s[nt][2 + e] + sTab[a_hi - aj];
                 if (MASK_MODE == SWIN_MASK_REGION) {
-                    const int rj = tj >> 16;
-                    if (rj != rg_lo) v_lo += kMasked;
-                    if (rj != rg_hi) v_hi += kMasked;
+                    if (masked) {
+                        const int rj = tj >> 16;
+                        if (rj != rg_lo) v_lo += kMasked;
+                        if (rj != rg_hi) v_hi += kMasked;
+                    }
                 } else if (MASK_MODE == SWIN_MASK_DENSE) {
                     if (j < N) { v_lo = fmaf(__ldg(mrow_lo + j), kLog2e, v_lo); v_hi = fmaf(__ldg(mrow_hi + j), kLog2e, v_hi); }
                 }
-                if (j >= N) { v_lo = -INFINITY; v_hi = -INFINITY; }          // padded keys never contribute
+                if (ragged && j >= N) { v_lo = -INFINITY; v_hi = -INFINITY; }   // padded keys never contribute
                 s[nt][e] = v_lo; s[nt][2 + e] = v_hi;
                 bm_lo = fmaxf(bm_lo, v_lo); bm_hi = fmaxf(bm_hi, v_hi);
             }

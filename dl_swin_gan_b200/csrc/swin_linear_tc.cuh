@@ -100,7 +100,7 @@ inline size_t linear_smem_bytes(int N, int K) {
 }
 
 template <int AMODE, int EMODE>
-__global__ void __launch_bounds__(kLinThreads, 1) swin_linear_tc_kernel(LinearParams p) {
+__global__ void __launch_bounds__(kLinThreads, 2) swin_linear_tc_kernel(LinearParams p) {
     extern __shared__ __align__(128) unsigned char lin_smem[];
     const int N = p.N, K = p.K, KC = K / 8;
     half_t* sW = reinterpret_cast<half_t*>(lin_smem);

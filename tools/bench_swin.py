@@ -44,6 +44,32 @@ for shift in (False, True):
         t_core = bench.time_op(core, 10, dev)
         t_eager = bench.time_op(eager, 5, dev)
         err = float((blk.forward_part1(x, mask) - eager()).norm() / eager().norm())
+    # the three fused launches one by one
+    import ctypes
+    from dl_swin_gan_b200 import _lib
+    lib = _lib.load()
+    heads_, hd = heads, C // heads
+    N = 448
+    B_ = B * 30
+    q16 = torch.empty((B_, heads, N, 32), dtype=torch.float16, device=dev); k16 = torch.empty_like(q16)
+    vt16 = torch.empty((B_, heads, 32, N), dtype=torch.float16, device=dev)
+    core_o = torch.empty((B_, N, C), device=dev); yv = torch.empty_like(x)
+    i3 = wa._i3
+    att = blk.attn
+    def f_qkv():
+        lib.dlsg_swin_qkv_fused_f32(x.data_ptr(), blk.norm1.weight.data_ptr(), blk.norm1.bias.data_ptr(), 1e-5, att.qkv.weight.data_ptr(),
+                                    att.qkv.bias.data_ptr(), q16.data_ptr(), k16.data_ptr(), vt16.data_ptr(), B, D, H, W, C, i3(ws), i3(ss),
+                                    heads, float(att.scale), wa._stream())
+    def f_core():
+        lib.dlsg_swin_window_attention_f16(q16.data_ptr(), k16.data_ptr(), vt16.data_ptr(), tab.data_ptr(), core_o.data_ptr(), B_, N, heads, hd,
+                                           i3(ws0), 1 if shift else 0, rid.data_ptr() if shift else None, 30, wa._stream())
+    def f_proj():
+        lib.dlsg_swin_proj_scatter_f32(core_o.data_ptr(), att.proj.weight.data_ptr(), att.proj.bias.data_ptr(), yv.data_ptr(), B, D, H, W, C,
+                                       i3(ws), i3(ss), wa._stream())
+    f_qkv(); f_core(); f_proj()
+    parts = {"qkv_fused_ms": round(bench.time_op(f_qkv, 10, dev), 4), "core16_ms": round(bench.time_op(f_core, 10, dev), 4),
+             "proj_scatter_ms": round(bench.time_op(f_proj, 10, dev), 4)}
+    print(json.dumps(parts), flush=True)
     nwin = B * mask.shape[0] if shift else B * 30
     flops_core = 4.0 * 448 * 448 * 160 * nwin
     print(json.dumps({"shift": shift, "slices": B, "windows": nwin, "part1_fused_ms": round(t_fused, 3), "core_ms": round(t_core, 3),
