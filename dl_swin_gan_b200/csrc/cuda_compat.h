@@ -147,6 +147,16 @@ static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
     __syncwarp();
     return r;
 }
+static inline float __shfl_sync(unsigned, float v, int src_lane) {
+    auto* ws = &dlsg_emu::t_ctx->scratch[dlsg_emu::t_threadIdx.x >> 5];
+    const int lane = dlsg_emu::t_threadIdx.x & 31;
+    ws->f[lane] = v;
+    __syncwarp();
+    const float r = ws->f[src_lane & 31];
+    __syncwarp();
+    return r;
+}
+struct int2 { int x, y; };
 // emulation of mma.sync.m16n8k16 (f16 x f16 -> f32) with the PTX ISA fragment layouts
 static inline void mma_m16n8k16_f16(float* c, const unsigned* a, unsigned b0, unsigned b1) {
     auto* ws = &dlsg_emu::t_ctx->scratch[dlsg_emu::t_threadIdx.x >> 5];

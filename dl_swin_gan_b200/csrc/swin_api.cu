@@ -53,20 +53,23 @@ static int attention_common(const float* qkv, const void* q16, const void* k16, 
     p.npad = (N + kAttnKB - 1) / kAttnKB * kAttnKB;
     p.vstride = p.npad + 8;
     p.table_len = (int)table_len;
-    const size_t smem = attn_smem_bytes(p.npad, p.vstride, p.table_len);
+    const bool fast = (mww % 2 == 0) && (head_dim < kAttnHdPad);
+    const size_t smem = attn_smem_bytes(p.npad, p.vstride, p.table_len, fast);
     if (smem > 227 * 1024) return DLSG_EUNSUPPORTED;
     const dim3 grid(heads, B_), block(32 * kAttnWarps);
     stream_t st = (stream_t)stream;
     int rc;
-    if (in16) {
-        if (mask_mode == SWIN_MASK_NONE)        rc = launch(swin_attn_core_kernel<SWIN_MASK_NONE, true>, grid, block, smem, st, p);
-        else if (mask_mode == SWIN_MASK_REGION) rc = launch(swin_attn_core_kernel<SWIN_MASK_REGION, true>, grid, block, smem, st, p);
-        else                                    rc = launch(swin_attn_core_kernel<SWIN_MASK_DENSE, true>, grid, block, smem, st, p);
-    } else {
-        if (mask_mode == SWIN_MASK_NONE)        rc = launch(swin_attn_core_kernel<SWIN_MASK_NONE, false>, grid, block, smem, st, p);
-        else if (mask_mode == SWIN_MASK_REGION) rc = launch(swin_attn_core_kernel<SWIN_MASK_REGION, false>, grid, block, smem, st, p);
-        else                                    rc = launch(swin_attn_core_kernel<SWIN_MASK_DENSE, false>, grid, block, smem, st, p);
-    }
+#define DLSG_ATTN_LAUNCH(MM, I16, FS) rc = launch(swin_attn_core_kernel<MM, I16, FS>, grid, block, smem, st, p)
+#define DLSG_ATTN_PICK(MM)                                                   \
+    do {                                                                     \
+        if (in16) { if (fast) DLSG_ATTN_LAUNCH(MM, true, true); else DLSG_ATTN_LAUNCH(MM, true, false); }   \
+        else      { if (fast) DLSG_ATTN_LAUNCH(MM, false, true); else DLSG_ATTN_LAUNCH(MM, false, false); } \
+    } while (0)
+    if (mask_mode == SWIN_MASK_NONE)        DLSG_ATTN_PICK(SWIN_MASK_NONE);
+    else if (mask_mode == SWIN_MASK_REGION) DLSG_ATTN_PICK(SWIN_MASK_REGION);
+    else                                    DLSG_ATTN_PICK(SWIN_MASK_DENSE);
+#undef DLSG_ATTN_PICK
+#undef DLSG_ATTN_LAUNCH
     return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
 }
 

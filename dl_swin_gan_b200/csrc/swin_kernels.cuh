@@ -134,18 +134,22 @@ struct AttnParams {
     int table_len;
 };
 
-inline size_t attn_smem_bytes(int npad, int vstride, int table_len) {   // host-side sizing of the dynamic shared memory
-    return (size_t)npad * kAttnKStride * 2 + (size_t)kAttnHdPad * vstride * 2 + (size_t)table_len * 4 + (size_t)npad * 4;
+inline size_t attn_smem_bytes(int npad, int vstride, int table_len, bool fast) {   // host-side sizing of the dynamic shared memory
+    return (size_t)npad * kAttnKStride * 2 + (size_t)kAttnHdPad * vstride * 2 +
+           (size_t)(fast ? 2 * (table_len + 1) : table_len) * 4 + (size_t)npad * 4;
 }
 
-template <int MASK_MODE, bool IN16>
+// FAST: (a) the bias table is stored as pairs (tab[i], tab[i-1]) so that the two adjacent key columns a lane owns cost
+// one 8-byte load and the bias initialises the MMA accumulator; (b) row sums come out of the PV MMA through a column of
+// ones appended to V (head dim hd is free when hd < 32).  Needs an even module window width and hd < 32.
+template <int MASK_MODE, bool IN16, bool FAST>
 DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(32 * kAttnWarps, 2)
 swin_attn_core_kernel(AttnParams p) {
     DLSG_DYN_SMEM(unsigned char, smem_raw);
     half_t* sK = reinterpret_cast<half_t*>(smem_raw);                                   // [npad][kAttnKStride]
     half_t* sVt = sK + (size_t)p.npad * kAttnKStride;                                   // [kAttnHdPad][vstride]
     float* sTab = reinterpret_cast<float*>(sVt + (size_t)kAttnHdPad * p.vstride);       // [table_len], * log2e
-    int* sTok = reinterpret_cast<int*>(sTab + p.table_len);                             // [npad]: a(t) | region << 16
+    int* sTok = reinterpret_cast<int*>(sTab + (FAST ? 2 * (p.table_len + 1) : p.table_len));   // [npad]: a(t) | region << 16
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
@@ -169,6 +173,7 @@ swin_attn_core_kernel(AttnParams p) {
         const int vch = N / 8;
         for (int i = tid; i < kAttnHdPad * vch; i += blockDim.x) {
             const int dd = i / vch, ch = i - dd * vch;
+            if (FAST && dd == hd) continue;                  // that row becomes the column of ones
             cp_async16(sVt + (size_t)dd * p.vstride + 8 * ch, vg + (size_t)dd * N + 8 * ch);
         }
         for (int i = tid; i < (p.npad - N) * kAttnHdPad; i += blockDim.x) {          // padded keys: zero rows / columns
@@ -200,10 +205,20 @@ swin_attn_core_kernel(AttnParams p) {
         kdst[0] = pack_h2(kv[0], kv[1]);
         kdst[1] = pack_h2(kv[2], kv[3]);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) sVt[(size_t)(dd + e) * p.vstride + tok] = f2h(vv[e]);
+        for (int e = 0; e < 4; ++e)
+            if (!(FAST && dd + e == hd)) sVt[(size_t)(dd + e) * p.vstride + tok] = f2h(vv[e]);
     }
     }
-    for (int i = tid; i < p.table_len; i += blockDim.x) sTab[i] = __ldg(p.table + (size_t)i * p.heads + head) * kLog2e;
+    if (FAST) {                                              // sTab as float2 pairs: [i] = (tab[i], tab[i-1])
+        float2* sTabP = reinterpret_cast<float2*>(sTab);
+        for (int i = tid; i <= p.table_len; i += blockDim.x) {
+            const float hi = (i < p.table_len) ? __ldg(p.table + (size_t)i * p.heads + head) * kLog2e : 0.f;
+            const float lo = (i > 0) ? __ldg(p.table + (size_t)(i - 1) * p.heads + head) * kLog2e : 0.f;
+            sTabP[i] = make_float2(hi, lo);
+        }
+    } else {
+        for (int i = tid; i < p.table_len; i += blockDim.x) sTab[i] = __ldg(p.table + (size_t)i * p.heads + head) * kLog2e;
+    }
     const int c_h = 2 * p.mww - 1, c_d = (2 * p.mwh - 1) * c_h;
     int mixed_local = 0;
     for (int tok = tid; tok < p.npad; tok += blockDim.x) {
@@ -213,6 +228,9 @@ swin_attn_core_kernel(AttnParams p) {
         if (MASK_MODE == SWIN_MASK_REGION && tok < N) r = p.region[(size_t)win * N + tok];
         sTok[tok] = a | (r << 16);
         if (MASK_MODE == SWIN_MASK_REGION && tok < N && r != (int)p.region[(size_t)win * N]) mixed_local = 1;
+    }
+    if (FAST) {                                              // V^T row hd = 1 for real keys, 0 for padded keys: PV then yields the row sums
+        for (int tok = tid; tok < p.npad; tok += blockDim.x) sVt[(size_t)hd * p.vstride + tok] = f2h(tok < N ? 1.f : 0.f);
     }
     if (IN16) cp_async_wait_all();
     // interior windows of a shifted block hold a single region: their mask is all zero and the test is skipped
@@ -264,43 +282,53 @@ swin_attn_core_kernel(AttnParams p) {
 
     for (int kb = 0; kb < p.npad; kb += kAttnKB) {
         const bool ragged = kb + kAttnKB > N;               // only the last key block can hold padded keys
-        // ---- S = Q K^T for 64 keys: 8 n8 tiles, 2 k16 steps
+        // ---- S = bias + Q K^T for 64 keys: 8 n8 tiles, 2 k16 steps (+ mask), running max
         float s[8][4];
+        float bm_lo = -INFINITY, bm_hi = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            const int j0 = kb + nt * 8 + 2 * t4;
+            int tj0, tj1;
+            if (FAST) {
+                const int2 tt = *reinterpret_cast<const int2*>(sTok + j0);       // j0 is even: 8-byte aligned
+                tj0 = tt.x; tj1 = tt.y;
+                const float2 b_lo = reinterpret_cast<const float2*>(sTab)[a_lo - (tj0 & 0xffff)];
+                const float2 b_hi = reinterpret_cast<const float2*>(sTab)[a_hi - (tj0 & 0xffff)];
+                s[nt][0] = b_lo.x; s[nt][1] = b_lo.y; s[nt][2] = b_hi.x; s[nt][3] = b_hi.y;
+            } else {
+                tj0 = sTok[j0]; tj1 = sTok[j0 + 1];
+                s[nt][0] = sTab[a_lo - (tj0 & 0xffff)]; s[nt][1] = sTab[a_lo - (tj1 & 0xffff)];
+                s[nt][2] = sTab[a_hi - (tj0 & 0xffff)]; s[nt][3] = sTab[a_hi - (tj1 & 0xffff)];
+            }
             const half_t* kp = sK + (size_t)(kb + nt * 8 + g) * kAttnKStride + 2 * t4;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 const unsigned b0 = lds_u32(kp + ks * 16), b1 = lds_u32(kp + ks * 16 + 8);
                 mma_m16n8k16_f16(s[nt], qa[ks], b0, b1);
             }
-        }
-        // ---- + bias (+ mask), running max
-        float bm_lo = -INFINITY, bm_hi = -INFINITY;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const int j0 = kb + nt * 8 + 2 * t4;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int j = j0 + e;
-                const int tj = sTok[j];
-                const int aj = tj & 0xffff;
-                float v_lo = s[nt][e] + sTab[a_lo - aj];
-                float v_hi = s[nt][2 + e] + sTab[a_hi - aj];
-                if (MASK_MODE == SWIN_MASK_REGION) {
-                    if (masked) {
-                        const int rj = tj >> 16;
-                        if (rj != rg_lo) v_lo += kMasked;
-                        if (rj != rg_hi) v_hi += kMasked;
-                    }
-                } else if (MASK_MODE == SWIN_MASK_DENSE) {
-                    if (j < N) { v_lo = fmaf(__ldg(mrow_lo + j), kLog2e, v_lo); v_hi = fmaf(__ldg(mrow_hi + j), kLog2e, v_hi); }
+            if (MASK_MODE == SWIN_MASK_REGION) {
+                if (masked) {
+                    const int r0 = tj0 >> 16, r1 = tj1 >> 16;
+                    if (r0 != rg_lo) s[nt][0] += kMasked;
+                    if (r1 != rg_lo) s[nt][1] += kMasked;
+                    if (r0 != rg_hi) s[nt][2] += kMasked;
+                    if (r1 != rg_hi) s[nt][3] += kMasked;
                 }
-                if (ragged && j >= N) { v_lo = -INFINITY; v_hi = -INFINITY; }   // padded keys never contribute
-                s[nt][e] = v_lo; s[nt][2 + e] = v_hi;
-                bm_lo = fmaxf(bm_lo, v_lo); bm_hi = fmaxf(bm_hi, v_hi);
+            } else if (MASK_MODE == SWIN_MASK_DENSE) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (j0 + e < N) {
+                        s[nt][e] = fmaf(__ldg(mrow_lo + j0 + e), kLog2e, s[nt][e]);
+                        s[nt][2 + e] = fmaf(__ldg(mrow_hi + j0 + e), kLog2e, s[nt][2 + e]);
+                    }
             }
+            if (ragged) {                                    // padded keys never contribute (last block only)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (j0 + e >= N) { s[nt][e] = -INFINITY; s[nt][2 + e] = -INFINITY; }
+            }
+            bm_lo = fmaxf(bm_lo, fmaxf(s[nt][0], s[nt][1]));
+            bm_hi = fmaxf(bm_hi, fmaxf(s[nt][2], s[nt][3]));
         }
         bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 1));
         bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
@@ -321,7 +349,7 @@ swin_attn_core_kernel(AttnParams p) {
                 const int nt = 2 * kk + h2;
                 const float p0 = fast_exp2(s[nt][0] - m_lo), p1 = fast_exp2(s[nt][1] - m_lo);
                 const float p2 = fast_exp2(s[nt][2] - m_hi), p3 = fast_exp2(s[nt][3] - m_hi);
-                l_lo += p0 + p1; l_hi += p2 + p3;
+                if (!FAST) { l_lo += p0 + p1; l_hi += p2 + p3; }
                 pa[2 * h2] = pack_h2(p0, p1);
                 pa[2 * h2 + 1] = pack_h2(p2, p3);
             }
@@ -335,8 +363,20 @@ swin_attn_core_kernel(AttnParams p) {
         }
     }
     // ---- normalise and store  out[bwin, row, head*hd + d]
-    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
-    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    if (FAST) {                                              // the row sums sit in output column hd (lanes with 2*t4 == hd % 8 ...)
+        float sl = 0.f, sh = 0.f;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (dn * 8 + 2 * t4 + e == hd) { sl = o[dn][e]; sh = o[dn][2 + e]; }
+        const int src = (lane & ~3) | ((hd & 7) >> 1);
+        l_lo = __shfl_sync(0xffffffffu, sl, src);
+        l_hi = __shfl_sync(0xffffffffu, sh, src);
+    } else {
+        l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+        l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    }
     const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;
     float* obase = p.out + (size_t)bwin * N * (p.heads * hd) + head * hd;
 #pragma unroll

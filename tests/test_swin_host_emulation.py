@@ -138,6 +138,22 @@ def test_attention_core_fp16_inputs(lib, name):
     assert rel_l2(out, ref) < 1e-3
 
 
+def test_attention_core_generic_path_odd_window_width(lib):
+    """Odd window width: no (tab[i], tab[i-1]) pairing, explicit row sums (the non-FAST template instance)."""
+    rng = np.random.default_rng(8)
+    window, heads, C = (2, 3, 3), 2, 16
+    N, hd, B_ = 18, 8, 3
+    table = (0.5 * rng.standard_normal(((2 * 2 - 1) * 5 * 5, heads))).astype(np.float32)
+    p = {"relative_position_bias_table": table, "qkv.weight": (rng.standard_normal((3 * C, C)) / 4).astype(np.float32),
+         "qkv.bias": np.zeros(3 * C, np.float32), "proj.weight": np.eye(C), "proj.bias": np.zeros(C)}
+    xw = rng.standard_normal((B_, N, C)).astype(np.float32)
+    qkv = (xw @ p["qkv.weight"].T).astype(np.float32)
+    ref = sw.window_attention(xw.astype(np.float64), p, heads, window, None)
+    out = np.full((B_, N, C), np.nan, np.float32)
+    st = lib.dlsg_swin_window_attention_f32(ptr(qkv), ptr(table), ptr(out), B_, N, heads, hd, i3(window), hd ** -0.5, 0, None, 1, None)
+    assert st == 0 and rel_l2(out, ref) < 1e-3
+
+
 def test_status_codes(lib):
     z = np.zeros(64, np.float32)
     w = i3((2, 4, 4))
