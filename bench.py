@@ -204,6 +204,33 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------- window attention (second half of the hot path)
+def swin_block_timing(dev, slices=8):
+    """forward_part1 of one Swin block (LN, shift, partition, qkv, attention, proj, reverse) for `slices` cine slices at the
+    hard-coded denoiser configuration (dim 160, 8 heads, window (7,8,8), feature volume 7x48x40), shifted block."""
+    from dl_swin_gan_b200.swin import window_attention as wa
+    torch.manual_seed(0)
+    D, H, W, C, heads = 7, 48, 40, 160, 8
+    blk = wa.SwinTransformerBlock3D(C, heads, (7, 8, 8), (3, 4, 4), qkv_bias=True).to(dev).eval()
+    x = torch.randn(slices, D, H, W, C, device=dev)
+    ws, ss = wa.get_window_size((D, H, W), (7, 8, 8), (3, 4, 4))
+    mask = wa.compute_mask(7, 48, 40, ws, ss, dev)
+    with torch.no_grad():
+        n0 = _lib_launches()
+        ms = time_op(lambda: blk.forward_part1(x, mask), 10, dev)
+        launches = (_lib_launches() - n0) // 12
+    windows = slices * mask.shape[0]
+    useful = windows * (2 * 448 * 160 * 480 + 4 * 448 * 448 * 160 + 2 * 448 * 160 * 160)      # qkv + QK^T/PV + proj
+    return {"what": "SwinTransformerBlock3D.forward_part1, shifted, fp16 tensor-core operands", "slices": slices,
+            "windows": windows, "ms": ms, "us_per_slice": 1e3 * ms / slices, "useful_TFLOPs": useful / (ms * 1e-3) / 1e12,
+            "launches_per_call": launches}
+
+
+def _lib_launches():
+    from dl_swin_gan_b200 import _lib
+    return int(_lib.load().dlsg_launch_count())
+
+
 # --------------------------------------------------------------------------- main arm
 def time_op(fn, iters, dev):
     for _ in range(2):
@@ -227,6 +254,7 @@ def main():
     ap.add_argument("--batch", type=int, default=WORKLOAD["B"], help="slices per GPU (default: the config's 64)")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-swin", action="store_true", help="skip the window-attention side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -341,6 +369,10 @@ def main():
         e2e = {"value": world * B * n_e2e / el, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e}
 
+    swin = None
+    if rank == 0 and not args.skip_swin:
+        swin = swin_block_timing(dev)
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         rate, threads, sample = cpu_port_rate(cfg)
@@ -354,7 +386,7 @@ def main():
             "config": {"workload": "config_recon.yaml", **cfg, "slices_per_gpu": B,
                        "l2": "working set per step (y 2.5 GB + x/maps/mask) >> 126 MB L2, no flush needed",
                        "workspace_MB": float(os.environ.get("DLSG_WORKSPACE_MB", 4096))},
-            "roofline": roofline, "ops": ops, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "ops": ops, "swin_window_attention": swin, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

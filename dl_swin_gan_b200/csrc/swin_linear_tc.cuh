@@ -25,7 +25,7 @@
 #if defined(__CUDACC__)
 namespace dlsg {
 
-constexpr int kLinThreads = 128;
+constexpr int kLinThreads = 256;              // 8 warps: two threads per tile row, two warps per TMEM lane quarter
 constexpr int kLinTileM = 128;
 
 enum : int { A_PLAIN = 0, A_LN_GATHER = 1 };
@@ -94,20 +94,21 @@ __host__ __device__ inline size_t linear_a_region_bytes(int K) {      // A tile,
     const size_t a = (size_t)kLinTileM * K * 2, st = (size_t)(kLinThreads / 32) * 32 * 33 * 4;
     return ((a > st ? a : st) + 127) / 128 * 128;
 }
-// dynamic smem: W fp16 | A fp16 (reused by the epilogue) | bias fp32 [N] | row offsets int64 [128] | ctrl
+// dynamic smem: W fp16 | A fp16 (reused by the epilogue) | bias fp32 [N] | row offsets int64 [128] | LN partials float2 [256] | ctrl
 inline size_t linear_smem_bytes(int N, int K) {
-    return (size_t)N * K * 2 + linear_a_region_bytes(K) + (size_t)N * 4 + (size_t)kLinTileM * 8 + 64;
+    return (size_t)N * K * 2 + linear_a_region_bytes(K) + (size_t)N * 4 + (size_t)kLinTileM * 8 + (size_t)kLinThreads * 8 + 64;
 }
 
 template <int AMODE, int EMODE>
-__global__ void __launch_bounds__(kLinThreads, 2) swin_linear_tc_kernel(LinearParams p) {
+__global__ void __launch_bounds__(kLinThreads, (EMODE == E_QKV16) ? 1 : 2) swin_linear_tc_kernel(LinearParams p) {
     extern __shared__ __align__(128) unsigned char lin_smem[];
     const int N = p.N, K = p.K, KC = K / 8;
     half_t* sW = reinterpret_cast<half_t*>(lin_smem);
     half_t* sA = sW + (size_t)N * K;
     float* sBias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sA) + linear_a_region_bytes(K));
     long long* sRowOff = reinterpret_cast<long long*>(sBias + N);           // destination offset of each tile row, -1 = dropped
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sRowOff + kLinTileM);
+    float2* sPart = reinterpret_cast<float2*>(sRowOff + kLinTileM);         // per-thread LayerNorm partial sums
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sPart + kLinThreads);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(mbar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned lboW = (unsigned)(N / 8) * 128u, lboA = (unsigned)(kLinTileM / 8) * 128u;
@@ -139,10 +140,11 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_linear_tc_kernel(LinearPa
     const int ntiles = (p.M + kLinTileM - 1) / kLinTileM;
     unsigned phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---- A tile: thread = row; fp32 -> fp16, canonical layout (rows beyond M are zero)
-        const int row = tile * kLinTileM + tid;
+        // ---- A tile: two threads per row (each one half of K); fp32 -> fp16, canonical layout (rows beyond M are zero)
+        const int trow = tid & (kLinTileM - 1), khalf = tid >> 7;
+        const int row = tile * kLinTileM + trow;
+        const int kc0 = khalf * (KC / 2), kc1 = khalf ? KC : KC / 2;
         const float* xr = nullptr;
-        float mu = 0.f, rstd = 1.f;
         if (AMODE == A_PLAIN) {
             if (row < p.M) xr = p.x + (size_t)row * K;
         }
@@ -156,24 +158,33 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_linear_tc_kernel(LinearPa
                 if (swin_token_coords(p.g, win, tok, d, h, w))
                     off = (((long long)b * p.g.D + d) * p.g.H + h) * p.g.W + w;          // token index in [B, D, H, W]
             }
-            if (EMODE == E_SCATTER) sRowOff[tid] = off;
-            if (AMODE == A_LN_GATHER && off >= 0) {
-                xr = p.x + (size_t)off * K;
-                float s = 0.f, ss = 0.f;
-                for (int kc = 0; kc < K / 4; ++kc) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(xr) + kc);
-                    s += (a.x + a.y) + (a.z + a.w);
-                }
-                mu = s / (float)K;
-                for (int kc = 0; kc < K / 4; ++kc) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(xr) + kc);
-                    const float d0 = a.x - mu, d1 = a.y - mu, d2 = a.z - mu, d3 = a.w - mu;
-                    ss += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-                }
-                rstd = 1.0f / sqrtf(ss / (float)K + p.eps);
-            }
+            if (EMODE == E_SCATTER && khalf == 0) sRowOff[trow] = off;
+            if (AMODE == A_LN_GATHER && off >= 0) xr = p.x + (size_t)off * K;
         }
-        for (int kc = 0; kc < KC; ++kc) {
+        float mu = 0.f, rstd = 1.f;
+        if (AMODE == A_LN_GATHER) {
+            // one pass over this thread's half row: shifted sums (shift = first element of the row), combined through smem
+            float s1 = 0.f, s2 = 0.f, x0 = 0.f;
+            if (xr) {
+                x0 = __ldg(xr);
+                for (int kc = kc0; kc < kc1; ++kc) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc + 4));
+                    const float d0 = a.x - x0, d1 = a.y - x0, d2 = a.z - x0, d3 = a.w - x0;
+                    const float d4 = b.x - x0, d5 = b.y - x0, d6 = b.z - x0, d7 = b.w - x0;
+                    s1 += ((d0 + d1) + (d2 + d3)) + ((d4 + d5) + (d6 + d7));
+                    s2 += ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
+                }
+            }
+            sPart[tid] = make_float2(s1, s2);
+            __syncthreads();
+            const float2 o2 = sPart[tid ^ kLinTileM];
+            s1 += o2.x; s2 += o2.y;
+            const float m0 = s1 / (float)K;
+            mu = x0 + m0;
+            rstd = 1.0f / sqrtf(fmaxf(s2 / (float)K - m0 * m0, 0.f) + p.eps);
+        }
+        for (int kc = kc0; kc < kc1; ++kc) {
             uint4 h = make_uint4(0u, 0u, 0u, 0u);
             if (xr) {
                 float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc));
@@ -190,7 +201,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_linear_tc_kernel(LinearPa
                 }
                 h.x = pack_h2(a.x, a.y); h.y = pack_h2(a.z, a.w); h.z = pack_h2(b.x, b.y); h.w = pack_h2(b.z, b.w);
             }
-            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(sA) + (size_t)kc * lboA + (size_t)(tid >> 3) * 128 + (tid & 7) * 16) = h;
+            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(sA) + (size_t)kc * lboA + (size_t)(trow >> 3) * 128 + (trow & 7) * 16) = h;
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
         __syncthreads();
@@ -219,14 +230,16 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_linear_tc_kernel(LinearPa
             phase ^= 1u;
         }
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const unsigned tlane = tmem_base + ((unsigned)(warp * 32) << 16);    // warp w owns TMEM lanes 32w..32w+31 (= tile rows)
+        const int quarter = warp & 3, wsub = warp >> 2;                        // warps q and q+4 share TMEM lanes 32q..32q+31
+        const unsigned tlane = tmem_base + ((unsigned)(quarter * 32) << 16);
         if (EMODE == E_QKV16) {
             // thread = token row; per (q|k|v, head) group of hd columns: fp16 rows of 32 for q / k, columns of v^T
             const int C = p.heads * p.hd;
-            const bool live = row < p.M;                      // tcgen05.ld is warp-collective: only the stores are predicated
-            const int tok = live ? row % p.ntok : 0, bw = live ? row / p.ntok : 0;
+            const int erow = tile * kLinTileM + quarter * 32 + lane;
+            const bool live = erow < p.M;                     // tcgen05.ld is warp-collective: only the stores are predicated
+            const int tok = live ? erow % p.ntok : 0, bw = live ? erow / p.ntok : 0;
             for (int which = 0; which < 3; ++which) {
-                for (int head = 0; head < p.heads; ++head) {
+                for (int head = wsub; head < p.heads; head += 2) {
                     const int c0 = which * C + head * p.hd;
                     float v[32];
 #pragma unroll
@@ -255,8 +268,8 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_linear_tc_kernel(LinearPa
         } else {
             // 32 columns at a time through a shared-memory transpose so that rows are written contiguously
             float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);
-            const int row0 = tile * kLinTileM + warp * 32;
-            for (int c0 = 0; c0 < N; c0 += 32) {
+            const int row0 = tile * kLinTileM + quarter * 32;
+            for (int c0 = wsub * 32; c0 < N; c0 += 64) {
                 float v[32];
                 tmem_ld32(tlane + (unsigned)c0, v);
 #pragma unroll
@@ -264,7 +277,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_linear_tc_kernel(LinearPa
                 __syncwarp();
                 for (int r = 0; r < 32; ++r) {
                     if (EMODE == E_SCATTER) {
-                        const long long off = sRowOff[warp * 32 + r];
+                        const long long off = sRowOff[quarter * 32 + r];
                         if (off >= 0) p.y[(size_t)off * N + c0 + lane] = stage[r * 33 + lane];
                     } else {
                         if (row0 + r < p.M) p.y[(size_t)(row0 + r) * N + c0 + lane] = stage[r * 33 + lane];

@@ -248,7 +248,7 @@ class WindowAttention3D(nn.Module):
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or layer.weight.requires_grad)
         K, N = layer.in_features, layer.out_features
         if (self.tc_linear and not needs_grad and K % 16 == 0 and N % 32 == 0 and N <= 512
-                and (N <= 256 or (N // 2) % 16 == 0) and N * K * 2 + max(256 * K, 16896) + 4 * N + 192 <= 227 * 1024):
+                and (N <= 256 or (N // 2) % 16 == 0) and N * K * 2 + max(256 * K, 33792) + 4 * N + 3328 <= 227 * 1024):
             return linear_tc(x, layer.weight, layer.bias)
         return layer(x)
 
@@ -373,7 +373,7 @@ class SwinTransformerBlock3D(nn.Module):
         heads = attn.num_heads
         hd = C // heads
         N = window_size[0] * window_size[1] * window_size[2]
-        smem_ok = lambda n_out: n_out * C * 2 + max(256 * C, 16896) + 4 * n_out + 1088 + 64 <= 227 * 1024
+        smem_ok = lambda n_out: n_out * C * 2 + max(256 * C, 33792) + 4 * n_out + 3328 <= 227 * 1024
         if not (attn.tc_linear and C % 16 == 0 and C % 32 == 0 and 3 * C <= 512 and ((3 * C) // 2) % 16 == 0
                 and hd <= 32 and hd % 4 == 0 and N % 8 == 0 and smem_ok(3 * C) and smem_ok(C)
                 and attn.qkv.in_features == C and attn.proj.out_features == C):
