@@ -219,3 +219,29 @@ def test_unrolled_dc_path_matches_cpu_port(dev):
     nrmse = rel_l2(got.cpu().numpy(), want.numpy())
     assert nrmse < 1e-5, nrmse
     assert rel_l2(xi.cpu().numpy(), want.numpy()) < 1e-5
+
+
+def test_perfusion_shape_properties(dev):
+    """BASELINE config 4 shape (E=2, C=32, T=40, 256x256; 6 frames here): several coil groups per CTA, radix (8, 8)."""
+    B, E, C, T, Y, X = 1, 2, 32, 6, 256, 256
+    g = torch.Generator(device=dev).manual_seed(1004)
+
+    def cn(*s):
+        return torch.view_as_complex(torch.randn(*s, 2, generator=g, device=dev))
+
+    from dl_swin_gan_b200.mri import SenseModel
+    maps = cn(B, E, C, 1, Y, X) / (E * C) ** 0.5
+    mask = (torch.rand(B, 1, T, Y, 1, generator=g, device=dev) < 0.15).float().expand(B, 1, T, Y, X).contiguous()
+    A = SenseModel(maps, weights=mask)
+    x, y = cn(B, E, T, Y, X), cn(B, C, T, Y, X)
+    Ax, Ahy = A(x), A(y, adjoint=True)
+    lhs, rhs = torch.vdot(y.flatten(), Ax.flatten()), torch.vdot(Ahy.flatten(), x.flatten())
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+    assert rel_l2(to_np(A.normal(x)), to_np(A(Ax, adjoint=True))) < 2e-6
+    # against torch.fft on the same device (the reference's own arithmetic, transforms.py:84-98)
+    from oracle import sense_oracle_torch as st
+    assert rel_l2(to_np(Ax), to_np(st.forward(x, maps, mask))) < TOL
+    assert rel_l2(to_np(Ahy), to_np(st.adjoint(y, maps, mask))) < TOL
+    aty = cn(B, E, T, Y, X)
+    want = x - 0.7 * (st.adjoint(st.forward(x, maps, mask), maps, mask) - aty)
+    assert rel_l2(to_np(A.dc_step(x, aty, -0.7)), to_np(want)) < TOL
