@@ -41,6 +41,16 @@ __device__ __forceinline__ unsigned pack_h2(float lo, float hi) {
     return *reinterpret_cast<const unsigned*>(&h);
 }
 __device__ __forceinline__ unsigned lds_u32(const half_t* p) { return *reinterpret_cast<const unsigned*>(p); }
+// four 8x8 b16 matrices from shared memory; lane L supplies the address of row L%8 of matrix L/8 (16-byte aligned).
+// r[i] of lane t = (M_i[t/4][2(t%4)], M_i[t/4][2(t%4)+1]);  with .trans = (M_i[2(t%4)][t/4], M_i[2(t%4)+1][t/4])
+__device__ __forceinline__ void ldmatrix_x4(unsigned* r, const half_t* row_ptr) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(row_ptr);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(unsigned* r, const half_t* row_ptr) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(row_ptr);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
 // D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col); fragment layouts per PTX ISA "mma.m16n8k16"
 __device__ __forceinline__ void mma_m16n8k16_f16(float* c, const unsigned* a, unsigned b0, unsigned b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -100,7 +110,7 @@ private:
     std::mutex m_;
     std::condition_variable cv_;
 };
-struct WarpScratch { unsigned a[32][4]; unsigned b[32][2]; float f[32]; };
+struct WarpScratch { unsigned a[32][4]; unsigned b[32][2]; float f[32]; const void* ptr[32]; };
 struct BlockCtx { Barrier* block_bar; std::vector<Barrier*> warp_bars; unsigned char* smem; WarpScratch* scratch; };
 extern thread_local dim3 t_threadIdx;
 extern thread_local dim3 t_blockIdx;
@@ -157,6 +167,24 @@ static inline float __shfl_sync(unsigned, float v, int src_lane) {
     return r;
 }
 struct int2 { int x, y; };
+// emulation of ldmatrix.m8n8.x4(.trans).b16 with the PTX ISA thread/row mapping
+static inline void ldmatrix_x4_impl(unsigned* r, const half_t* row_ptr, bool trans) {
+    auto* ws = &dlsg_emu::t_ctx->scratch[dlsg_emu::t_threadIdx.x >> 5];
+    const int lane = dlsg_emu::t_threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    ws->ptr[lane] = row_ptr;
+    __syncwarp();
+    for (int i = 0; i < 4; ++i) {
+        half_t e[2];
+        for (int h = 0; h < 2; ++h) {
+            const int row = trans ? 2 * t4 + h : g, col = trans ? g : 2 * t4 + h;
+            e[h] = static_cast<const half_t*>(ws->ptr[8 * i + row])[col];
+        }
+        std::memcpy(&r[i], e, 4);
+    }
+    __syncwarp();
+}
+static inline void ldmatrix_x4(unsigned* r, const half_t* row_ptr) { ldmatrix_x4_impl(r, row_ptr, false); }
+static inline void ldmatrix_x4_trans(unsigned* r, const half_t* row_ptr) { ldmatrix_x4_impl(r, row_ptr, true); }
 // emulation of mma.sync.m16n8k16 (f16 x f16 -> f32) with the PTX ISA fragment layouts
 static inline void mma_m16n8k16_f16(float* c, const unsigned* a, unsigned b0, unsigned b1) {
     auto* ws = &dlsg_emu::t_ctx->scratch[dlsg_emu::t_threadIdx.x >> 5];

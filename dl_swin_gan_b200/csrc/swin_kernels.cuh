@@ -121,7 +121,7 @@ struct AttnParams {
     const float* qkv;        // [B_, N, 3, heads, hd] fp32 (output of the qkv Linear, untouched); NULL when the fp16 triple is given
     const half_t* q16;       // [B_, heads, N, 32] fp16, already multiplied by scale*log2(e)   (written by the fused qkv GEMM)
     const half_t* k16;       // [B_, heads, N, 32] fp16
-    const half_t* vt16;      // [B_, heads, 32, N] fp16
+    const half_t* vt16;      // v16 [B_, heads, N, 32] fp16 (same row layout as k16; column head_dim holds 1.0 when head_dim < 32)
     const float* table;      // relative_position_bias_table [(2Wd-1)(2Wh-1)(2Ww-1), heads] fp32
     const unsigned char* region;   // [nW, N] region ids (SWIN_MASK_REGION)
     const float* mask;       // [nW, N, N] additive mask (SWIN_MASK_DENSE)
@@ -130,12 +130,13 @@ struct AttnParams {
     int mwd, mwh, mww;       // the MODULE's window size (bias table geometry, :115-129)
     float scale;
     int npad;                // N rounded up to a multiple of kAttnKB
-    int vstride;             // halves per V^T row in smem
+    int vstride;             // unused (V shares the K row stride)
     int table_len;
 };
 
 inline size_t attn_smem_bytes(int npad, int vstride, int table_len, bool fast) {   // host-side sizing of the dynamic shared memory
-    return (size_t)npad * kAttnKStride * 2 + (size_t)kAttnHdPad * vstride * 2 +
+    (void)vstride;
+    return (size_t)npad * kAttnKStride * 2 * 2 +
            (size_t)(fast ? 2 * (table_len + 1) : table_len) * 4 + (size_t)npad * 4;
 }
 
@@ -147,8 +148,8 @@ DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(32 * kAttnWarps, 2)
 swin_attn_core_kernel(AttnParams p) {
     DLSG_DYN_SMEM(unsigned char, smem_raw);
     half_t* sK = reinterpret_cast<half_t*>(smem_raw);                                   // [npad][kAttnKStride]
-    half_t* sVt = sK + (size_t)p.npad * kAttnKStride;                                   // [kAttnHdPad][vstride]
-    float* sTab = reinterpret_cast<float*>(sVt + (size_t)kAttnHdPad * p.vstride);       // [table_len], * log2e
+    half_t* sV = sK + (size_t)p.npad * kAttnKStride;                                    // [npad][kAttnKStride] (row = key, like K)
+    float* sTab = reinterpret_cast<float*>(sV + (size_t)p.npad * kAttnKStride);         // [table_len], * log2e
     int* sTok = reinterpret_cast<int*>(sTab + (FAST ? 2 * (p.table_len + 1) : p.table_len));   // [npad]: a(t) | region << 16
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -165,21 +166,19 @@ swin_attn_core_kernel(AttnParams p) {
     if (IN16) {
         // fp16 q / k / v^T straight from the fused qkv GEMM: plain 16-byte asynchronous copies (N % 8 == 0)
         const half_t* kg = p.k16 + bh * (size_t)N * 32;
-        const half_t* vg = p.vt16 + bh * 32 * (size_t)N;
+        const half_t* vg = p.vt16 + bh * (size_t)N * 32;
         for (int i = tid; i < N * 4; i += blockDim.x) {
             const int tok = i >> 2, ch = i & 3;
             cp_async16(sK + (size_t)tok * kAttnKStride + 8 * ch, kg + (size_t)tok * 32 + 8 * ch);
         }
-        const int vch = N / 8;
-        for (int i = tid; i < kAttnHdPad * vch; i += blockDim.x) {
-            const int dd = i / vch, ch = i - dd * vch;
-            if (FAST && dd == hd) continue;                  // that row becomes the column of ones
-            cp_async16(sVt + (size_t)dd * p.vstride + 8 * ch, vg + (size_t)dd * N + 8 * ch);
+        for (int i = tid; i < N * 4; i += blockDim.x) {
+            const int tok = i >> 2, ch = i & 3;
+            cp_async16(sV + (size_t)tok * kAttnKStride + 8 * ch, vg + (size_t)tok * 32 + 8 * ch);
         }
-        for (int i = tid; i < (p.npad - N) * kAttnHdPad; i += blockDim.x) {          // padded keys: zero rows / columns
+        for (int i = tid; i < (p.npad - N) * kAttnHdPad; i += blockDim.x) {          // padded keys: zero rows
             const int tok = N + i / kAttnHdPad, dd = i % kAttnHdPad;
             sK[(size_t)tok * kAttnKStride + dd] = f2h(0.f);
-            sVt[(size_t)dd * p.vstride + tok] = f2h(0.f);
+            sV[(size_t)tok * kAttnKStride + dd] = f2h(0.f);
         }
     } else {
     const bool vec4 = (hd % 4 == 0) && (((size_t)C3 * 4) % 16 == 0) && ((((size_t)head * hd + koff) * 4) % 16 == 0) &&
@@ -201,12 +200,13 @@ swin_attn_core_kernel(AttnParams p) {
                     if (dd + e < hd) { kv[e] = __ldg(kp + e); vv[e] = __ldg(vp + e); }
             }
         }
+        if (FAST && tok < N && dd <= hd && hd < dd + 4) vv[hd - dd] = 1.f;       // the column of ones (row sums through the PV MMA)
         unsigned* kdst = reinterpret_cast<unsigned*>(sK + (size_t)tok * kAttnKStride + dd);
         kdst[0] = pack_h2(kv[0], kv[1]);
         kdst[1] = pack_h2(kv[2], kv[3]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (!(FAST && dd + e == hd)) sVt[(size_t)(dd + e) * p.vstride + tok] = f2h(vv[e]);
+        unsigned* vdst = reinterpret_cast<unsigned*>(sV + (size_t)tok * kAttnKStride + dd);
+        vdst[0] = pack_h2(vv[0], vv[1]);
+        vdst[1] = pack_h2(vv[2], vv[3]);
     }
     }
     if (FAST) {                                              // sTab as float2 pairs: [i] = (tab[i], tab[i-1])
@@ -228,9 +228,6 @@ swin_attn_core_kernel(AttnParams p) {
         if (MASK_MODE == SWIN_MASK_REGION && tok < N) r = p.region[(size_t)win * N + tok];
         sTok[tok] = a | (r << 16);
         if (MASK_MODE == SWIN_MASK_REGION && tok < N && r != (int)p.region[(size_t)win * N]) mixed_local = 1;
-    }
-    if (FAST) {                                              // V^T row hd = 1 for real keys, 0 for padded keys: PV then yields the row sums
-        for (int tok = tid; tok < p.npad; tok += blockDim.x) sVt[(size_t)hd * p.vstride + tok] = f2h(tok < N ? 1.f : 0.f);
     }
     if (IN16) cp_async_wait_all();
     // interior windows of a shifted block hold a single region: their mask is all zero and the test is skipped
@@ -300,12 +297,10 @@ swin_attn_core_kernel(AttnParams p) {
                 s[nt][0] = sTab[a_lo - (tj0 & 0xffff)]; s[nt][1] = sTab[a_lo - (tj1 & 0xffff)];
                 s[nt][2] = sTab[a_hi - (tj0 & 0xffff)]; s[nt][3] = sTab[a_hi - (tj1 & 0xffff)];
             }
-            const half_t* kp = sK + (size_t)(kb + nt * 8 + g) * kAttnKStride + 2 * t4;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const unsigned b0 = lds_u32(kp + ks * 16), b1 = lds_u32(kp + ks * 16 + 8);
-                mma_m16n8k16_f16(s[nt], qa[ks], b0, b1);
-            }
+            unsigned kf[4];                                  // (b0, b1) of both k16 steps in one ldmatrix.x4
+            ldmatrix_x4(kf, sK + (size_t)(kb + nt * 8 + (lane & 7)) * kAttnKStride + 8 * (lane >> 3));
+            mma_m16n8k16_f16(s[nt], qa[0], kf[0], kf[1]);
+            mma_m16n8k16_f16(s[nt], qa[1], kf[2], kf[3]);
             if (MASK_MODE == SWIN_MASK_REGION) {
                 if (masked) {
                     const int r0 = tj0 >> 16, r1 = tj1 >> 16;
@@ -353,12 +348,14 @@ swin_attn_core_kernel(AttnParams p) {
                 pa[2 * h2] = pack_h2(p0, p1);
                 pa[2 * h2 + 1] = pack_h2(p2, p3);
             }
-            const int key0 = kb + kk * 16 + 2 * t4;
+            // V fragments: transposing ldmatrix on [key][dim] rows; one x4 = (b0, b1) of two output tiles
+            const half_t* vrow = sV + (size_t)(kb + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * kAttnKStride + 8 * (lane >> 4);
 #pragma unroll
-            for (int dn = 0; dn < 4; ++dn) {                // output dims dn*8 .. dn*8+7
-                const half_t* vp = sVt + (size_t)(dn * 8 + g) * p.vstride + key0;
-                const unsigned b0 = lds_u32(vp), b1 = lds_u32(vp + 8);
-                mma_m16n8k16_f16(o[dn], pa, b0, b1);
+            for (int dp = 0; dp < 2; ++dp) {                // output dims dp*16 .. dp*16+15
+                unsigned vf[4];
+                ldmatrix_x4_trans(vf, vrow + dp * 16);
+                mma_m16n8k16_f16(o[2 * dp], pa, vf[0], vf[1]);
+                mma_m16n8k16_f16(o[2 * dp + 1], pa, vf[2], vf[3]);
             }
         }
     }

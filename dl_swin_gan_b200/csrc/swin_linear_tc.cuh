@@ -12,8 +12,8 @@
 // Fusions around the GEMM (template modes):
 //   A_LN_GATHER  rows are window tokens gathered from the feature volume [B,D,H,W,C] through the cyclic shift,
 //                LayerNorm'ed on the fly (norm1 + pad + roll + window_partition, :218-236); padded tokens are zero rows
-//   E_QKV16      the epilogue splits the 3C outputs into q (pre-scaled by scale*log2e), k [B_,heads,N,32] and
-//                v^T [B_,heads,32,N] as fp16, the layouts the attention core stages with plain 16-byte copies
+//   E_QKV16      the epilogue splits the 3C outputs into q (pre-scaled by scale*log2e), k and v, each [B_,heads,N,32] fp16
+//                (v carries a column of ones at index head_dim), the layout the attention core stages with 16-byte copies
 //   E_SCATTER    the epilogue writes each row to its place in [B,D,H,W,C] (window_reverse + roll back + crop, :238-248)
 // CUDA-only (no host emulation: tcgen05 / TMEM have no software model here); validated on the B200 against
 // torch in tests/test_swin_gpu.py.
@@ -85,7 +85,7 @@ struct LinearParams {
     SwinGeom g;
     const float* gamma; const float* beta; float eps;
     // E_QKV16
-    half_t* q16; half_t* k16; half_t* vt16;     // [B_,heads,Ntok,32], [B_,heads,Ntok,32], [B_,heads,32,Ntok]
+    half_t* q16; half_t* k16; half_t* vt16;     // q, k, v: each [B_,heads,Ntok,32]
     int heads, hd, ntok;
     float qscale;        // scale * log2(e), folded into q
 };
@@ -251,17 +251,15 @@ __global__ void __launch_bounds__(kLinThreads, (EMODE == E_QKV16) ? 1 : 2) swin_
                     const float sc = (which == 0) ? p.qscale : 1.0f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = (j < p.hd) ? (v[j] + sBias[c0 + (j < p.hd ? j : 0)]) * sc : 0.f;
+                    if (which == 2 && p.hd < 32) v[p.hd] = 1.0f;          // column of ones: the attention core reads the softmax row sums off the PV MMA
                     const size_t bh = (size_t)bw * p.heads + head;
-                    if (live && which < 2) {
-                        uint4* dst = reinterpret_cast<uint4*>((which == 0 ? p.q16 : p.k16) + (bh * p.ntok + tok) * 32);
+                    if (live) {
+                        half_t* base16 = (which == 0) ? p.q16 : (which == 1 ? p.k16 : p.vt16);
+                        uint4* dst = reinterpret_cast<uint4*>(base16 + (bh * p.ntok + tok) * 32);
 #pragma unroll
                         for (int q4 = 0; q4 < 4; ++q4)
                             dst[q4] = make_uint4(pack_h2(v[8 * q4], v[8 * q4 + 1]), pack_h2(v[8 * q4 + 2], v[8 * q4 + 3]),
                                                  pack_h2(v[8 * q4 + 4], v[8 * q4 + 5]), pack_h2(v[8 * q4 + 6], v[8 * q4 + 7]));
-                    } else if (live) {
-                        half_t* dst = p.vt16 + bh * 32 * (size_t)p.ntok + tok;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) dst[(size_t)j * p.ntok] = f2h(v[j]);
                     }
                 }
             }

@@ -387,7 +387,7 @@ class SwinTransformerBlock3D(nn.Module):
         dev = x.device
         q16 = torch.empty((B_, heads, N, 32), dtype=torch.float16, device=dev)
         k16 = torch.empty_like(q16)
-        vt16 = torch.empty((B_, heads, 32, N), dtype=torch.float16, device=dev)
+        vt16 = torch.empty_like(q16)                      # v, same row layout (+ a column of ones at index head_dim)
         core = torch.empty((B_, N, C), dtype=torch.float32, device=dev)
         y = torch.empty((B, D, H, W, C), dtype=torch.float32, device=dev)
         n1 = self.norm1

@@ -121,10 +121,11 @@ int dlsg_swin_window_attention_f32(const float* qkv, const float* bias_table, fl
                                    int B_, int N, int heads, int head_dim, const int* module_window, float scale,
                                    int mask_mode, const void* mask, int nW, void* stream);
 
-/* Attention core on fp16 q / k / v^T as written by dlsg_swin_qkv_fused_f32:
- *   q16 [B_, heads, N, 32] (already multiplied by scale*log2(e)), k16 [B_, heads, N, 32], vt16 [B_, heads, 32, N]; N % 8 == 0.
+/* Attention core on fp16 q / k / v as written by dlsg_swin_qkv_fused_f32:
+ *   q16 (already multiplied by scale*log2(e)), k16, v16: each [B_, heads, N, 32], zero beyond head_dim except v16[..., head_dim] = 1
+ *   when head_dim < 32 (the softmax row sums then come out of the PV MMA); N % 8 == 0.
  * Everything else as dlsg_swin_window_attention_f32. */
-int dlsg_swin_window_attention_f16(const void* q16, const void* k16, const void* vt16, const float* bias_table, float* out,
+int dlsg_swin_window_attention_f16(const void* q16, const void* k16, const void* v16, const float* bias_table, float* out,
                                    int B_, int N, int heads, int head_dim, const int* module_window,
                                    int mask_mode, const void* mask, int nW, void* stream);
 
@@ -133,7 +134,7 @@ int dlsg_swin_window_attention_f16(const void* q16, const void* k16, const void*
  * (q pre-scaled by scale*log2(e)).  weight [3C, C], bias [3C] or NULL, gamma / beta [C] or NULL.  head_dim = C/heads <= 32,
  * head_dim % 4 == 0, tokens per window % 8 == 0, C % 16 == 0. */
 int dlsg_swin_qkv_fused_f32(const float* x, const float* gamma, const float* beta, float eps,
-                            const float* weight, const float* bias, void* q16, void* k16, void* vt16,
+                            const float* weight, const float* bias, void* q16, void* k16, void* v16,
                             int B, int D, int H, int W, int C, const int* window, const int* shift,
                             int heads, float scale, void* stream);
 

@@ -107,7 +107,7 @@ def test_attention_core(lib, name, mode):
 
 @pytest.mark.parametrize("name", ["small_shift", "small_pad_shift"])
 def test_attention_core_fp16_inputs(lib, name):
-    """The layout the fused qkv GEMM writes: q16 (pre-scaled by scale*log2e) / k16 [B_,heads,N,32], v^T [B_,heads,32,N]."""
+    """The layout the fused qkv GEMM writes: q16 (pre-scaled by scale*log2e), k16, v16, each [B_,heads,N,32]."""
     c = swin_case(name)
     x, p = c["x"], c["params"]
     B, D, H, W, C = x.shape
@@ -121,10 +121,11 @@ def test_attention_core_fp16_inputs(lib, name):
     scale = hd ** -0.5
     q16 = np.zeros((B * nW, heads, N, 32), np.float16)
     k16 = np.zeros((B * nW, heads, N, 32), np.float16)
-    vt16 = np.zeros((B * nW, heads, 32, N), np.float16)
+    vt16 = np.zeros((B * nW, heads, N, 32), np.float16)
     q16[..., :hd] = (qkv[:, :, 0].transpose(0, 2, 1, 3) * scale * np.log2(np.e)).astype(np.float16)
     k16[..., :hd] = qkv[:, :, 1].transpose(0, 2, 1, 3).astype(np.float16)
-    vt16[:, :, :hd, :] = qkv[:, :, 2].transpose(0, 2, 3, 1).astype(np.float16)
+    vt16[..., :hd] = qkv[:, :, 2].transpose(0, 2, 1, 3).astype(np.float16)
+    vt16[..., hd] = 1.0                                      # the column of ones the fused GEMM appends (head_dim < 32)
     mask = sw.compute_mask(Dp, Hp, Wp, ws, ss).astype(np.float32)
     rid = np.ascontiguousarray(region_ids(Dp, Hp, Wp, ws, ss))
     ap = {k[5:]: v for k, v in p.items() if k.startswith("attn.")}

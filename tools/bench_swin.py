@@ -52,7 +52,7 @@ for shift in (False, True):
     N = 448
     B_ = B * 30
     q16 = torch.empty((B_, heads, N, 32), dtype=torch.float16, device=dev); k16 = torch.empty_like(q16)
-    vt16 = torch.empty((B_, heads, 32, N), dtype=torch.float16, device=dev)
+    vt16 = torch.empty_like(q16)
     core_o = torch.empty((B_, N, C), device=dev); yv = torch.empty_like(x)
     i3 = wa._i3
     att = blk.attn
