@@ -269,6 +269,8 @@ swin_attn_core_kernel(AttnParams p) {
         mrow_hi = p.mask + ((size_t)win * N + min(r_hi, N - 1)) * N;
     }
 
+    const half_t* kfrag = sK + (lane & 7) * kAttnKStride + 8 * (lane >> 3);                        // this lane's ldmatrix row, key 0
+    const half_t* vfrag = sV + (((lane >> 3) & 1) * 8 + (lane & 7)) * kAttnKStride + 8 * (lane >> 4);
     float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
     float o[4][4];                                         // 16 x 32 output accumulator (4 n8 tiles)
 #pragma unroll
@@ -298,7 +300,7 @@ swin_attn_core_kernel(AttnParams p) {
                 s[nt][2] = sTab[a_hi - (tj0 & 0xffff)]; s[nt][3] = sTab[a_hi - (tj1 & 0xffff)];
             }
             unsigned kf[4];                                  // (b0, b1) of both k16 steps in one ldmatrix.x4
-            ldmatrix_x4(kf, sK + (size_t)(kb + nt * 8 + (lane & 7)) * kAttnKStride + 8 * (lane >> 3));
+            ldmatrix_x4(kf, kfrag + (kb + nt * 8) * kAttnKStride);
             mma_m16n8k16_f16(s[nt], qa[0], kf[0], kf[1]);
             mma_m16n8k16_f16(s[nt], qa[1], kf[2], kf[3]);
             if (MASK_MODE == SWIN_MASK_REGION) {
@@ -317,7 +319,9 @@ swin_attn_core_kernel(AttnParams p) {
                         s[nt][2 + e] = fmaf(__ldg(mrow_hi + j0 + e), kLog2e, s[nt][2 + e]);
                     }
             }
-            if (ragged) {                                    // padded keys never contribute (last block only)
+            // padded keys: with the ones column (FAST) their V row is all zero, so they add nothing to the numerator nor to
+            // the row sum whatever their score; only the explicit-sum variant has to push them to -inf (last block only)
+            if (!FAST && ragged) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
                     if (j0 + e >= N) { s[nt][e] = -INFINITY; s[nt][2 + e] = -INFINITY; }
@@ -349,7 +353,7 @@ swin_attn_core_kernel(AttnParams p) {
                 pa[2 * h2 + 1] = pack_h2(p2, p3);
             }
             // V fragments: transposing ldmatrix on [key][dim] rows; one x4 = (b0, b1) of two output tiles
-            const half_t* vrow = sV + (size_t)(kb + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * kAttnKStride + 8 * (lane >> 4);
+            const half_t* vrow = vfrag + (kb + kk * 16) * kAttnKStride;
 #pragma unroll
             for (int dp = 0; dp < 2; ++dp) {                // output dims dp*16 .. dp*16+15
                 unsigned vf[4];
