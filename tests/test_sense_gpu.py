@@ -245,3 +245,35 @@ def test_perfusion_shape_properties(dev):
     aty = cn(B, E, T, Y, X)
     want = x - 0.7 * (st.adjoint(st.forward(x, maps, mask), maps, mask) - aty)
     assert rel_l2(to_np(A.dc_step(x, aty, -0.7)), to_np(want)) < TOL
+
+
+def test_side_stream_and_cuda_graph_replay(dev):
+    """The C ABI enqueues on the caller's stream only: results on a side stream match, and a DC step captured into a
+    CUDA graph (step size read from device memory) replays correctly with new inputs."""
+    B, E, C, T, Y, X = 2, 1, 4, 3, 64, 96
+    maps, x, mask = so.synthetic_problem(B, E, C, T, Y, X, seed=21)
+    A = make_model(maps, mask, dev)
+    xd = torch.from_numpy(x).to(dev)
+    want = A(xd)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        got = A(xd)
+    side.synchronize()
+    assert torch.equal(got, want)
+
+    aty = A(want, adjoint=True)
+    step = torch.tensor([-1.5], device=dev)
+    static_x = xd.clone()
+    A.dc_step(static_x, aty, step)                      # warm-up outside capture (lazy preparation, allocator)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_out = A.dc_step(static_x, aty, step)
+    for scale, s in ((1.0, -1.5), (0.5, -0.25)):
+        static_x.copy_(xd * scale)
+        step.fill_(s)
+        graph.replay()
+        torch.cuda.synchronize()
+        ref = static_x + s * (A(A(static_x), adjoint=True) - aty)
+        assert rel_l2(to_np(static_out), to_np(ref)) < 2e-6

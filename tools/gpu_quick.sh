@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-SWEEP_MB=8192 timeout 600 python tools/sweep_workspace.py 2>&1 | grep workspace > gpurun_out/quick.log
-SWEEP_MB=8192 SWEEP_E=2 SWEEP_B=32 timeout 600 python tools/sweep_workspace.py 2>&1 | grep workspace >> gpurun_out/quick.log
-cat gpurun_out/quick.log
+timeout 600 python -m pytest tests/test_sense_gpu.py -m gpu -x -q 2>&1 | tail -5
+SWEEP_MB=8192 timeout 600 python tools/sweep_workspace.py 2>&1 | grep workspace
