@@ -335,9 +335,15 @@ def main():
                      "frac_hbm": nbytes / (t * 1e-3) / 1e9 / hbm_peak,
                      "TFLOPs_nominal": algorithmic_flops(name, B, E, C, T, Y, X) / (t * 1e-3) / 1e12}
     dom = "dc_step"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic_per_slice.json")
+    if os.path.exists(tpath) and (E, C, T, Y, X) == (1, 8, 20, 192, 160):
+        with open(tpath) as f:
+            traffic = json.load(f)["ops_MB_per_slice"][dom] * 1e6 * B      # ncu-measured DRAM bytes per launch chain
     roofline = {"bound": "hbm", "kernel": "fused DC step chain (rows_fwd + cols_normal + rows_adj)",
                 "achieved": ops[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": ops[dom]["frac_hbm"],
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": "ncu --set full, profiles/r1_dram_traffic_per_slice.json",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algorithmic_bytes(dom, B, E, C, T, Y, X, mask.numel())}
 
     # ---- end to end from pinned host memory through the same API
