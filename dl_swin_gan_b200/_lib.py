@@ -33,6 +33,7 @@ SIGNATURES = {
     "dlsg_sense_forward_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz] + _shape7 + [_vp]),
     "dlsg_sense_adjoint_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz] + _shape7 + [_vp]),
     "dlsg_sense_normal_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz] + _shape7 + [_vp]),
+    "dlsg_sense_normal_reg_c64": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _sz] + _shape7 + [_vp]),
     "dlsg_sense_dc_step_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _sz] + _shape7 + [_vp]),
     "dlsg_swin_ln_partition_f32": (_i, [_vp, _vp, _vp, _f, _vp] + [_i] * 5 + [_vp, _vp, _vp]),
     "dlsg_swin_window_reverse_f32": (_i, [_vp, _vp] + [_i] * 5 + [_vp, _vp, _vp]),

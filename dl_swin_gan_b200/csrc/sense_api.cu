@@ -363,6 +363,13 @@ int dlsg_sense_normal_c64(const void* x, const void* maps, const float* weights,
                      nullptr, 0.f, nullptr, dlsg::EPI_PLAIN, workspace, workspace_bytes, B, E, C, T, Y, X, ndims, stream);
 }
 
+int dlsg_sense_normal_reg_c64(const void* x, const void* maps, const float* weights, const long long* w_strides,
+                              float lamda, const float* lamda_dev, void* x_out, void* workspace, size_t workspace_bytes,
+                              int B, int E, int C, int T, int Y, int X, int ndims, void* stream) {
+    return dlsg::run(dlsg::OP_NORMAL, (const float2*)x, (const float2*)maps, weights, w_strides, (float2*)x_out,
+                     nullptr, lamda, lamda_dev, dlsg::EPI_REG, workspace, workspace_bytes, B, E, C, T, Y, X, ndims, stream);
+}
+
 int dlsg_sense_dc_step_c64(const void* x, const void* aty, const void* maps, const float* weights,
                            const long long* w_strides, float step, const float* step_dev, void* x_out,
                            void* workspace, size_t workspace_bytes,

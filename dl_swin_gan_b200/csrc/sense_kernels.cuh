@@ -54,7 +54,7 @@ struct SenseDims {
 struct WeightStrides { long long b, c, t, y, x; };
 
 enum : int { MODE_FWD = 0, MODE_ADJ = 1, MODE_NORMAL = 2 };
-enum : int { EPI_PLAIN = 0, EPI_DC = 1 };
+enum : int { EPI_PLAIN = 0, EPI_DC = 1, EPI_REG = 2 };   // REG: out = acc + step * xin  (A^H A x + lambda x, the MoDL normal equations)
 
 DLSG_DEVICE size_t idx_x(const SenseDims& d, int b, int e, int t, int y) {
     return ((((size_t)b * d.E + e) * d.T + t) * d.Y + y) * (size_t)d.X;
@@ -321,7 +321,7 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
 
         // x and A^H y rows of frame t for the DC epilogue, fetched asynchronously when the frame is started
         auto stage_dc = [&](int t) {
-            if (last_group && epi == EPI_DC) {
+            if (last_group && epi != EPI_PLAIN) {
                 __syncwarp();                    // the previous frame's epilogue has read the buffer
                 for (int e = 0; e < ne; ++e) {
                     const size_t base = idx_x(d, b, e0 + e, t, y);
@@ -330,7 +330,7 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
                         const int q = lane + 32 * m;
                         if ((X / 2) % 32 == 0 || q < X / 2) {
                             cp_async16(dcb + e * X + 2 * q, xin + base + 2 * q);
-                            cp_async16(dcb + (EMAX + e) * X + 2 * q, aty + base + 2 * q);
+                            if (epi == EPI_DC) cp_async16(dcb + (EMAX + e) * X + 2 * q, aty + base + 2 * q);
                         }
                     }
                 }
@@ -338,7 +338,7 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
             }
         };
         auto flush = [&](int t) {
-            if (last_group && epi == EPI_DC) { cp_async_wait_group0(); __syncwarp(); }
+            if (last_group && epi != EPI_PLAIN) { cp_async_wait_group0(); __syncwarp(); }
 #pragma unroll
             for (int e = 0; e < EMAX; ++e) {
                 if (e < ne) {
@@ -350,6 +350,9 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
                         if (last_group && epi == EPI_DC) {
                             const float2 xv = dcb[e * X + lane + 32 * j], av = dcb[(EMAX + e) * X + lane + 32 * j];
                             r = make_float2(fmaf(step, r.x - av.x, xv.x), fmaf(step, r.y - av.y, xv.y));
+                        } else if (last_group && epi == EPI_REG) {
+                            const float2 xv = dcb[e * X + lane + 32 * j];
+                            r = make_float2(fmaf(step, xv.x, r.x), fmaf(step, xv.y, r.y));
                         }
                         out[base + 32 * j] = r;
                         acc[e][j] = make_float2(0.f, 0.f);
@@ -700,6 +703,9 @@ sense_rows_adj_direct_kernel(const float2* __restrict__ src, const float2* __res
         if (epi == EPI_DC) {
             const float2 xv = __ldg(xin + g), av = __ldg(aty + g);
             r = make_float2(fmaf(step, r.x - av.x, xv.x), fmaf(step, r.y - av.y, xv.y));
+        } else if (epi == EPI_REG) {
+            const float2 xv = __ldg(xin + g);
+            r = make_float2(fmaf(step, xv.x, r.x), fmaf(step, xv.y, r.y));
         }
         out[g] = r;
     }

@@ -44,7 +44,7 @@ def _require_cuda_c64(t: torch.Tensor, what: str) -> None:
 # --------------------------------------------------------------------------------------
 def _launch(kind: str, data: torch.Tensor, maps5: Optional[torch.Tensor], wexp: Optional[torch.Tensor],
             dims, ndims: int, aty: Optional[torch.Tensor] = None, step=None) -> torch.Tensor:
-    """kind in {'fwd','adj','normal','dc'}; dims = (B,E,C,T,Y,X); tensors already validated/contiguous."""
+    """kind in {'fwd','adj','normal','reg','dc'}; dims = (B,E,C,T,Y,X); tensors already validated/contiguous."""
     lib = _lib.load()
     B, E, C, T, Y, X = dims
     dev = data.device
@@ -69,6 +69,12 @@ def _launch(kind: str, data: torch.Tensor, maps5: Optional[torch.Tensor], wexp: 
             st = lib.dlsg_sense_adjoint_c64(data.data_ptr(), mptr, wptr, wstr, out.data_ptr(), *tail)
         elif kind == "normal":
             st = lib.dlsg_sense_normal_c64(data.data_ptr(), mptr, wptr, wstr, out.data_ptr(), *tail)
+        elif kind == "reg":
+            if isinstance(step, torch.Tensor):
+                lam_host, lam_dev = 0.0, step.data_ptr()
+            else:
+                lam_host, lam_dev = float(step), None
+            st = lib.dlsg_sense_normal_reg_c64(data.data_ptr(), mptr, wptr, wstr, lam_host, lam_dev, out.data_ptr(), *tail)
         elif kind == "dc":
             if isinstance(step, torch.Tensor):
                 step_host, step_dev = 0.0, step.data_ptr()
@@ -191,6 +197,13 @@ class SenseModel(nn.Module):
         assert torch.is_complex(data)
         return _SenseFn.apply(data, self, "normal")
 
+    def normal_reg(self, data: torch.Tensor, lamda) -> torch.Tensor:
+        """A(A(x), adjoint=True) + lamda * x  — `model_normal` of the MoDL / HQS solvers (unrolledswin.py:154) in one chain."""
+        assert torch.is_complex(data)
+        if not isinstance(lamda, torch.Tensor):
+            lamda = torch.as_tensor(float(lamda), dtype=torch.float32)
+        return _RegFn.apply(data, lamda, self)
+
     def dc_step(self, x: torch.Tensor, aty: torch.Tensor, step) -> torch.Tensor:
         """x + step * (A(A(x), adjoint=True) - aty)   — unrolledswin.py:109 in one fused chain."""
         assert torch.is_complex(x) and torch.is_complex(aty)
@@ -268,6 +281,11 @@ class SenseModel(nn.Module):
         if wexp is not None and wexp.device != data.device:
             raise RuntimeError(f"SENSE input on {data.device} but weights on {wexp.device}")
         data = data.detach().contiguous()
+        if kind == "reg" and isinstance(step, torch.Tensor):
+            if not (step.is_cuda and step.dtype == torch.float32 and step.numel() == 1 and step.device == data.device):
+                step = float(step)
+            else:
+                step = step.detach()
         if kind == "dc":
             _require_cuda_c64(aty, "ATy")
             if aty.shape != data.shape:
@@ -294,6 +312,26 @@ class _SenseFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         return _SenseFn.apply(grad, ctx.model, _SenseFn._BACK[ctx.kind]), None, None
+
+
+class _RegFn(torch.autograd.Function):
+    """x -> A^H A x + lamda x ; self-adjoint in x, d/dlamda = x."""
+
+    @staticmethod
+    def forward(ctx, x, lamda, model):
+        ctx.model = model
+        ctx.save_for_backward(x, lamda)
+        return model._run("reg", x, step=lamda)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, lamda = ctx.saved_tensors
+        gx = glam = None
+        if ctx.needs_input_grad[0]:
+            gx = _RegFn.apply(grad, lamda, ctx.model)
+        if ctx.needs_input_grad[1]:
+            glam = (x.conj() * grad).real.sum().reshape(lamda.shape).to(lamda.device)
+        return gx, glam, None
 
 
 class _DcFn(torch.autograd.Function):

@@ -41,3 +41,34 @@ class ProximalGradientDescent(nn.Module):
             if self.cnn_update is not None:
                 xi = self.cnn_update[i](xi)
         return xi
+
+
+class HalfQuadraticSplitting(nn.Module):
+    """MoDL / half-quadratic-splitting solver, mirror of dl_cs/models/unrolledswin.py:125-172 (== unrolled.py:120-167):
+    x <- CG( A^H A + lamda I,  A^H y + lamda * cnn_i(x) ).  The normal equations go through the fused
+    `A.normal_reg` entry when the operator offers it."""
+
+    def __init__(self, num_unrolls: int = 5, num_cg_iter: int = 10, cnn_update: Optional[Sequence[Callable]] = None,
+                 fix_step_size: bool = True, lamda_init: float = 0.1) -> None:
+        super().__init__()
+        from .mri.algorithms import ConjugateGradient
+        self._cg_cls = ConjugateGradient
+        self.num_unrolls = num_unrolls
+        self.num_cg_iter = num_cg_iter
+        self.cnn_update = nn.ModuleList(cnn_update) if cnn_update is not None and all(
+            isinstance(m, nn.Module) for m in cnn_update) else cnn_update
+        self.lamda = nn.Parameter(torch.tensor([lamda_init], dtype=torch.float32), requires_grad=(not fix_step_size))
+
+    def forward(self, y, A, x0=None):
+        ATy = A(y, adjoint=True)
+        xi = ATy if x0 is None else x0
+        fused = getattr(A, "normal_reg", None)
+        if fused is not None:
+            model_normal = lambda m: fused(m, self.lamda)
+        else:
+            model_normal = lambda m: A(A(m), adjoint=True) + self.lamda * m
+        cg_solve = self._cg_cls(model_normal, self.num_cg_iter)
+        for i in range(self.num_unrolls):
+            z = self.cnn_update[i](xi) if self.cnn_update is not None else xi
+            xi = cg_solve(xi, ATy + self.lamda * z)
+        return xi

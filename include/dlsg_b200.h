@@ -79,6 +79,13 @@ int dlsg_sense_normal_c64(const void* x, const void* maps, const float* weights,
                           void* x_out, void* workspace, size_t workspace_bytes,
                           int B, int E, int C, int T, int Y, int X, int ndims, void* stream);
 
+/* Regularised normal operator  x_out = A^H(A(x)) + lamda * x  — `model_normal` of the MoDL / half-quadratic-splitting solver
+ * (dl_cs/models/unrolledswin.py:154, dl_cs/models/unrolled.py:151), the operator ConjugateGradient (dl_cs/mri/algorithms.py:11-73)
+ * inverts.  lamda from the host float or, if lamda_dev is non-NULL, from that device address.  x_out must not alias x. */
+int dlsg_sense_normal_reg_c64(const void* x, const void* maps, const float* weights, const long long* w_strides,
+                              float lamda, const float* lamda_dev, void* x_out, void* workspace, size_t workspace_bytes,
+                              int B, int E, int C, int T, int Y, int X, int ndims, void* stream);
+
 /* Fused data-consistency update (dl_cs/models/unrolledswin.py:109):
  *     x_out = x + step * ( A^H(A(x)) - aty )
  * aty [B,E,T,Y,X] complex64 is A^H y precomputed once per reconstruction (unrolledswin.py:96).

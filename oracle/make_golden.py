@@ -73,6 +73,22 @@ def main():
         "sliding_window5": ref_utils.sliding_window(torch.from_numpy(series), 2, 5).numpy(),
         "get_mask": ref_utils.get_mask(torch.from_numpy(series)).numpy(),
     }
+    # conjugate gradient on the regularised normal equations (MoDL / HQS), reference code on the "tiny_odd" and "pow2_32" inputs
+    from dl_cs.mri.algorithms import ConjugateGradient
+    for name in ("tiny_odd", "pow2_32"):
+        B, E, C, T, Y, X, wkind = CASES[name]
+        maps, x, k, aty, w = make_inputs(name, B, E, C, T, Y, X, wkind)
+        A = SenseModel(torch.from_numpy(maps), weights=None if w is None else torch.from_numpy(w))
+        lam = 0.1
+        model_normal = lambda m: A(A(m), adjoint=True) + lam * m
+        ty = torch.from_numpy(k)
+        ATy = A(ty, adjoint=True)
+        cg = ConjugateGradient(model_normal, 6)
+        misc[f"cg6_{name}"] = cg(torch.from_numpy(x), ATy + lam * torch.from_numpy(aty)).numpy()
+        xi = ATy
+        for _ in range(2):                                   # HalfQuadraticSplitting.forward with cnn_update = identity
+            xi = ConjugateGradient(model_normal, 4)(xi, ATy + lam * xi)
+        misc[f"hqs2x4_{name}"] = xi.numpy()
     np.savez_compressed(os.path.join(OUT, "sense_misc.npz"), **misc)
     print("misc", list(misc))
 

@@ -12,6 +12,7 @@ What is restated (all citations relative to /root/reference):
   * SenseModel._forward_op     dl_cs/mri/transforms.py:92-98   k = W * F( sum_e S * x )
   * SenseModel._adjoint_op     dl_cs/mri/transforms.py:84-90   x = sum_c conj(S) * F^H( W * k )
   * DC update                  dl_cs/models/unrolledswin.py:109 (== dl_cs/models/unrolled.py:104)
+  * ConjugateGradient          dl_cs/mri/algorithms.py:11-73, HalfQuadraticSplitting dl_cs/models/unrolledswin.py:139-172
   * fftmod                     dl_cs/mri/utils.py:7-19
   * sliding_window / time_average / get_mask   dl_cs/mri/utils.py:29-49, 69-79
 
@@ -101,6 +102,33 @@ def sense_normal(x: np.ndarray, maps: np.ndarray, weights=None) -> np.ndarray:
 def dc_step(x: np.ndarray, aty: np.ndarray, maps: np.ndarray, weights, step: float) -> np.ndarray:
     """x + step * (A^H A x - A^H y)   (unrolledswin.py:109, unrolled.py:104)."""
     return x + step * (sense_normal(x, maps, weights) - aty)
+
+
+def conjugate_gradient(A, x, y, num_iter: int):
+    """ConjugateGradient.forward (dl_cs/mri/algorithms.py:38-73): dot products over the whole batch."""
+    zdot = lambda a, b: np.sum(np.conj(a) * b)
+    r = y - A(x)
+    rsold = zdot(r, r).real
+    p = r
+    for _ in range(num_iter):
+        Ap = A(p)
+        alpha = rsold / zdot(p, Ap)
+        x = x + alpha * p
+        r = r - alpha * Ap
+        rsnew = zdot(r, r).real
+        p = (rsnew / rsold) * p + r
+        rsold = rsnew
+    return x
+
+
+def hqs_path(y, maps, weights, num_unrolls: int, num_cg_iter: int, lamda: float, x0=None):
+    """HalfQuadraticSplitting.forward (unrolledswin.py:139-172) with the CNN omitted (z = x)."""
+    aty = sense_adjoint(y, maps, weights)
+    x = aty if x0 is None else x0
+    normal = lambda m: sense_normal(m, maps, weights) + lamda * m
+    for _ in range(num_unrolls):
+        x = conjugate_gradient(normal, x, aty + lamda * x, num_cg_iter)
+    return x
 
 
 # --------------------------------------------------------------------------- helpers either side of the path

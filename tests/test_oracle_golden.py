@@ -143,3 +143,16 @@ def test_swin_host_helpers_match_oracle():
     assert shapes == {"relative_position_bias_table": (2925, 8), "relative_position_index": (448, 448),
                       "qkv.weight": (480, 160), "qkv.bias": (480,), "proj.weight": (160, 160), "proj.bias": (160,)}
     assert np.array_equal(mod.relative_position_index.numpy(), sw.relative_position_index((7, 8, 8)))
+
+
+@pytest.mark.parametrize("name", ["tiny_odd", "pow2_32"])
+def test_oracle_cg_and_hqs_match_reference(golden_cases, name):
+    ref = np.load(os.path.join(GOLDEN, "sense_misc.npz"))
+    inp, _ = golden_cases[name]
+    maps, x, k, aty, w = inp["maps"], inp["x"], inp["k"], inp["aty"], inp["weights"]
+    lam = 0.1
+    normal = lambda m: so.sense_normal(m, maps, w) + lam * m
+    ATy = so.sense_adjoint(k, maps, w)
+    got = so.conjugate_gradient(normal, x, ATy + lam * aty, 6)
+    assert rel_l2(got, ref[f"cg6_{name}"]) < 2e-5
+    assert rel_l2(so.hqs_path(k, maps, w, 2, 4, lam), ref[f"hqs2x4_{name}"]) < 2e-5

@@ -277,3 +277,35 @@ def test_side_stream_and_cuda_graph_replay(dev):
         torch.cuda.synchronize()
         ref = static_x + s * (A(A(static_x), adjoint=True) - aty)
         assert rel_l2(to_np(static_out), to_np(ref)) < 2e-6
+
+
+@pytest.mark.parametrize("name", ["tiny_odd", "pow2_32"])
+def test_conjugate_gradient_and_hqs_match_reference(golden_cases, dev, name):
+    """MoDL / HQS path: the reference's ConjugateGradient on A^H A + lamda I (algorithms.py:11-73,
+    unrolledswin.py:139-172), here on the fused normal_reg entry; vectors from the unmodified reference."""
+    import os
+    from conftest import GOLDEN
+    from dl_swin_gan_b200.mri import ConjugateGradient
+    from dl_swin_gan_b200.unrolled import HalfQuadraticSplitting
+    ref = np.load(os.path.join(GOLDEN, "sense_misc.npz"))
+    inp, _ = golden_cases[name]
+    A = make_model(inp["maps"], inp["weights"], dev)
+    x, k, aty = (torch.from_numpy(inp[n]).to(dev) for n in ("x", "k", "aty"))
+    lam = torch.tensor([0.1], device=dev)
+    with torch.no_grad():
+        ATy = A(k, adjoint=True)
+        assert rel_l2(to_np(A.normal_reg(x, lam)), to_np(A(A(x), adjoint=True) + lam * x)) < 2e-6
+        got = ConjugateGradient(lambda m: A.normal_reg(m, lam), 6)(x, ATy + lam * aty)
+        assert rel_l2(to_np(got), ref[f"cg6_{name}"]) < 1e-4
+        hqs = HalfQuadraticSplitting(num_unrolls=2, num_cg_iter=4, lamda_init=0.1).to(dev)
+        assert rel_l2(to_np(hqs(k, A)), ref[f"hqs2x4_{name}"]) < 1e-4
+    # gradient of the regularised normal operator w.r.t. a learnable lamda and x
+    lam_g = torch.tensor([0.1], device=dev, requires_grad=True)
+    xg = x.clone().requires_grad_()
+    out = A.normal_reg(xg, lam_g)
+    go = torch.randn_like(out)
+    gx, gl = torch.autograd.grad(out, (xg, lam_g), go)
+    x2 = x.clone().requires_grad_()
+    l2 = lam_g.detach().clone().requires_grad_()
+    gx2, gl2 = torch.autograd.grad(A(A(x2), adjoint=True) + l2 * x2, (x2, l2), go)
+    assert rel_l2(to_np(gx), to_np(gx2)) < 1e-5 and rel_l2(to_np(gl), to_np(gl2)) < 1e-4

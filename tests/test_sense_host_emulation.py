@@ -19,6 +19,7 @@ def lib(sense_emu_lib):
     for name in ("forward", "adjoint", "normal"):
         getattr(lib, f"dlsg_sense_{name}_c64").argtypes = [vp] * 5 + tail
     lib.dlsg_sense_dc_step_c64.argtypes = [vp] * 5 + [ctypes.c_float, vp, vp] + tail
+    lib.dlsg_sense_normal_reg_c64.argtypes = [vp] * 4 + [ctypes.c_float, vp, vp] + tail
     lib.dlsg_sense_workspace_bytes.restype = ctypes.c_size_t
     lib.dlsg_sense_workspace_bytes.argtypes = [ctypes.c_int] * 7 + [ctypes.c_size_t]
     return lib
@@ -58,6 +59,9 @@ def run_all(lib, B, E, C, T, Y, X, wkind, budget=0, ndims=2, seed=7):
     out = np.full((B, E, T, Y, X), np.nan, np.complex64)
     assert lib.dlsg_sense_dc_step_c64(ptr(x), ptr(aty), ptr(m5), wp, ws, -2.0, None, ptr(out), *tail) == 0
     err["dc"] = rel_l2(out, so.dc_step(x128, a128, m128, w, -2.0))
+    out = np.full((B, E, T, Y, X), np.nan, np.complex64)
+    assert lib.dlsg_sense_normal_reg_c64(ptr(x), ptr(m5), wp, ws, 0.25, None, ptr(out), *tail) == 0
+    err["reg"] = rel_l2(out, so.sense_normal(x128, m128, w) + 0.25 * x128)
     return err
 
 
