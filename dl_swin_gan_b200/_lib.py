@@ -35,6 +35,9 @@ SIGNATURES = {
     "dlsg_sense_normal_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz] + _shape7 + [_vp]),
     "dlsg_sense_normal_reg_c64": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _sz] + _shape7 + [_vp]),
     "dlsg_sense_dc_step_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _sz] + _shape7 + [_vp]),
+    "dlsg_fftmod_c64": (_i, [_vp, ctypes.c_longlong, _i, _i, _vp]),
+    "dlsg_get_mask_c64": (_i, [_vp, _vp, ctypes.c_longlong, _f, _vp]),
+    "dlsg_sliding_window_c64": (_i, [_vp, _vp, ctypes.c_longlong, _i, ctypes.c_longlong, _i, _i, _f, _f, _vp]),
     "dlsg_swin_ln_partition_f32": (_i, [_vp, _vp, _vp, _f, _vp] + [_i] * 5 + [_vp, _vp, _vp]),
     "dlsg_swin_window_reverse_f32": (_i, [_vp, _vp] + [_i] * 5 + [_vp, _vp, _vp]),
     "dlsg_swin_window_attention_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _f, _i, _vp, _i, _vp]),

@@ -157,6 +157,23 @@ int dlsg_swin_proj_scatter_f32(const float* attn_out, const float* weight, const
 int dlsg_swin_linear_f32(const float* x, const float* weight, const float* bias, float* y,
                          int M, int N, int K, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * k-t pre-processing either side of the operator (dl_cs/mri/utils.py), complex64, contiguous.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* fftmod (:7-19), in place on n_images images of Y x X: data[..., y, x] *= -(-1)^(x+y) (the three sign flips combined). */
+int dlsg_fftmod_c64(void* data, long long n_images, int Y, int X, void* stream);
+
+/* get_mask (:69-79): mask[i] = |data[i]| > eps ? 1 : 0. */
+int dlsg_get_mask_c64(const void* data, float* mask, long long n, float eps, void* stream);
+
+/* sliding_window (:37-49) / time_average (:29-34) along the middle axis of data [outer, T, inner]:
+ *   out[o, t, p] = sum_{j < window} data[o, (t - window/2 + j) mod T, p] / (#{|data| > mask_eps in that window} + eps)
+ * keep_all_frames != 0: out [outer, T, inner];  keep_all_frames == 0: out [outer, 1, inner], frame t = 0 only —
+ * with window == T that is time_average(dim, keepdim=True) (a full-ring sum does not depend on the phase). */
+int dlsg_sliding_window_c64(const void* data, void* out, long long outer, int T, long long inner, int window,
+                            int keep_all_frames, float mask_eps, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,37 @@ def main():
         for _ in range(2):                                   # HalfQuadraticSplitting.forward with cnn_update = identity
             xi = ConjugateGradient(model_normal, 4)(xi, ATy + lam * xi)
         misc[f"hqs2x4_{name}"] = xi.numpy()
+    # DataTransform.__call__ (scripts/reconstruct.py:132-171): the script itself needs pytorch_lightning, so the same
+    # reference functions are called here in the same order on an undersampled cine-like series (even sizes: fftmod)
+    rng = np.random.default_rng(99)
+    C_, T_, Y_, X_ = 3, 7, 12, 10
+    ksp = (rng.standard_normal((C_, T_, Y_, X_)) + 1j * rng.standard_normal((C_, T_, Y_, X_))).astype(np.complex64)
+    keep = rng.random((1, T_, Y_, 1)) < 0.4
+    ksp = ksp * keep
+    mp = (rng.standard_normal((2, C_, 1, Y_, X_)) + 1j * rng.standard_normal((2, C_, 1, Y_, X_))).astype(np.complex64) / 2
+    misc["dt_kspace_in"], misc["dt_maps_in"] = ksp, mp
+    for slwin in (False, True):
+        kspace = torch.from_numpy(ksp.copy()).unsqueeze(0)
+        maps_t = torch.from_numpy(mp.copy()).unsqueeze(0)
+        mask = ref_utils.get_mask(kspace)[:, 0, None]
+        kspace = ref_utils.fftmod(kspace)
+        maps_t = ref_utils.fftmod(maps_t)
+        A = SenseModel(maps_t, weights=None)
+        averaged = ref_utils.time_average(kspace, dim=2)
+        image = A(averaged, adjoint=True)
+        magnitude = torch.abs(image).reshape(-1)
+        kk = int(round(0.05 * magnitude.numel()))
+        scale = torch.min(torch.topk(magnitude, kk).values)
+        kspace /= scale
+        init_kspace = ref_utils.sliding_window(kspace, dim=2, window_size=5) if slwin else kspace
+        init_image = A(init_kspace, adjoint=True)
+        tag = "slwin" if slwin else "plain"
+        misc[f"dt_{tag}_kspace"] = kspace.squeeze(0).numpy()
+        misc[f"dt_{tag}_maps"] = maps_t.squeeze(0).numpy()
+        misc[f"dt_{tag}_mask"] = mask.squeeze(0).numpy()
+        misc[f"dt_{tag}_init"] = init_image.squeeze(0).numpy()
+        misc[f"dt_{tag}_scale"] = np.float32(scale.item())
+        misc["time_average"] = averaged.numpy()
     np.savez_compressed(os.path.join(OUT, "sense_misc.npz"), **misc)
     print("misc", list(misc))
 

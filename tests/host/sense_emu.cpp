@@ -3,6 +3,7 @@
 // very same index math on the CPU (tests/test_sense_host_emulation.py).  Never shipped.
 #include "../../dl_swin_gan_b200/csrc/sense_api.cu"
 #include "../../dl_swin_gan_b200/csrc/swin_api.cu"
+#include "../../dl_swin_gan_b200/csrc/kt_api.cu"
 
 namespace dlsg_emu {
 thread_local dim3 t_threadIdx;

@@ -156,3 +156,21 @@ def test_oracle_cg_and_hqs_match_reference(golden_cases, name):
     got = so.conjugate_gradient(normal, x, ATy + lam * aty, 6)
     assert rel_l2(got, ref[f"cg6_{name}"]) < 2e-5
     assert rel_l2(so.hqs_path(k, maps, w, 2, 4, lam), ref[f"hqs2x4_{name}"]) < 2e-5
+
+
+def test_oracle_preprocessing_chain_matches_reference():
+    """DataTransform.__call__ (scripts/reconstruct.py:132-171) restated with the oracle helpers."""
+    ref = np.load(os.path.join(GOLDEN, "sense_misc.npz"))
+    for slwin, tag in ((False, "plain"), (True, "slwin")):
+        k = ref["dt_kspace_in"][None].copy()
+        maps = ref["dt_maps_in"][None].copy()
+        mask = so.get_mask(k)[:, 0, None]
+        k, maps = so.fftmod(k), so.fftmod(maps)
+        img = so.sense_adjoint(so.time_average(k, 2), maps, None)
+        mag = np.sort(np.abs(img).reshape(-1))[::-1]
+        scale = mag[int(round(0.05 * mag.size)) - 1]
+        k = k / scale
+        init = so.sense_adjoint(so.sliding_window(k, 2, 5) if slwin else k, maps, None)
+        assert np.array_equal(mask[0], ref[f"dt_{tag}_mask"])
+        assert abs(scale - ref[f"dt_{tag}_scale"]) / ref[f"dt_{tag}_scale"] < 1e-5
+        assert rel_l2(k[0], ref[f"dt_{tag}_kspace"]) < 2e-6 and rel_l2(init[0], ref[f"dt_{tag}_init"]) < 2e-6

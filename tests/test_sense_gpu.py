@@ -309,3 +309,32 @@ def test_conjugate_gradient_and_hqs_match_reference(golden_cases, dev, name):
     l2 = lam_g.detach().clone().requires_grad_()
     gx2, gl2 = torch.autograd.grad(A(A(x2), adjoint=True) + l2 * x2, (x2, l2), go)
     assert rel_l2(to_np(gx), to_np(gx2)) < 1e-5 and rel_l2(to_np(gl), to_np(gl2)) < 1e-4
+
+
+def test_kt_preprocessing_matches_reference(dev):
+    """fftmod / get_mask / time_average / sliding_window kernels and the DataTransform chain (reconstruct.py:132-171)
+    against outputs of the reference functions (tests/golden/sense_misc.npz)."""
+    import os
+    from conftest import GOLDEN
+    from dl_swin_gan_b200.mri import utils as U
+    from dl_swin_gan_b200.data import DataTransform
+    ref = np.load(os.path.join(GOLDEN, "sense_misc.npz"))
+    assert np.array_equal(to_np(U.fftmod(torch.from_numpy(ref["img_even"].copy()).to(dev))), ref["fftmod"])
+    series = torch.from_numpy(ref["series"]).to(dev)
+    assert np.array_equal(to_np(U.get_mask(series)), ref["get_mask"])
+    assert rel_l2(to_np(U.sliding_window(series, 2, 5)), ref["sliding_window5"]) < 1e-6
+    for slwin, tag in ((False, "plain"), (True, "slwin")):
+        k, m, mask, init, scale = DataTransform(slwin_init=slwin, device=dev)(ref["dt_kspace_in"], ref["dt_maps_in"])
+        assert np.array_equal(to_np(mask), ref[f"dt_{tag}_mask"])
+        assert np.array_equal(to_np(m), ref[f"dt_{tag}_maps"])
+        assert abs(float(scale) - float(ref[f"dt_{tag}_scale"])) / float(ref[f"dt_{tag}_scale"]) < 1e-5
+        assert rel_l2(to_np(k), ref[f"dt_{tag}_kspace"]) < 1e-5
+        assert rel_l2(to_np(init), ref[f"dt_{tag}_init"]) < 1e-5
+    tav = U.time_average(U.fftmod(torch.from_numpy(ref["dt_kspace_in"].copy()).to(dev).unsqueeze(0)), dim=2)
+    assert rel_l2(to_np(tav), ref["time_average"]) < 1e-6
+    big = torch.view_as_complex(torch.randn(2, 8, 20, 192, 160, 2, device=dev))
+    big[:, :, ::3] = 0
+    want = torch.cat([torch.roll(big, 2 - i, 2).narrow(2, 0, 5).sum(2, keepdim=True) /
+                      ((torch.roll(big, 2 - i, 2).narrow(2, 0, 5).abs() > 1e-12).float().sum(2, keepdim=True) + 1e-6)
+                      for i in range(20)], dim=2)
+    assert rel_l2(to_np(U.sliding_window(big, 2, 5)), to_np(want)) < 1e-6

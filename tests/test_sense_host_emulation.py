@@ -100,3 +100,29 @@ def test_status_codes(lib):
     assert lib.dlsg_sense_forward_c64(ptr(z), ptr(z), None, None, ptr(z), ptr(z), 128, 1, 1, 1, 1, 4, 4, 3, None) == -1
     assert lib.dlsg_sense_forward_c64(ptr(z), ptr(z), None, None, ptr(z), ptr(z), 128, 1, 1, 1, 1, 4, 5000, 2, None) == -3
     assert lib.dlsg_sense_forward_c64(ptr(z), ptr(z), ptr(z), None, ptr(z), *tail) == -1   # weights without strides
+
+
+def test_kt_kernels_emulated(sense_emu_lib):
+    """fftmod / get_mask / sliding-window kernels under the host emulation vs the oracle helpers."""
+    lib = ctypes.CDLL(sense_emu_lib)
+    ll = ctypes.c_longlong
+    lib.dlsg_fftmod_c64.argtypes = [vp, ll, ctypes.c_int, ctypes.c_int, vp]
+    lib.dlsg_get_mask_c64.argtypes = [vp, vp, ll, ctypes.c_float, vp]
+    lib.dlsg_sliding_window_c64.argtypes = [vp, vp, ll, ctypes.c_int, ll, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, vp]
+    rng = np.random.default_rng(4)
+    a = (rng.standard_normal((2, 3, 6, 5)) + 1j * rng.standard_normal((2, 3, 6, 5))).astype(np.complex64)
+    b = a.copy()
+    assert lib.dlsg_fftmod_c64(ptr(b), 6, 6, 5, None) == 0
+    assert np.array_equal(b, so.fftmod(a.copy()))
+    s = (rng.standard_normal((2, 7, 4, 3)) + 1j * rng.standard_normal((2, 7, 4, 3))).astype(np.complex64)
+    s[:, ::3] = 0
+    m = np.empty(s.shape, np.float32)
+    assert lib.dlsg_get_mask_c64(ptr(s), ptr(m), s.size, 1e-12, None) == 0
+    assert np.array_equal(m, so.get_mask(s))
+    out = np.empty_like(s)
+    assert lib.dlsg_sliding_window_c64(ptr(s), ptr(out), 2, 7, 12, 5, 1, 1e-12, 1e-6, None) == 0
+    assert rel_l2(out, so.sliding_window(s, 1, 5)) < 1e-6
+    avg = np.empty((2, 1, 4, 3), np.complex64)
+    assert lib.dlsg_sliding_window_c64(ptr(s), ptr(avg), 2, 7, 12, 7, 0, 1e-12, 1e-6, None) == 0
+    assert rel_l2(avg, so.time_average(s, 1)) < 1e-6
+    assert lib.dlsg_sliding_window_c64(ptr(s), ptr(out), 2, 7, 12, 9, 1, 1e-12, 1e-6, None) == -1
