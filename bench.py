@@ -334,13 +334,29 @@ def main():
         ops[name] = {"ms": t, "algorithmic_MB_per_slice": nbytes / B / 1e6, "GBps": nbytes / (t * 1e-3) / 1e9,
                      "frac_hbm": nbytes / (t * 1e-3) / 1e9 / hbm_peak,
                      "TFLOPs_nominal": algorithmic_flops(name, B, E, C, T, Y, X) / (t * 1e-3) / 1e12}
+    # the same ops on the dense kernels (what runs when W has no empty ky lines), for comparison
+    plan = A._line_plans.get((B, E, C, T, Y, X))
+    path = "sampled-lines" if plan is not None else "dense"
+    ops_dense = None
+    if plan is not None:
+        os.environ["DLSG_SAMPLED_LINES"] = "0"
+        with torch.no_grad():
+            ops_dense = {"forward_ms": time_op(lambda: A(x0), iters, dev),
+                         "adjoint_ms": time_op(lambda: A(y, adjoint=True), iters, dev),
+                         "dc_step_ms": time_op(lambda: A.dc_step(x0, aty, pgd.step_size), iters, dev)}
+        os.environ["DLSG_SAMPLED_LINES"] = "1"
     dom = "dc_step"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic_per_slice.json")
+    tkey = "ops_MB_per_slice_sampled_lines" if plan is not None else "ops_MB_per_slice"
     if os.path.exists(tpath) and (E, C, T, Y, X) == (1, 8, 20, 192, 160):
         with open(tpath) as f:
-            traffic = json.load(f)["ops_MB_per_slice"][dom] * 1e6 * B      # ncu-measured DRAM bytes per launch chain
-    roofline = {"bound": "hbm", "kernel": "fused DC step chain (rows_fwd + cols_normal + rows_adj)",
+            tj = json.load(f)
+        if tkey in tj:
+            traffic = tj[tkey][dom] * 1e6 * B      # ncu-measured DRAM bytes per launch chain
+    chain = ("cols_fwd_lines + rows_lines<NORMAL> + cols_adj_lines" if plan is not None
+             else "rows_fwd + cols<NORMAL> + rows_adj")
+    roofline = {"bound": "hbm", "kernel": f"fused DC step chain ({chain})",
                 "achieved": ops[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": ops[dom]["frac_hbm"],
                 "traffic": traffic, "traffic_source": "ncu --set full, profiles/r1_dram_traffic_per_slice.json",
                 "peak_source": peak_src,
@@ -404,8 +420,9 @@ def main():
             "vs_baseline": None, "dtype": "f32 (complex64)", "data": "synthetic",
             "config": {"workload": "config_recon.yaml", **cfg, "slices_per_gpu": B,
                        "l2": "working set per step (y 2.5 GB + x/maps/mask) >> 126 MB L2, no flush needed",
-                       "workspace_MB": float(os.environ.get("DLSG_WORKSPACE_MB", 4096))},
-            "roofline": roofline, "ops": ops, "swin_window_attention": swin, "cpu_baseline": cpu, "e2e": e2e,
+                       "workspace_MB": float(os.environ.get("DLSG_WORKSPACE_MB", 4096)),
+                       "kernel_path": path, "sampled_ky_lines_max": (plan[1] if plan is not None else Y)},
+            "roofline": roofline, "ops": ops, "ops_dense_kernels": ops_dense, "swin_window_attention": swin, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

@@ -35,6 +35,13 @@ SIGNATURES = {
     "dlsg_sense_normal_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz] + _shape7 + [_vp]),
     "dlsg_sense_normal_reg_c64": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _sz] + _shape7 + [_vp]),
     "dlsg_sense_dc_step_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _sz] + _shape7 + [_vp]),
+    "dlsg_sense_line_plan_bytes": (_sz, [_i, _i, _i]),
+    "dlsg_sense_line_plan_build": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "dlsg_sense_lines_supported": (_i, [_i, _i, _i, _i]),
+    "dlsg_sense_lines_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _sz]),
+    "dlsg_sense_forward_lines_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz] + [_i] * 6 + [_vp]),
+    "dlsg_sense_adjoint_lines_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz] + [_i] * 6 + [_vp]),
+    "dlsg_sense_normal_lines_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _i, _vp, _vp, _sz] + [_i] * 6 + [_vp]),
     "dlsg_fftmod_c64": (_i, [_vp, ctypes.c_longlong, _i, _i, _vp]),
     "dlsg_get_mask_c64": (_i, [_vp, _vp, ctypes.c_longlong, _f, _vp]),
     "dlsg_sliding_window_c64": (_i, [_vp, _vp, ctypes.c_longlong, _i, ctypes.c_longlong, _i, _i, _f, _f, _vp]),

@@ -29,6 +29,8 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_group0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// all but the most recently committed group have landed
+__device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
 #include <cuda_fp16.h>
 typedef __half half_t;
@@ -209,6 +211,7 @@ static inline void cp_async16(void* smem_dst, const void* gmem_src) { std::memcp
 static inline void cp_async_wait_all() {}
 static inline void cp_async_commit() {}
 static inline void cp_async_wait_group0() {}
+static inline void cp_async_wait_group1() {}
 using std::min;
 using std::max;
 

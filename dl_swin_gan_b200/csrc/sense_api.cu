@@ -3,6 +3,7 @@
 // axis length, launches.  No allocation, no synchronisation, no global state.
 #include "../../include/dlsg_b200.h"
 #include "sense_kernels.cuh"
+#include "sense_lines.cuh"
 
 #include <cmath>
 
@@ -17,8 +18,23 @@ constexpr long long kTargetColCtas = 148LL * 4;
 inline int radix_of(int n) {   // R if n == 32*R with a compiled radix, else 0
     if (n % 32) return 0;
     const int r = n / 32;
+#ifdef DLSG_FAST_BUILD
+    return (r == 5 || r == 6) ? r : 0;
+#else
     switch (r) { case 1: case 2: case 3: case 4: case 5: case 6: case 8: case 10: return r; default: return 0; }
+#endif
 }
+
+// One `case R:` per compiled radix (DLSG_FAST_BUILD: cine radices only, for tuning builds; never shipped).
+#define DLSG_RADIX_CASE(n, EXPR) case n: { constexpr int R = n; return EXPR; }
+#ifdef DLSG_FAST_BUILD
+#define DLSG_RADIX_CASES(EXPR) DLSG_RADIX_CASE(5, EXPR) DLSG_RADIX_CASE(6, EXPR)
+#else
+#define DLSG_RADIX_CASES(EXPR)                                                                         \
+    DLSG_RADIX_CASE(1, EXPR) DLSG_RADIX_CASE(2, EXPR) DLSG_RADIX_CASE(3, EXPR) DLSG_RADIX_CASE(4, EXPR) \
+    DLSG_RADIX_CASE(5, EXPR) DLSG_RADIX_CASE(6, EXPR) DLSG_RADIX_CASE(8, EXPR) DLSG_RADIX_CASE(10, EXPR)
+#endif
+#define DLSG_RADIX_SWITCH(r, EXPR) switch (r) { DLSG_RADIX_CASES(EXPR) default: return -1; }
 
 struct Problem {          // what stays fixed over the chunk walk
     WeightStrides ws;
@@ -70,17 +86,7 @@ int launch_rows_fwd(const float2* x, const float2* maps, float2* tmp, const Sens
 int rows_fwd(const Problem& p, const float2* x, const float2* maps, const float* w, float2* k,
              const SenseDims& d, float scale, int final1d) {
     const int rx = (p.ndims == 2) ? radix_of(d.X) : 0;
-    switch (rx) {
-        case 1: return launch_rows_fwd<1>(x, maps, p.tmp, d, p.stream);
-        case 2: return launch_rows_fwd<2>(x, maps, p.tmp, d, p.stream);
-        case 3: return launch_rows_fwd<3>(x, maps, p.tmp, d, p.stream);
-        case 4: return launch_rows_fwd<4>(x, maps, p.tmp, d, p.stream);
-        case 5: return launch_rows_fwd<5>(x, maps, p.tmp, d, p.stream);
-        case 6: return launch_rows_fwd<6>(x, maps, p.tmp, d, p.stream);
-        case 8: return launch_rows_fwd<8>(x, maps, p.tmp, d, p.stream);
-        case 10: return launch_rows_fwd<10>(x, maps, p.tmp, d, p.stream);
-        default: break;
-    }
+    switch (rx) { DLSG_RADIX_CASES((launch_rows_fwd<R>(x, maps, p.tmp, d, p.stream))) default: break; }
     const size_t smem = (size_t)2 * d.X * sizeof(float2);
     const unsigned grid = (unsigned)((long long)d.B * d.t_count * d.Y);
     float2* dst = (final1d == 1) ? k : p.tmp;
@@ -113,17 +119,7 @@ int rows_adj_groups(const float2* maps, float2* out, const float2* xin, const fl
 int rows_adj(const Problem& p, const float2* src_k, const float2* maps, const float* w, float2* out,
              const float2* xin, const float2* aty, const SenseDims& d, float scale, int final1d) {
     const int rx = (p.ndims == 2) ? radix_of(d.X) : 0;
-    switch (rx) {
-        case 1: return rows_adj_groups<1>(maps, out, xin, aty, p, d);
-        case 2: return rows_adj_groups<2>(maps, out, xin, aty, p, d);
-        case 3: return rows_adj_groups<3>(maps, out, xin, aty, p, d);
-        case 4: return rows_adj_groups<4>(maps, out, xin, aty, p, d);
-        case 5: return rows_adj_groups<5>(maps, out, xin, aty, p, d);
-        case 6: return rows_adj_groups<6>(maps, out, xin, aty, p, d);
-        case 8: return rows_adj_groups<8>(maps, out, xin, aty, p, d);
-        case 10: return rows_adj_groups<10>(maps, out, xin, aty, p, d);
-        default: break;
-    }
+    switch (rx) { DLSG_RADIX_CASES((rows_adj_groups<R>(maps, out, xin, aty, p, d))) default: break; }
     const size_t smem = (size_t)(2 + d.E) * d.X * sizeof(float2);
     const unsigned grid = (unsigned)((long long)d.B * d.t_count * d.Y);
     const float2* src = (final1d == 1) ? src_k : (const float2*)p.tmp;
@@ -150,17 +146,7 @@ template <int MODE>
 int cols(const Problem& p, const float2* src, float2* dst, const float* w, const SenseDims& d, float scale) {
     // the fast column kernel walks 32-column slabs, so it also needs X % 32 == 0
     const int ry = (d.X % 32 == 0) ? radix_of(d.Y) : 0;
-    switch (ry) {
-        case 1: return launch_cols<1, MODE>(src, dst, w, p, d, scale);
-        case 2: return launch_cols<2, MODE>(src, dst, w, p, d, scale);
-        case 3: return launch_cols<3, MODE>(src, dst, w, p, d, scale);
-        case 4: return launch_cols<4, MODE>(src, dst, w, p, d, scale);
-        case 5: return launch_cols<5, MODE>(src, dst, w, p, d, scale);
-        case 6: return launch_cols<6, MODE>(src, dst, w, p, d, scale);
-        case 8: return launch_cols<8, MODE>(src, dst, w, p, d, scale);
-        case 10: return launch_cols<10, MODE>(src, dst, w, p, d, scale);
-        default: break;
-    }
+    switch (ry) { DLSG_RADIX_CASES((launch_cols<R, MODE>(src, dst, w, p, d, scale))) default: break; }
     const size_t smem = ((size_t)2 * d.Y * kDirectColW + d.Y) * sizeof(float2);
     const int ncolblk = (d.X + kDirectColW - 1) / kDirectColW;
     const unsigned grid = (unsigned)((long long)d.B * d.C * d.t_count * ncolblk);
@@ -308,6 +294,107 @@ int run(Op op, const float2* in, const float2* maps, const float* w, const long 
     return DLSG_OK;
 }
 
+// ---- sampled-line path (sense_lines.cuh) ---------------------------------------------------
+
+constexpr size_t kSmemTwoPerSm = 113 * 1024;     // largest dynamic shared memory that still lets two CTAs share an SM
+constexpr size_t kSmemMax = 227 * 1024;
+
+template <int RY>
+int launch_cols_fwd_lines(const float2* x, const float2* maps, float2* tl, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    using Cfg = ColLinesCfg<RY>;
+    const unsigned grid = (unsigned)((long long)(d.X / Cfg::SW) * d.t_count * d.B);
+#ifndef DLSG_LINES_FWD_NO_XS
+    if (Cfg::smem_fwd(d.E) <= kSmemTwoPerSm)
+        return launch(sense_cols_fwd_lines_kernel<RY, true>, dim3(grid), dim3(Cfg::NT), Cfg::smem_fwd(d.E), s, x, maps, tl, lp, d);
+#endif
+    return launch(sense_cols_fwd_lines_kernel<RY, false>, dim3(grid), dim3(Cfg::NT), Cfg::smem_fwd(0), s, x, maps, tl, lp, d);
+}
+int cols_fwd_lines(const float2* x, const float2* maps, float2* tl, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    DLSG_RADIX_SWITCH(radix_of(d.Y), (launch_cols_fwd_lines<R>(x, maps, tl, lp, d, s)))
+}
+
+template <int RY>
+int launch_cols_adj_lines(const float2* tl, const float2* maps, float2* out, const float2* xin, const float2* aty,
+                          float step, const float* step_dev, int epi, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    using Cfg = ColLinesCfg<RY>;
+    const unsigned grid = (unsigned)((long long)(d.X / Cfg::SW) * d.t_count * d.B);
+    return launch(sense_cols_adj_lines_kernel<RY>, dim3(grid), dim3(Cfg::NT), Cfg::smem_adj(d.E, lp.lmax), s,
+                  tl, maps, out, xin, aty, step, step_dev, epi, lp, d);
+}
+int cols_adj_lines(const float2* tl, const float2* maps, float2* out, const float2* xin, const float2* aty,
+                   float step, const float* step_dev, int epi, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    DLSG_RADIX_SWITCH(radix_of(d.Y), (launch_cols_adj_lines<R>(tl, maps, out, xin, aty, step, step_dev, epi, lp, d, s)))
+}
+size_t cols_adj_lines_smem(int E, int Y, int lmax) {     // ColLinesCfg<RY>::smem_adj without the template argument
+    const size_t sw = (radix_of(Y) <= 6) ? 32 : 16;
+    return ((size_t)(1 + E) * Y * sw + (size_t)lmax * sw) * sizeof(float2) + (size_t)Y * (sizeof(float2) + sizeof(int));
+}
+
+template <int RX, int MODE>
+int launch_rows_lines(const float2* src, float2* dst, const float* w, const WeightStrides& ws, float scale,
+                      const LinePlan& lp, const SenseDims& d, stream_t s) {
+    using Cfg = RowCfg<RX>;
+    const size_t smem = (size_t)Cfg::WARPS * (MODE == MODE_NORMAL ? 2 : 1) * Cfg::BUF * sizeof(float2);
+    const unsigned grid = (unsigned)((long long)d.B * d.t_count);
+    return launch(sense_rows_lines_kernel<RX, MODE>, dim3(grid), dim3(32 * Cfg::WARPS), smem, s, src, dst, w, ws, scale, lp, d);
+}
+template <int MODE>
+int rows_lines(const float2* src, float2* dst, const float* w, const WeightStrides& ws, float scale,
+               const LinePlan& lp, const SenseDims& d, stream_t s) {
+    DLSG_RADIX_SWITCH(radix_of(d.X), (launch_rows_lines<R, MODE>(src, dst, w, ws, scale, lp, d, s)))
+}
+
+bool lines_supported(int E, int Y, int X, int lmax) {
+    if (E <= 0 || lmax <= 0 || lmax > Y) return false;
+    if (!radix_of(Y) || !radix_of(X)) return false;
+    return cols_adj_lines_smem(E, Y, lmax) <= kSmemMax;
+}
+
+int run_lines(Op op, const float2* in, const float2* maps, const float* w, const long long* w_strides,
+              const int* plan, int lmax, float2* out, const float2* aty, float step, const float* step_dev, int epi,
+              void* workspace, size_t workspace_bytes, int B, int E, int C, int T, int Y, int X, void* stream) {
+    if (B <= 0 || E <= 0 || C <= 0 || T <= 0 || Y <= 0 || X <= 0) return DLSG_EINVAL;
+    if (!in || !out || !maps || !w || !w_strides || !plan) return DLSG_EINVAL;
+    if (epi == EPI_DC && !aty) return DLSG_EINVAL;
+    if (!lines_supported(E, Y, X, lmax)) return DLSG_EUNSUPPORTED;
+    const size_t per_slice = (size_t)C * T * lmax * X * sizeof(float2);
+    if (!workspace || workspace_bytes < per_slice) return DLSG_EWORKSPACE;
+    long long bchunk = (long long)(workspace_bytes / per_slice);
+    if (bchunk > B) bchunk = B;
+    const WeightStrides ws{w_strides[0], w_strides[1], w_strides[2], w_strides[3], w_strides[4]};
+    float2* tl = static_cast<float2*>(workspace);
+    stream_t s = static_cast<stream_t>(stream);
+    const float scale = (float)(1.0 / sqrt((double)Y * (double)X));
+    const size_t x_slice = (size_t)E * T * Y * X, m_slice = (size_t)E * C * Y * X, k_slice = (size_t)C * T * Y * X;
+    const int* counts = plan;
+    const int* list = plan + (size_t)B * T;
+    const int* pos = list + (size_t)B * T * Y;
+    for (long long b0 = 0; b0 < B; b0 += bchunk) {
+        const int bc = (int)((B - b0 < bchunk) ? (B - b0) : bchunk);
+        const SenseDims d{bc, E, C, T, Y, X, 0, T};
+        const LinePlan lp{counts + b0 * T, list + b0 * T * Y, pos + b0 * T * Y, lmax};
+        const float2* maps_b = maps ? maps + b0 * m_slice : nullptr;
+        const float* w_b = w + b0 * ws.b;
+        if (op == OP_ADJ) {
+            DLSG_TRY((rows_lines<MODE_ADJ>(in + b0 * k_slice, tl, w_b, ws, scale, lp, d, s)));
+            DLSG_TRY(cols_adj_lines(tl, maps_b, out + b0 * x_slice, nullptr, nullptr, 0.f, nullptr, EPI_PLAIN, lp, d, s));
+            continue;
+        }
+        const float2* x_b = in + b0 * x_slice;
+        DLSG_TRY(cols_fwd_lines(x_b, maps_b, tl, lp, d, s));
+        if (op == OP_FWD) {
+            float2* k_b = out + b0 * k_slice;
+            DLSG_TRY(launch(sense_zero_unsampled_kernel, dim3((unsigned)((long long)bc * T * C)), dim3(256), 0, s, k_b, lp, d));
+            DLSG_TRY((rows_lines<MODE_FWD>(tl, k_b, w_b, ws, scale, lp, d, s)));
+        } else {
+            DLSG_TRY((rows_lines<MODE_NORMAL>(tl, tl, w_b, ws, scale, lp, d, s)));
+            DLSG_TRY(cols_adj_lines(tl, maps_b, out + b0 * x_slice, x_b, aty ? aty + b0 * x_slice : nullptr,
+                                    step, step_dev, epi, lp, d, s));
+        }
+    }
+    return DLSG_OK;
+}
+
 }  // namespace
 }  // namespace dlsg
 
@@ -376,6 +463,61 @@ int dlsg_sense_dc_step_c64(const void* x, const void* aty, const void* maps, con
                            int B, int E, int C, int T, int Y, int X, int ndims, void* stream) {
     return dlsg::run(dlsg::OP_NORMAL, (const float2*)x, (const float2*)maps, weights, w_strides, (float2*)x_out,
                      (const float2*)aty, step, step_dev, dlsg::EPI_DC, workspace, workspace_bytes, B, E, C, T, Y, X, ndims, stream);
+}
+
+// ---- sampled-line entry points ---------------------------------------------------------------
+size_t dlsg_sense_line_plan_bytes(int B, int T, int Y) {
+    if (B <= 0 || T <= 0 || Y <= 0) return 0;
+    return sizeof(int) * (size_t)B * T * (1 + 2 * (size_t)Y);
+}
+
+int dlsg_sense_line_plan_build(const float* weights, const long long* w_strides, int B, int C, int T, int Y, int X,
+                               void* plan, void* stream) {
+    if (B <= 0 || C <= 0 || T <= 0 || Y <= 0 || X <= 0) return DLSG_EINVAL;
+    if (!weights || !w_strides || !plan) return DLSG_EINVAL;
+    const dlsg::WeightStrides ws{w_strides[0], w_strides[1], w_strides[2], w_strides[3], w_strides[4]};
+    int* counts = static_cast<int*>(plan);
+    int* list = counts + (size_t)B * T;
+    int* pos = list + (size_t)B * T * Y;
+    const int rc = dlsg::launch(dlsg::sense_line_plan_kernel, dim3((unsigned)((long long)B * T)), dim3(256), (size_t)Y * sizeof(int),
+                                static_cast<dlsg::stream_t>(stream), weights, ws, C, T, Y, X, counts, list, pos);
+    return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
+}
+
+int dlsg_sense_lines_supported(int E, int Y, int X, int lmax) { return dlsg::lines_supported(E, Y, X, lmax) ? 1 : 0; }
+
+size_t dlsg_sense_lines_workspace_bytes(int B, int C, int T, int X, int lmax, size_t budget_bytes) {
+    if (B <= 0 || C <= 0 || T <= 0 || X <= 0 || lmax <= 0) return 0;
+    const size_t per_slice = (size_t)C * T * lmax * X * sizeof(float2);
+    size_t nb = budget_bytes / per_slice;
+    if (nb < 1) nb = 1;
+    if (nb > (size_t)B) nb = (size_t)B;
+    return nb * per_slice;
+}
+
+int dlsg_sense_forward_lines_c64(const void* x, const void* maps, const float* weights, const long long* w_strides,
+                                 const void* plan, int lmax, void* k_out, void* workspace, size_t workspace_bytes,
+                                 int B, int E, int C, int T, int Y, int X, void* stream) {
+    return dlsg::run_lines(dlsg::OP_FWD, (const float2*)x, (const float2*)maps, weights, w_strides, (const int*)plan, lmax,
+                           (float2*)k_out, nullptr, 0.f, nullptr, dlsg::EPI_PLAIN, workspace, workspace_bytes, B, E, C, T, Y, X, stream);
+}
+
+int dlsg_sense_adjoint_lines_c64(const void* k, const void* maps, const float* weights, const long long* w_strides,
+                                 const void* plan, int lmax, void* x_out, void* workspace, size_t workspace_bytes,
+                                 int B, int E, int C, int T, int Y, int X, void* stream) {
+    return dlsg::run_lines(dlsg::OP_ADJ, (const float2*)k, (const float2*)maps, weights, w_strides, (const int*)plan, lmax,
+                           (float2*)x_out, nullptr, 0.f, nullptr, dlsg::EPI_PLAIN, workspace, workspace_bytes, B, E, C, T, Y, X, stream);
+}
+
+int dlsg_sense_normal_lines_c64(const void* x, const void* aty, const void* maps, const float* weights,
+                                const long long* w_strides, const void* plan, int lmax,
+                                float step, const float* step_dev, int epilogue, void* x_out,
+                                void* workspace, size_t workspace_bytes,
+                                int B, int E, int C, int T, int Y, int X, void* stream) {
+    if (epilogue < 0 || epilogue > 2) return DLSG_EINVAL;
+    return dlsg::run_lines(dlsg::OP_NORMAL, (const float2*)x, (const float2*)maps, weights, w_strides, (const int*)plan, lmax,
+                           (float2*)x_out, (const float2*)aty, step, step_dev, epilogue, workspace, workspace_bytes,
+                           B, E, C, T, Y, X, stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,438 @@
+// Sampled-line path of the SENSE operator (sm_100a): same operator as sense_kernels.cuh
+//   SenseModel._forward_op / _adjoint_op   dl_cs/mri/transforms.py:84-98
+//   DC update                              dl_cs/models/unrolledswin.py:109
+// for k-space weights W that are zero on whole ky lines, which is what the reference's k-t sampling
+// masks are (dl_cs/mri/utils.py:69-79 get_mask of ky-undersampled data; 12x in config_recon.yaml).
+//
+// The 2-D transform is separable, so the axis order is free.  Here the Y axis goes first:
+//   forward :  cols_fwd_lines  tl[b,c,t,i,:] = DFT_Y( sum_e S x )[ky_i, :]      only the sampled lines ky_i are stored
+//              rows_lines<FWD> k[b,c,t,ky_i,:] = W * DFT_X( tl[i,:] )            unsampled lines of k are zero-filled
+//   adjoint :  rows_lines<ADJ> tl[i,:] = IDFT_X( W * k[ky_i,:] )
+//              cols_adj_lines  x = sum_c conj(S) * IDFT_Y( scatter(tl) )  (+ DC / REG epilogue)
+//   normal  :  cols_fwd_lines, rows_lines<NORMAL> (DFT_X, W^2, IDFT_X in place), cols_adj_lines
+// so the intermediate `tl` [B,C,T,lmax,X] holds n(b,t) <= lmax lines per image instead of Y, the X passes run on
+// those lines only, and the fused normal operator moves ~4x less HBM traffic than the dense path at 12x undersampling.
+// A line is "sampled" when any weight on it (over coils and kx) is non-zero, so the result equals the dense
+// path's for finite data (0 * k contributes exactly 0 there too); the plan is built once per weights tensor.
+#pragma once
+
+#include "sense_kernels.cuh"
+
+// Tuning knobs (defaults are what ships; overridden only by the variant builds of tools/build_variant.sh)
+#ifndef DLSG_LINES_ITEM_UNROLL
+#define DLSG_LINES_ITEM_UNROLL 2            // phase-A items unrolled together (full unrolling overflows the instruction cache)
+#endif
+#ifndef DLSG_LINES_FWD_MINB
+#define DLSG_LINES_FWD_MINB(RY) ColCfg<RY>::MINB
+#endif
+#ifndef DLSG_LINES_ADJ_MINB
+#define DLSG_LINES_ADJ_MINB(RY) ColCfg<RY>::MINB
+#endif
+#define DLSG_PRAGMA(x) _Pragma(#x)
+#define DLSG_UNROLL(n) DLSG_PRAGMA(unroll n)
+
+namespace dlsg {
+
+// Device-resident plan (int32), see dlsg_sense_line_plan_build:
+//   counts[b*T + t]          n(b,t)
+//   list  [(b*T + t)*Y + i]  ky of the i-th sampled line, ascending
+//   pos   [(b*T + t)*Y + ky] i with list[i] == ky, or -1
+struct LinePlan { const int* counts; const int* list; const int* pos; int lmax; };
+
+DLSG_DEVICE size_t idx_lines(const SenseDims& d, int lmax, int b, int c, int t, int i) {
+    return ((((size_t)b * d.C + c) * d.t_count + (t - d.t_begin)) * lmax + i) * (size_t)d.X;
+}
+
+// ---------------------------------------------------------------------------- plan
+// CTA = (b, t): flags the ky lines that carry any non-zero (or NaN) weight, then one thread compacts them.
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(256)
+sense_line_plan_kernel(const float* __restrict__ w, WeightStrides ws, int C, int T, int Y, int X,
+                       int* counts, int* list, int* pos) {
+    DLSG_DYN_SMEM(int, flag);                    // [Y]
+    const int bt = blockIdx.x, b = bt / T, t = bt - b * T;
+    for (int y = threadIdx.x; y < Y; y += blockDim.x) flag[y] = 0;
+    __syncthreads();
+    const int nc = ws.c ? C : 1, nx = ws.x ? X : 1, ny = ws.y ? Y : 1;   // broadcast axes are visited once
+    const long long total = (long long)nc * ny * nx;
+    const float* base = w + (b * ws.b + t * ws.t);
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+        const int x = (int)(i % nx);
+        const long long r = i / nx;
+        const int y = (int)(r % ny), c = (int)(r / ny);
+        if (__ldg(base + (c * ws.c + y * ws.y + x * ws.x)) != 0.f) flag[y] = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int y = 0; y < Y; ++y) {
+            const bool on = flag[ny == 1 ? 0 : y] != 0;
+            pos[(size_t)bt * Y + y] = on ? n : -1;
+            if (on) list[(size_t)bt * Y + n++] = y;
+        }
+        for (int i = n; i < Y; ++i) list[(size_t)bt * Y + i] = 0;
+        counts[bt] = n;
+    }
+}
+
+// ---------------------------------------------------------------------------- column passes
+template <int RY>
+struct ColLinesCfg {
+    static constexpr int Y = 32 * RY;
+    static constexpr int SW = ColCfg<RY>::SW, NT = ColCfg<RY>::NT, ITEMS = ColCfg<RY>::ITEMS, MINB = ColCfg<RY>::MINB;
+    static constexpr size_t SLAB = (size_t)Y * SW;                   // complex elements of one slab
+    static size_t tables() { return (size_t)Y * sizeof(float2) + (size_t)Y * sizeof(int); }
+    static size_t smem_fwd(int e_staged) { return (size_t)(e_staged + 1) * SLAB * sizeof(float2) + tables(); }
+    static size_t smem_adj(int E, int lmax) { return ((size_t)(1 + E) * SLAB + (size_t)lmax * SW) * sizeof(float2) + tables(); }
+};
+
+// asynchronous copy of the SW-column slab of one image (row stride Xs) into shared memory [Y][SW]
+template <int RY>
+DLSG_DEVICE void fetch_slab(float2* slab, const float2* img, int Xs, int rows, int tid) {
+    constexpr int SW = ColLinesCfg<RY>::SW, NT = ColLinesCfg<RY>::NT;
+#pragma unroll 4
+    for (int q = tid; q < rows * (SW / 2); q += NT) {
+        const int yy = q / (SW / 2), ch = q - yy * (SW / 2);
+        cp_async16(slab + yy * SW + 2 * ch, img + (size_t)yy * Xs + 2 * ch);
+    }
+}
+
+// twiddles of the radix-RY stage and the line table of this (b,t): sp[ky] = pos[ky] * mul, or -1 when ky is not sampled
+template <int RY>
+DLSG_DEVICE void fill_col_tables(float2* twy, int* sp, const int* pos, int mul, int tid) {
+    constexpr int Y = 32 * RY, NT = ColLinesCfg<RY>::NT;
+    for (int i = tid; i < Y; i += NT) {
+        const int l = i / RY, k2 = i - l * RY;
+        int m = (l * k2) % Y;
+        if (2 * m > Y) m -= Y;
+        float sn, cs;
+        sincospif((float)(2 * m) / (float)Y, &sn, &cs);
+        twy[i] = make_float2(cs, -sn);           // forward sign; the inverse uses the conjugate
+        const int p = __ldg(pos + i);
+        sp[i] = (p >= 0) ? p * mul : -1;
+    }
+}
+
+// tl[b,c,t,i,kx] = DFT_Y( sum_e maps[b,e,c,:,kx] * x[b,e,t,:,kx] )[ky_i]   for the sampled lines of (b,t).
+// CTA = (SW-column slab, t, b), all coils.  The coil's map slab arrives by cp.async in the work slab while the
+// previous coil's radix-32 runs; XS: the x slabs are staged once per CTA (else read through L1/L2 per coil).
+template <int RY, bool XS>
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(ColCfg<RY>::NT, DLSG_LINES_FWD_MINB(RY))
+sense_cols_fwd_lines_kernel(const float2* __restrict__ x, const float2* __restrict__ maps,
+                            float2* __restrict__ tl_out, LinePlan lp, SenseDims d) {
+    using Cfg = ColLinesCfg<RY>;
+    constexpr int ITEMS = Cfg::ITEMS, SW = Cfg::SW, Y = Cfg::Y;
+    DLSG_DYN_SMEM(float2, smem);
+    const int es = XS ? d.E : 0;
+    float2* xs = smem;                           // [e][Y][SW]
+    float2* work = smem + (size_t)es * Cfg::SLAB;
+    float2* twy = work + Cfg::SLAB;
+    int* sp = reinterpret_cast<int*>(twy + Y);
+    const int tid = threadIdx.x, col = tid % SW, grp = tid / SW;
+
+    const int ncolblk = d.X / SW;
+    long long u = blockIdx.x;
+    const int colblk = (int)(u % ncolblk); u /= ncolblk;
+    const int tl = (int)(u % d.t_count);
+    const int b = (int)(u / d.t_count);
+    const int t = d.t_begin + tl;
+    const int kx0 = colblk * SW, kx = kx0 + col;
+    const int bt = b * d.T + t;
+    if (__ldg(lp.counts + bt) == 0) return;      // nothing sampled in this frame (uniform over the CTA)
+
+    if (XS)
+        for (int e = 0; e < d.E; ++e) fetch_slab<RY>(xs + (size_t)e * Cfg::SLAB, x + idx_x(d, b, e, t, 0) + kx0, d.X, Y, tid);
+    fetch_slab<RY>(work, maps + idx_maps(d, b, 0, 0, 0) + kx0, d.X, Y, tid);
+    cp_async_commit();
+    fill_col_tables<RY>(twy, sp, lp.pos + (size_t)bt * Y, d.X, tid);    // sp = element offset of the line in tl
+
+#pragma unroll 1
+    for (int c = 0; c < d.C; ++c) {
+        cp_async_wait_group0();
+        __syncthreads();                         // slab(s) landed, tables written
+        // ---- phase A (in place): coil image column, radix-RY over y = l + 32 j, twiddle
+DLSG_UNROLL(DLSG_LINES_ITEM_UNROLL)
+        for (int i = 0; i < ITEMS; ++i) {
+            const int l = grp + i * RY;
+            if (l < 32) {
+                float2 v[RY];
+#pragma unroll
+                for (int j = 0; j < RY; ++j) {
+                    const int yy = l + 32 * j;
+                    float2 a = cmul(work[yy * SW + col], XS ? xs[yy * SW + col] : __ldg(x + idx_x(d, b, 0, t, yy) + kx));
+#pragma unroll 1
+                    for (int e = 1; e < d.E; ++e)    // further map sets: through the cache (rare; keeps the code small)
+                        a = cfma(__ldg(maps + idx_maps(d, b, e, c, yy) + kx),
+                                 XS ? xs[(size_t)e * Cfg::SLAB + yy * SW + col] : __ldg(x + idx_x(d, b, e, t, yy) + kx), a);
+                    v[j] = a;
+                }
+                Dft<RY, -1>::run(v);
+#pragma unroll
+                for (int k2 = 0; k2 < RY; ++k2)
+                    work[(k2 * 32 + l) * SW + col] = (k2 == 0) ? v[0] : cmul(v[k2], twy[l * RY + k2]);
+            }
+        }
+        __syncthreads();
+        // ---- phase B: radix-32 over l for (k2 = grp, column); ky = RY*k1 + k2
+        float2 r[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = work[(grp * 32 + i) * SW + col];
+        __syncthreads();                         // the work slab is free: the next coil's maps land during the radix-32
+        if (c + 1 < d.C) fetch_slab<RY>(work, maps + idx_maps(d, b, 0, c + 1, 0) + kx0, d.X, Y, tid);
+        cp_async_commit();
+        Dft<32, -1>::run(r);
+        float2* outp = tl_out + idx_lines(d, lp.lmax, b, c, t, 0) + kx;
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) {
+            const int off = sp[RY * k1 + grp];
+            if (off >= 0) outp[off] = r[k1];
+        }
+    }
+}
+
+// out_e[b,t,y,kx] = EPI( sum_c conj(maps[b,e,c,y,kx]) * IDFT_Y( scatter of tl[b,c,t,:,kx] to its ky lines )[y] )
+// CTA = (SW-column slab, t, b), all coils.  The accumulator of map set 0 stays in registers; the coil's map slab is
+// prefetched one coil ahead (cp.async) into its own buffer, the sampled lines of the next coil into a small one.
+template <int RY>
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(ColCfg<RY>::NT, DLSG_LINES_ADJ_MINB(RY))
+sense_cols_adj_lines_kernel(const float2* __restrict__ tl_in, const float2* __restrict__ maps, float2* __restrict__ out,
+                            const float2* __restrict__ xin, const float2* __restrict__ aty,
+                            float step_host, const float* __restrict__ step_dev, int epi, LinePlan lp, SenseDims d) {
+    using Cfg = ColLinesCfg<RY>;
+    constexpr int ITEMS = Cfg::ITEMS, SW = Cfg::SW, Y = Cfg::Y, NT = Cfg::NT;
+    DLSG_DYN_SMEM(float2, smem);
+    float2* work = smem;                                   // [Y][SW] exchange between the two radix stages
+    float2* mbuf = smem + Cfg::SLAB;                       // [Y][SW] maps[b,0,c,:,slab] of the coil being accumulated
+    float2* accx = mbuf + Cfg::SLAB;                       // [e-1][Y][SW] accumulators of map sets e >= 1 (thread-private slots)
+    float2* cmp = accx + (size_t)(d.E - 1) * Cfg::SLAB;    // [lmax][SW] sampled lines of the coil being transformed
+    float2* twy = cmp + (size_t)lp.lmax * SW;
+    int* sp = reinterpret_cast<int*>(twy + Y);
+    const int tid = threadIdx.x, col = tid % SW, grp = tid / SW;
+
+    const int ncolblk = d.X / SW;
+    long long u = blockIdx.x;
+    const int colblk = (int)(u % ncolblk); u /= ncolblk;
+    const int tl = (int)(u % d.t_count);
+    const int b = (int)(u / d.t_count);
+    const int t = d.t_begin + tl;
+    const int kx0 = colblk * SW, kx = kx0 + col;
+    const int bt = b * d.T + t;
+    const int n = __ldg(lp.counts + bt);
+    const float step = step_dev ? __ldg(step_dev) : step_host;
+
+    auto fetch_cmp = [&](int c) {
+        const float2* src = tl_in + idx_lines(d, lp.lmax, b, c, t, 0) + kx0;
+        for (int q = tid; q < n * (SW / 2); q += NT) {
+            const int i = q / (SW / 2), ch = q - i * (SW / 2);
+            cp_async16(cmp + i * SW + 2 * ch, src + (size_t)i * d.X + 2 * ch);
+        }
+    };
+    float2 acc0[32];
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) acc0[k1] = make_float2(0.f, 0.f);
+
+    if (n > 0) {
+        fetch_cmp(0);
+        fetch_slab<RY>(mbuf, maps + idx_maps(d, b, 0, 0, 0) + kx0, d.X, Y, tid);
+    }
+    cp_async_commit();
+    fill_col_tables<RY>(twy, sp, lp.pos + (size_t)bt * Y, SW, tid);     // sp = element offset of the line in cmp
+    cp_async_wait_group0();
+    __syncthreads();
+
+#pragma unroll 1
+    for (int c = 0; c < d.C && n > 0; ++c) {
+        // ---- phase A: gather the sampled lines (zeros elsewhere), radix-RY over ky = l + 32 j, twiddle
+DLSG_UNROLL(DLSG_LINES_ITEM_UNROLL)
+        for (int i = 0; i < ITEMS; ++i) {
+            const int l = grp + i * RY;
+            if (l < 32) {
+                float2 v[RY];
+#pragma unroll
+                for (int j = 0; j < RY; ++j) {
+                    const int off = sp[l + 32 * j];
+                    v[j] = (off >= 0) ? cmp[off + col] : make_float2(0.f, 0.f);
+                }
+                Dft<RY, +1>::run(v);
+#pragma unroll
+                for (int k2 = 0; k2 < RY; ++k2)
+                    work[(k2 * 32 + l) * SW + col] = (k2 == 0) ? v[0] : cmulc(v[k2], twy[l * RY + k2]);
+            }
+        }
+        __syncthreads();
+        if (c + 1 < d.C) fetch_cmp(c + 1);       // the line buffer has been consumed
+        cp_async_commit();
+        // ---- phase B: radix-32 over l for (k2 = grp, column); y = RY*k1 + k2
+        float2 r[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = work[(grp * 32 + i) * SW + col];
+        Dft<32, +1>::run(r);
+        cp_async_wait_group1();                  // this coil's maps (committed before the lines of the next coil)
+        __syncthreads();
+        {
+            const float2* m0 = mbuf + grp * SW + col;    // y = RY*k1 + grp
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) acc0[k1] = cfmac(r[k1], m0[RY * k1 * SW], acc0[k1]);
+        }
+#pragma unroll 1
+        for (int e = 1; e < d.E; ++e) {          // further map sets: maps through the cache (rare; keeps the code small)
+            float2* ae = accx + (size_t)(e - 1) * Cfg::SLAB + grp * SW + col;
+            const float2* me = maps + idx_maps(d, b, e, c, grp) + kx;
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) {
+                const float2 prev = (c == 0) ? make_float2(0.f, 0.f) : ae[RY * k1 * SW];
+                ae[RY * k1 * SW] = cfmac(r[k1], __ldg(me + (size_t)RY * k1 * d.X), prev);
+            }
+        }
+        cp_async_wait_group0();
+        __syncthreads();                         // map buffer and work slab are free, the next coil's lines have landed
+        if (c + 1 < d.C) fetch_slab<RY>(mbuf, maps + idx_maps(d, b, 0, c + 1, 0) + kx0, d.X, Y, tid);
+        cp_async_commit();
+    }
+    // ---- epilogue (each thread owns its outputs: y = RY*k1 + grp, column kx)
+    // out = a * (acc - av) + bx * xv :  PLAIN (a, bx) = (1, 0);  DC (step, 1) with av = aty;  REG (1, step)
+    const float ea = (epi == EPI_DC) ? step : 1.f;
+    const float eb = (epi == EPI_DC) ? 1.f : (epi == EPI_REG ? step : 0.f);
+    const size_t rstride = (size_t)RY * d.X;      // consecutive outputs of a thread are RY image rows apart
+    // x and A^H y are read in batches of 16 rows with all loads of a batch in flight together (the accumulators
+    // hold 64 registers, so the compiler would otherwise serialise one DRAM latency per row)
+    auto finish16 = [&](const float2* accv, const float2* xp, const float2* ap, float2* op) {
+        float2 xv[16], av[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xv[i] = av[i] = make_float2(0.f, 0.f);
+        if (epi != EPI_PLAIN) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xv[i] = __ldg(xp + i * rstride);
+        }
+        if (epi == EPI_DC) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) av[i] = __ldg(ap + i * rstride);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            op[i * rstride] = make_float2(fmaf(ea, accv[i].x - av[i].x, eb * xv[i].x), fmaf(ea, accv[i].y - av[i].y, eb * xv[i].y));
+    };
+    {
+        const size_t g0 = idx_x(d, b, 0, t, grp) + kx;
+        finish16(acc0, xin + g0, aty + g0, out + g0);
+        finish16(acc0 + 16, xin + g0 + 16 * rstride, aty + g0 + 16 * rstride, out + g0 + 16 * rstride);
+    }
+#pragma unroll 1
+    for (int e = 1; e < d.E; ++e) {
+        const float2* ae = accx + (size_t)(e - 1) * Cfg::SLAB + grp * SW + col;
+        const size_t g0 = idx_x(d, b, e, t, grp) + kx;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            float2 a16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a16[i] = (n > 0) ? ae[RY * (16 * h + i) * SW] : make_float2(0.f, 0.f);
+            finish16(a16, xin + g0 + 16 * h * rstride, aty + g0 + 16 * h * rstride, out + g0 + 16 * h * rstride);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- row pass on the sampled lines
+//   MODE_FWD   : k[b,c,t,ky_i,:] = W*scale * DFT_X(tl[b,c,t,i,:])
+//   MODE_ADJ   : tl[b,c,t,i,:]   = IDFT_X(W*scale * k[b,c,t,ky_i,:])
+//   MODE_NORMAL: tl              = IDFT_X((W*scale)^2 * DFT_X(tl))            in place
+// CTA (4 warps) = (b, t); the flattened (coil, line) items are walked in warp batches of NB = 32/RX rows.
+template <int RX, int MODE>
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(128, 3)
+sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict__ w, WeightStrides ws, float scale,
+                        LinePlan lp, SenseDims d) {
+    using Cfg = RowCfg<RX>;
+    constexpr int NB = Cfg::NB;
+    constexpr int DIR = (MODE == MODE_ADJ) ? +1 : -1;
+    constexpr int NBUF = (MODE == MODE_NORMAL) ? 2 : 1;
+    DLSG_DYN_SMEM(float2, smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* buf = smem + warp * (NBUF * Cfg::BUF);
+    float2* buf2 = buf + (NBUF - 1) * Cfg::BUF;  // way back of the normal operator (aliases buf otherwise, unused)
+    const int tl = (int)(blockIdx.x % d.t_count), b = (int)(blockIdx.x / d.t_count);
+    const int t = d.t_begin + tl;
+    const int bt = b * d.T + t;
+    const int n = __ldg(lp.counts + bt);
+    const int items = d.C * n;
+    const int* list = lp.list + (size_t)bt * d.Y;
+
+    float2 tw[RX];
+    lane_twiddles<RX, DIR>(lane, tw);
+
+    for (int it0 = warp * NB; it0 < items; it0 += Cfg::WARPS * NB) {
+        const int nrows = min(NB, items - it0);
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
+            if (r < nrows) {
+                const int item = it0 + r, c = item / n, i = item - c * n;
+                const int ky = __ldg(list + i);
+                const float2* s = src + ((MODE == MODE_ADJ) ? idx_k(d, b, c, t, ky) : idx_lines(d, lp.lmax, b, c, t, i)) + lane;
+                float2 v[RX];
+#pragma unroll
+                for (int j = 0; j < RX; ++j) {
+                    v[j] = s[32 * j];
+                    if (MODE == MODE_ADJ) v[j] = cscale(v[j], scale * load_w(w, ws, b, c, t, ky, lane + 32 * j));
+                }
+                Dft<RX, DIR>::run(v);
+                float2* o = buf + (r * RX) * Cfg::S1 + lane;
+#pragma unroll
+                for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmul(v[k2], tw[k2]);
+            }
+        }
+        __syncwarp();
+        row_radix32<RX, DIR>(buf, lane, nrows);
+        if (MODE == MODE_NORMAL) {
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {
+                if (r < nrows) {
+                    const int item = it0 + r, c = item / n, i = item - c * n;
+                    const int ky = __ldg(list + i);
+                    float2 v[RX];
+#pragma unroll
+                    for (int j = 0; j < RX; ++j) {
+                        const float wv = scale * load_w(w, ws, b, c, t, ky, lane + 32 * j);
+                        v[j] = cscale(buf[r * Cfg::S2 + lane + 32 * j], wv * wv);
+                    }
+                    Dft<RX, +1>::run(v);
+                    float2* o = buf2 + (r * RX) * Cfg::S1 + lane;
+#pragma unroll
+                    for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmulc(v[k2], tw[k2]);
+                }
+            }
+            __syncwarp();
+            row_radix32<RX, +1>(buf2, lane, nrows);
+        }
+        const float2* res = (MODE == MODE_NORMAL) ? buf2 : buf;
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
+            if (r < nrows) {
+                const int item = it0 + r, c = item / n, i = item - c * n;
+                const int ky = __ldg(list + i);
+                float2* o = dst + ((MODE == MODE_FWD) ? idx_k(d, b, c, t, ky) : idx_lines(d, lp.lmax, b, c, t, i)) + lane;
+                const float2* sv = res + r * Cfg::S2 + lane;
+#pragma unroll
+                for (int j = 0; j < RX; ++j) {
+                    float2 q = sv[32 * j];
+                    if (MODE == MODE_FWD) q = cscale(q, scale * load_w(w, ws, b, c, t, ky, lane + 32 * j));
+                    o[32 * j] = q;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Forward operator: the ky lines of k that carry no weight are zero.  CTA = (c, t, b).
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(256)
+sense_zero_unsampled_kernel(float2* __restrict__ k, LinePlan lp, SenseDims d) {
+    long long u = blockIdx.x;
+    const int c = (int)(u % d.C); u /= d.C;
+    const int tl = (int)(u % d.t_count);
+    const int b = (int)(u / d.t_count);
+    const int t = d.t_begin + tl;
+    const int* pos = lp.pos + (size_t)(b * d.T + t) * d.Y;
+    float4* img = reinterpret_cast<float4*>(k + idx_k(d, b, c, t, 0));
+    const int per_row = d.X / 2;                 // X is a multiple of 32 on this path
+    for (int q = threadIdx.x; q < d.Y * per_row; q += blockDim.x)
+        if (__ldg(pos + q / per_row) < 0) img[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+}  // namespace dlsg

@@ -8,6 +8,12 @@ unrolledswin.py:91, unrolled.py:86) run unchanged.  Arithmetic happens in the ha
 sm_100a kernels behind the C ABI of include/dlsg_b200.h; torch is used for device memory,
 streams and autograd plumbing only.  There is no CPU path: CPU tensors raise.
 
+Sampled lines: when the weights are a k-t sampling mask (whole ky lines of W are zero, which is what
+`get_mask` of undersampled data gives, dl_cs/mri/utils.py:69-79) the operator runs the Y transform first and
+keeps only the lines that carry weight (csrc/sense_lines.cuh); same results, a fraction of the HBM traffic.
+The plan is built on first use (one pass over W and one scalar read-back) and cached with the weights.
+`DLSG_SAMPLED_LINES=0` forces the dense kernels.
+
 Beyond the reference interface the operator offers two fused entries the solvers may use
 when present (they fall back to two calls otherwise):
     A.normal(x)              == A(A(x), adjoint=True)
@@ -42,6 +48,43 @@ def _require_cuda_c64(t: torch.Tensor, what: str) -> None:
 # --------------------------------------------------------------------------------------
 # low-level launcher shared by SenseModel and FFT
 # --------------------------------------------------------------------------------------
+_LINES_MAX_FRACTION = 0.5      # use the sampled-line kernels when at most this share of the ky lines carries weight
+
+
+def _sampled_lines_enabled() -> bool:
+    return os.environ.get("DLSG_SAMPLED_LINES", "1") != "0"
+
+
+def _launch_lines(kind: str, data, maps5, wexp, dims, lines, aty=None, step=None) -> torch.Tensor:
+    """Same contract as _launch, through the sampled-line entry points; lines = (plan int32 tensor, lmax)."""
+    lib = _lib.load()
+    B, E, C, T, Y, X = dims
+    dev = data.device
+    plan, lmax = lines
+    out = torch.empty((B, C, T, Y, X) if kind == "fwd" else (B, E, T, Y, X), dtype=torch.complex64, device=dev)
+    wstr = (ctypes.c_longlong * 5)(*wexp.stride())
+    nbytes = lib.dlsg_sense_lines_workspace_bytes(B, C, T, X, lmax, _workspace_budget())
+    work = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        tail = (work.data_ptr(), nbytes, B, E, C, T, Y, X, stream)
+        head = (maps5.data_ptr(), wexp.data_ptr(), wstr, plan.data_ptr(), lmax)
+        if kind == "fwd":
+            st = lib.dlsg_sense_forward_lines_c64(data.data_ptr(), *head, out.data_ptr(), *tail)
+        elif kind == "adj":
+            st = lib.dlsg_sense_adjoint_lines_c64(data.data_ptr(), *head, out.data_ptr(), *tail)
+        else:
+            epi = {"normal": 0, "dc": 1, "reg": 2}[kind]
+            if isinstance(step, torch.Tensor):
+                s_host, s_dev = 0.0, step.data_ptr()
+            else:
+                s_host, s_dev = (0.0 if step is None else float(step)), None
+            st = lib.dlsg_sense_normal_lines_c64(data.data_ptr(), aty.data_ptr() if aty is not None else None, *head,
+                                                 s_host, s_dev, epi, out.data_ptr(), *tail)
+    _lib.check(st, f"dlsg_sense_{kind}_lines")
+    return out
+
+
 def _launch(kind: str, data: torch.Tensor, maps5: Optional[torch.Tensor], wexp: Optional[torch.Tensor],
             dims, ndims: int, aty: Optional[torch.Tensor] = None, step=None) -> torch.Tensor:
     """kind in {'fwd','adj','normal','reg','dc'}; dims = (B,E,C,T,Y,X); tensors already validated/contiguous."""
@@ -179,6 +222,7 @@ class SenseModel(nn.Module):
             self.weights = weights
         self._maps5 = None
         self._w32 = None
+        self._line_plans = {}
 
     # ---- reference interface ---------------------------------------------------------
     def forward(self, data: torch.Tensor, adjoint: Optional[bool] = False) -> torch.Tensor:
@@ -245,6 +289,28 @@ class SenseModel(nn.Module):
             raise ValueError(f"weights must broadcast to [batch, coils, t, y, x]; got {tuple(w32.shape)}")
         return w32.expand(B, C, T, Y, X)   # raises like torch broadcasting does when incompatible
 
+    def _line_plan(self, dims, wexp, ndims):
+        """-> (plan, lmax) when the weights leave at most half of the ky lines sampled, else None (dense kernels)."""
+        if wexp is None or ndims != 2 or not isinstance(self.weights, torch.Tensor) or not _sampled_lines_enabled():
+            return None
+        key = tuple(dims)
+        if key not in self._line_plans:
+            lib = _lib.load()
+            B, E, C, T, Y, X = dims
+            plan = None
+            if B * T > 0 and lib.dlsg_sense_lines_supported(E, Y, X, 1):
+                buf = torch.empty(int(lib.dlsg_sense_line_plan_bytes(B, T, Y)) // 4, dtype=torch.int32, device=wexp.device)
+                wstr = (ctypes.c_longlong * 5)(*wexp.stride())
+                with torch.cuda.device(wexp.device):
+                    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+                    _lib.check(lib.dlsg_sense_line_plan_build(wexp.data_ptr(), wstr, B, C, T, Y, X, buf.data_ptr(), stream),
+                               "dlsg_sense_line_plan_build")
+                lmax = max(1, int(buf[: B * T].max().item()))          # the one read-back: sizes the intermediate
+                if lmax <= _LINES_MAX_FRACTION * Y and lib.dlsg_sense_lines_supported(E, Y, X, lmax):
+                    plan = (buf, lmax)
+            self._line_plans[key] = plan
+        return self._line_plans[key]
+
     def _dims(self, data: torch.Tensor, kind: str):
         maps5 = self._prepared_maps()
         Bm, E, C, Y, X = maps5.shape
@@ -296,7 +362,11 @@ class SenseModel(nn.Module):
                     step = step.detach()
                 else:
                     step = float(step)
-        return _launch(kind, data, maps5, wexp, dims, self._kernel_ndims(dims), aty, step)
+        ndims = self._kernel_ndims(dims)
+        lines = self._line_plan(dims, wexp, ndims) if data.numel() else None
+        if lines is not None:
+            return _launch_lines(kind, data, maps5, wexp, dims, lines, aty, step)
+        return _launch(kind, data, maps5, wexp, dims, ndims, aty, step)
 
 
 class _SenseFn(torch.autograd.Function):

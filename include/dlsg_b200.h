@@ -98,6 +98,54 @@ int dlsg_sense_dc_step_c64(const void* x, const void* aty, const void* maps, con
                            int B, int E, int C, int T, int Y, int X, int ndims, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Sampled-line path of the same operators.  The reference's k-space weights are k-t sampling masks
+ * (dl_cs/mri/utils.py:69-79 get_mask; scripts/reconstruct.py:151): whole ky lines of W are zero.
+ * With the Y transform done first, only the lines that carry a non-zero weight need the X
+ * transform and the HBM intermediate, so the operators below compute exactly what the dense entry
+ * points above compute (for finite data: 0 * k contributes 0 in both), with an intermediate of
+ * lmax lines per image instead of Y.  2-D only (ndims == 2), Y and X in {32..320 step 32*R} as
+ * accepted by dlsg_sense_lines_supported; everything else stays on the dense entry points.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Bytes of the device-resident line plan for B slices of T frames with Y lines:
+ * int32 counts[B*T] | list[B*T*Y] | pos[B*T*Y]   (n(b,t) = counts; list = sampled ky ascending;
+ * pos[ky] = index of ky in list or -1). */
+size_t dlsg_sense_line_plan_bytes(int B, int T, int Y);
+
+/* Builds the plan from the weights (same addressing as above; one pass over W, run once per
+ * SenseModel, i.e. where the reference stores `self.weights`, transforms.py:79-82).  A line is
+ * sampled when any weight on it over (c, kx) is non-zero or NaN.  The caller reads counts[] back
+ * and passes lmax >= max n(b,t) (>= 1) to the operators. */
+int dlsg_sense_line_plan_build(const float* weights, const long long* w_strides, int B, int C, int T, int Y, int X,
+                               void* plan, void* stream);
+
+/* 1 when the sampled-line kernels cover this problem (compiled radices and shared-memory budget). */
+int dlsg_sense_lines_supported(int E, int Y, int X, int lmax);
+
+/* Workspace for the sampled-line operators: B*C*T*lmax*X complex64 holds everything at once; any
+ * multiple of one slice (C*T*lmax*X*8 bytes, the minimum) is accepted and walked in slice chunks. */
+size_t dlsg_sense_lines_workspace_bytes(int B, int C, int T, int X, int lmax, size_t budget_bytes);
+
+/* SenseModel._forward_op (transforms.py:92-98) / _adjoint_op (:84-90) through the sampled lines. */
+int dlsg_sense_forward_lines_c64(const void* x, const void* maps, const float* weights, const long long* w_strides,
+                                 const void* plan, int lmax, void* k_out, void* workspace, size_t workspace_bytes,
+                                 int B, int E, int C, int T, int Y, int X, void* stream);
+int dlsg_sense_adjoint_lines_c64(const void* k, const void* maps, const float* weights, const long long* w_strides,
+                                 const void* plan, int lmax, void* x_out, void* workspace, size_t workspace_bytes,
+                                 int B, int E, int C, int T, int Y, int X, void* stream);
+
+/* A^H A x with the epilogues of the dense entry points, selected by `epilogue`:
+ *   0  x_out = A^H A x                                   (dlsg_sense_normal_c64)
+ *   1  x_out = x + step * (A^H A x - aty)                (dlsg_sense_dc_step_c64, unrolledswin.py:109)
+ *   2  x_out = A^H A x + step * x                        (dlsg_sense_normal_reg_c64, unrolledswin.py:154)
+ * step_dev (device pointer) overrides step when non-NULL; aty is only read for epilogue 1. */
+int dlsg_sense_normal_lines_c64(const void* x, const void* aty, const void* maps, const float* weights,
+                                const long long* w_strides, const void* plan, int lmax,
+                                float step, const float* step_dev, int epilogue, void* x_out,
+                                void* workspace, size_t workspace_bytes,
+                                int B, int E, int C, int T, int Y, int X, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Shifted-window attention of the Swin denoiser block
  * (dl_cs/models/video_swin_transformer_mri_downsample.py).  All tensors fp32, contiguous.
  * `window` / `shift` are the values actually used for this volume, i.e. after get_window_size (:72-85).

@@ -35,8 +35,15 @@ def to_np(t):
     return t.detach().cpu().numpy()
 
 
+@pytest.fixture(params=["sampled-lines", "dense"])
+def kernel_path(request, monkeypatch):
+    """Masks with empty ky lines take the sampled-line kernels by default; every parity case also runs on the dense kernels."""
+    monkeypatch.setenv("DLSG_SAMPLED_LINES", "1" if request.param == "sampled-lines" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("name", list(CASES))
-def test_matches_reference_golden_vectors(golden_cases, dev, name):
+def test_matches_reference_golden_vectors(golden_cases, dev, name, kernel_path):
     inp, ref = golden_cases[name]
     A = make_model(inp["maps"], inp["weights"], dev)
     assert A.fft.ndims == int(ref["ndims"])
@@ -69,7 +76,7 @@ SWEEP = [
 
 
 @pytest.mark.parametrize("case", SWEEP)
-def test_matches_oracle_on_seeded_inputs(dev, case):
+def test_matches_oracle_on_seeded_inputs(dev, case, kernel_path):
     B, E, C, T, Y, X, wkind = case
     rng = np.random.default_rng(11)
     maps, x, mask = so.synthetic_problem(B, E, C, T, Y, X, seed=1000)
@@ -84,6 +91,46 @@ def test_matches_oracle_on_seeded_inputs(dev, case):
     assert rel_l2(to_np(A.normal(xd)), so.sense_normal(x.astype(np.complex128), m128, w)) < TOL
     ref_dc = so.dc_step(x.astype(np.complex128), aty.astype(np.complex128), m128, w, -2.0)
     assert rel_l2(to_np(A.dc_step(xd, ad, -2.0)), ref_dc) < TOL
+
+
+def test_sampled_line_path_is_selected_and_agrees_with_dense(dev, monkeypatch):
+    """12x k-t mask at the cine size: the plan is built, the sampled-line kernels run, and every operator agrees with the
+    dense kernels to fp32 rounding; per-coil real weights, a frame without samples, and a dense mask (falls back)."""
+    from dl_swin_gan_b200.mri import SenseModel
+    B, E, C, T, Y, X = 3, 1, 8, 6, 192, 160
+    g = torch.Generator(device=dev).manual_seed(5)
+
+    def cn(*s):
+        return torch.view_as_complex(torch.randn(*s, 2, generator=g, device=dev))
+
+    maps = cn(B, E, C, 1, Y, X) / C ** 0.5
+    x, k, aty = cn(B, E, T, Y, X), cn(B, C, T, Y, X), cn(B, E, T, Y, X)
+    lines = (torch.rand(B, 1, T, Y, 1, generator=g, device=dev) < 1 / 12).float()
+    lines[1, :, 2] = 0                                                    # a frame with no sampled line at all
+    mask = lines.expand(B, 1, T, Y, X).contiguous()
+    mask[..., : X // 4] = 0
+    percoil = mask * torch.randn(B, C, T, Y, X, generator=g, device=dev)  # real-valued weights that differ per coil
+    for w in (mask, percoil):
+        outs = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("DLSG_SAMPLED_LINES", mode)
+            A = SenseModel(maps, weights=w)
+            outs[mode] = [A(x), A(k, adjoint=True), A.normal(x), A.dc_step(x, aty, -2.0), A.normal_reg(x, 0.3)]
+            plan = A._line_plans.get((B, E, C, T, Y, X))
+            if mode == "1":
+                counts = (w != 0).any(dim=1).any(dim=-1).sum(-1)          # [B, T]
+                assert plan is not None and plan[1] == int(counts.max())
+                assert torch.equal(plan[0][: B * T].cpu(), counts.flatten().to(torch.int32).cpu())
+            else:
+                assert plan is None
+        for a, b in zip(outs["1"], outs["0"]):
+            assert rel_l2(to_np(a), to_np(b)) < 2e-6
+        assert not outs["1"][0][(w == 0).expand(B, C, T, Y, X)].any()     # forward: unsampled samples are exact zeros
+    monkeypatch.setenv("DLSG_SAMPLED_LINES", "1")
+    dense = (torch.rand(B, 1, T, Y, 1, generator=g, device=dev) < 0.7).float().expand(B, 1, T, Y, X).contiguous()
+    A = SenseModel(maps, weights=dense)
+    A(x)
+    assert A._line_plans[(B, E, C, T, Y, X)] is None                      # more than half of the lines sampled: dense kernels
 
 
 def test_workspace_chunking_does_not_change_results(dev, monkeypatch):

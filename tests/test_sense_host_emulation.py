@@ -126,3 +126,104 @@ def test_kt_kernels_emulated(sense_emu_lib):
     assert lib.dlsg_sliding_window_c64(ptr(s), ptr(avg), 2, 7, 12, 7, 0, 1e-12, 1e-6, None) == 0
     assert rel_l2(avg, so.time_average(s, 1)) < 1e-6
     assert lib.dlsg_sliding_window_c64(ptr(s), ptr(out), 2, 7, 12, 9, 1, 1e-12, 1e-6, None) == -1
+
+
+# ---------------------------------------------------------------------------- sampled-line path (sense_lines.cuh)
+def _lines_lib(sense_emu_lib):
+    lib = ctypes.CDLL(sense_emu_lib)
+    i, sz = ctypes.c_int, ctypes.c_size_t
+    lib.dlsg_sense_line_plan_bytes.restype = sz
+    lib.dlsg_sense_line_plan_bytes.argtypes = [i, i, i]
+    lib.dlsg_sense_line_plan_build.argtypes = [vp, vp, i, i, i, i, i, vp, vp]
+    lib.dlsg_sense_lines_supported.argtypes = [i, i, i, i]
+    lib.dlsg_sense_lines_workspace_bytes.restype = sz
+    lib.dlsg_sense_lines_workspace_bytes.argtypes = [i, i, i, i, i, sz]
+    tail = [vp, sz] + [i] * 6 + [vp]
+    lib.dlsg_sense_forward_lines_c64.argtypes = [vp, vp, vp, vp, vp, i, vp] + tail
+    lib.dlsg_sense_adjoint_lines_c64.argtypes = [vp, vp, vp, vp, vp, i, vp] + tail
+    lib.dlsg_sense_normal_lines_c64.argtypes = [vp, vp, vp, vp, vp, vp, i, ctypes.c_float, vp, i, vp] + tail
+    return lib
+
+
+def _line_weights(rng, B, C, T, Y, X, kind):
+    """k-t style weights: a few ky lines per (slice, frame); 'mask' = 0/1 broadcast over coils with an empty kx quarter,
+    'coil' = real-valued per-coil weights on those lines, 'ragged' = different line counts per frame incl. an empty one."""
+    w = np.zeros((B, C if kind == "coil" else 1, T, Y, X), np.float32)
+    for b in range(B):
+        for t in range(T):
+            nl = 0 if (kind == "ragged" and t == 1) else 3 + (2 * t + b) % 4
+            lines = rng.choice(Y, size=nl, replace=False)
+            for c in range(w.shape[1]):
+                w[b, c, t, lines, :] = rng.standard_normal((nl, X)) if kind == "coil" else 1.0
+    if kind == "mask":
+        w[..., : X // 4] = 0
+    return w
+
+
+LINE_CASES = [
+    (1, 1, 2, 2, 32, 32, "mask", 0),
+    (2, 2, 3, 3, 64, 96, "coil", 0),
+    (2, 1, 2, 3, 96, 64, "ragged", 1),                      # one slice per workspace chunk, a frame without lines
+    (1, 3, 2, 2, 64, 160, "mask", 0),                       # E = 3: maps of e >= 1 read through the cache
+]
+
+
+@pytest.mark.parametrize("B,E,C,T,Y,X,kind,budget", LINE_CASES)
+def test_emulated_sampled_line_path_matches_oracle(sense_emu_lib, B, E, C, T, Y, X, kind, budget):
+    lib = _lines_lib(sense_emu_lib)
+    rng = np.random.default_rng(11)
+    maps, x, _ = so.synthetic_problem(B, E, C, T, Y, X, seed=5)
+    w = _line_weights(rng, B, C, T, Y, X, kind)
+    k = (rng.standard_normal((B, C, T, Y, X)) + 1j * rng.standard_normal((B, C, T, Y, X))).astype(np.complex64)
+    aty = (rng.standard_normal((B, E, T, Y, X)) + 1j * rng.standard_normal((B, E, T, Y, X))).astype(np.complex64)
+    m5 = np.ascontiguousarray(maps[:, :, :, 0])
+    wb = np.broadcast_to(w, (B, C, T, Y, X))
+    ws = (ctypes.c_longlong * 5)(*[s // 4 for s in wb.strides])
+
+    plan = np.full(lib.dlsg_sense_line_plan_bytes(B, T, Y) // 4, -7, np.int32)
+    assert lib.dlsg_sense_line_plan_build(ptr(w), ws, B, C, T, Y, X, ptr(plan), None) == 0
+    counts = plan[: B * T]
+    sampled = (wb != 0).any(axis=(1, 4))                    # [B, T, Y]
+    assert np.array_equal(counts.reshape(B, T), sampled.sum(-1))
+    lst = plan[B * T: B * T * (1 + Y)].reshape(B, T, Y)
+    pos = plan[B * T * (1 + Y):].reshape(B, T, Y)
+    for b in range(B):
+        for t in range(T):
+            ky = np.flatnonzero(sampled[b, t])
+            assert np.array_equal(lst[b, t, : len(ky)], ky)
+            assert np.array_equal(pos[b, t, ky], np.arange(len(ky))) and (pos[b, t, ~sampled[b, t]] == -1).all()
+    lmax = max(1, int(counts.max()))
+    assert lib.dlsg_sense_lines_supported(E, Y, X, lmax) == 1
+
+    nbytes = lib.dlsg_sense_lines_workspace_bytes(B, C, T, X, lmax, budget)
+    work = np.zeros(nbytes // 8 + 1, np.complex64)
+    tail = (ptr(work), nbytes, B, E, C, T, Y, X, None)
+    m128, x128, k128, a128 = (a.astype(np.complex128) for a in (maps, x, k, aty))
+    out = np.full((B, C, T, Y, X), np.nan, np.complex64)
+    assert lib.dlsg_sense_forward_lines_c64(ptr(x), ptr(m5), ptr(w), ws, ptr(plan), lmax, ptr(out), *tail) == 0
+    assert rel_l2(out, so.sense_forward(x128, m128, w)) < 1e-5
+    assert not out[np.broadcast_to(~sampled[:, None, :, :, None], out.shape)].any()      # unsampled lines are exact zeros
+    out = np.full((B, E, T, Y, X), np.nan, np.complex64)
+    assert lib.dlsg_sense_adjoint_lines_c64(ptr(k), ptr(m5), ptr(w), ws, ptr(plan), lmax, ptr(out), *tail) == 0
+    assert rel_l2(out, so.sense_adjoint(k128, m128, w)) < 1e-5
+    want = {0: so.sense_normal(x128, m128, w), 1: so.dc_step(x128, a128, m128, w, -2.0),
+            2: so.sense_normal(x128, m128, w) + (-2.0) * x128}
+    for epi in (0, 1, 2):
+        out = np.full((B, E, T, Y, X), np.nan, np.complex64)
+        assert lib.dlsg_sense_normal_lines_c64(ptr(x), ptr(aty), ptr(m5), ptr(w), ws, ptr(plan), lmax, -2.0, None, epi,
+                                               ptr(out), *tail) == 0
+        assert rel_l2(out, want[epi]) < 1e-5, epi
+
+
+def test_sampled_line_status_codes(sense_emu_lib):
+    lib = _lines_lib(sense_emu_lib)
+    assert lib.dlsg_sense_lines_supported(1, 192, 160, 27) == 1
+    assert lib.dlsg_sense_lines_supported(1, 190, 160, 27) == 0       # not 32*R
+    assert lib.dlsg_sense_lines_supported(1, 192, 160, 0) == 0
+    assert lib.dlsg_sense_lines_supported(8, 320, 320, 160) == 0      # accumulators do not fit in shared memory
+    z = np.zeros(64, np.complex64)
+    ws = (ctypes.c_longlong * 5)(0, 0, 0, 32, 1)
+    args = (ptr(z), ptr(z), ptr(z), ws, ptr(z), 4, ptr(z))
+    assert lib.dlsg_sense_forward_lines_c64(*args, ptr(z), 8, 1, 1, 1, 1, 32, 32, None) == -2
+    assert lib.dlsg_sense_forward_lines_c64(*args, ptr(z), 1 << 20, 1, 1, 1, 1, 33, 32, None) == -3
+    assert lib.dlsg_sense_forward_lines_c64(ptr(z), ptr(z), None, ws, ptr(z), 4, ptr(z), ptr(z), 1 << 20, 1, 1, 1, 1, 32, 32, None) == -1
