@@ -369,25 +369,45 @@ def main():
         hm = torch.empty(maps.shape, dtype=maps.dtype, pin_memory=True).copy_(maps)
         hw = torch.empty(mask.shape, dtype=mask.dtype, pin_memory=True).copy_(mask)
         hx = torch.empty((B, E, T, Y, X), dtype=torch.complex64, pin_memory=True)
-        h2d = hy.numel() * 8 + hm.numel() * 8 + hw.numel() * 4
         d2h = hx.numel() * 8
 
-        # The batch goes through the same public API in chunks of 16 slices on two streams, so that the H2D copy of
+        # The batch goes through the same public API in chunks of 16 slices on two streams, so that the H2D traffic of
         # chunk i+1 and the D2H copy of chunk i-1 overlap the reconstruction of chunk i (slices are independent).
-        n_chunk = 4 if B % 4 == 0 and B >= 8 else 1
+        # The zero-filled k-space stays in pinned host memory: A(y, adjoint=True) reads its sampled lines over PCIe
+        # (dlsg_sense_adjoint_lines_gather_c64); maps and mask are copied.  With dense weights it is copied as before.
+        host_y = plan is not None and os.environ.get("DLSG_E2E_HOST_Y", "1") != "0"
+        n_chunk = int(os.environ.get("DLSG_E2E_CHUNKS", 8))
+        if n_chunk < 1 or B % n_chunk:
+            n_chunk = 1
         cb = B // n_chunk
-        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        n_streams = int(os.environ.get("DLSG_E2E_STREAMS", 2))
+        streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+        xfer = torch.cuda.Stream(device=dev, priority=-1)     # transfers + A^H y (PCIe-bound) ahead of the DC steps
+        if host_y:
+            sampled_rows = int(plan[0][: B * T].sum().item())                  # sum of n(b,t)
+            y_bytes = sampled_rows * C * X * 8
+        else:
+            y_bytes = hy.numel() * 8
+        h2d = y_bytes + hm.numel() * 8 + hw.numel() * 4
 
         def e2e_step():
             with torch.no_grad():
                 for i in range(n_chunk):
-                    st = streams[i % 2]
                     sl = slice(i * cb, (i + 1) * cb)
-                    with torch.cuda.stream(st):
-                        dy = hy[sl].to(dev, non_blocking=True)
-                        dm = hm[sl].to(dev, non_blocking=True)
+                    st = streams[i % n_streams]
+                    with torch.cuda.stream(xfer):              # chunk i+1's traffic overlaps chunk i's DC steps
                         dw = hw[sl].to(dev, non_blocking=True)
-                        res = pgd(dy, SenseModel(dm, weights=dw))
+                        dm = hm[sl].to(dev, non_blocking=True)
+                        dy = hy[sl] if host_y else hy[sl].to(dev, non_blocking=True)
+                        A_i = SenseModel(dm, weights=dw)
+                        aty_i = A_i(dy, adjoint=True)
+                        ev = torch.cuda.Event()
+                        ev.record(xfer)
+                    with torch.cuda.stream(st):
+                        st.wait_event(ev)
+                        for tns in (dm, dw, aty_i):
+                            tns.record_stream(st)
+                        res = pgd(None, A_i, ATy=aty_i)
                         hx[sl].copy_(res, non_blocking=True)
                 for st in streams:
                     torch.cuda.current_stream(dev).wait_stream(st)
@@ -402,7 +422,9 @@ def main():
         el = max_over_ranks(time.perf_counter() - t0, dev)
         e2e = {"value": world * B * n_e2e / el, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
-               "pipeline": f"{n_chunk} chunks of {cb} slices on 2 streams (copies overlap compute)"}
+               "pipeline": f"{n_chunk} chunks of {cb} slices: H2D + A^H y on a high-priority transfer stream, DC steps + D2H on {n_streams} streams",
+               "kspace": ("left in pinned host memory, sampled ky lines read in place over PCIe" if host_y
+                          else "dense copy to the device")}
 
     swin = None
     if rank == 0 and not args.skip_swin:

@@ -41,6 +41,7 @@ SIGNATURES = {
     "dlsg_sense_lines_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _sz]),
     "dlsg_sense_forward_lines_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz] + [_i] * 6 + [_vp]),
     "dlsg_sense_adjoint_lines_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz] + [_i] * 6 + [_vp]),
+    "dlsg_sense_adjoint_lines_gather_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz] + [_i] * 6 + [_vp]),
     "dlsg_sense_normal_lines_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _i, _vp, _vp, _sz] + [_i] * 6 + [_vp]),
     "dlsg_fftmod_c64": (_i, [_vp, ctypes.c_longlong, _i, _i, _vp]),
     "dlsg_get_mask_c64": (_i, [_vp, _vp, ctypes.c_longlong, _f, _vp]),

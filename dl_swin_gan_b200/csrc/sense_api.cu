@@ -332,16 +332,16 @@ size_t cols_adj_lines_smem(int E, int Y, int lmax) {     // ColLinesCfg<RY>::sme
 
 template <int RX, int MODE>
 int launch_rows_lines(const float2* src, float2* dst, const float* w, const WeightStrides& ws, float scale,
-                      const LinePlan& lp, const SenseDims& d, stream_t s) {
+                      const LinePlan& lp, const SenseDims& d, stream_t s, int src_lines) {
     using Cfg = RowCfg<RX>;
     const size_t smem = (size_t)Cfg::WARPS * (MODE == MODE_NORMAL ? 2 : 1) * Cfg::BUF * sizeof(float2);
     const unsigned grid = (unsigned)((long long)d.B * d.t_count);
-    return launch(sense_rows_lines_kernel<RX, MODE>, dim3(grid), dim3(32 * Cfg::WARPS), smem, s, src, dst, w, ws, scale, lp, d);
+    return launch(sense_rows_lines_kernel<RX, MODE>, dim3(grid), dim3(32 * Cfg::WARPS), smem, s, src, dst, w, ws, scale, lp, d, src_lines);
 }
 template <int MODE>
 int rows_lines(const float2* src, float2* dst, const float* w, const WeightStrides& ws, float scale,
-               const LinePlan& lp, const SenseDims& d, stream_t s) {
-    DLSG_RADIX_SWITCH(radix_of(d.X), (launch_rows_lines<R, MODE>(src, dst, w, ws, scale, lp, d, s)))
+               const LinePlan& lp, const SenseDims& d, stream_t s, int src_lines = 0) {
+    DLSG_RADIX_SWITCH(radix_of(d.X), (launch_rows_lines<R, MODE>(src, dst, w, ws, scale, lp, d, s, src_lines)))
 }
 
 bool lines_supported(int E, int Y, int X, int lmax) {
@@ -352,7 +352,8 @@ bool lines_supported(int E, int Y, int X, int lmax) {
 
 int run_lines(Op op, const float2* in, const float2* maps, const float* w, const long long* w_strides,
               const int* plan, int lmax, float2* out, const float2* aty, float step, const float* step_dev, int epi,
-              void* workspace, size_t workspace_bytes, int B, int E, int C, int T, int Y, int X, void* stream) {
+              void* workspace, size_t workspace_bytes, int B, int E, int C, int T, int Y, int X, void* stream,
+              bool gather_k = false) {
     if (B <= 0 || E <= 0 || C <= 0 || T <= 0 || Y <= 0 || X <= 0) return DLSG_EINVAL;
     if (!in || !out || !maps || !w || !w_strides || !plan) return DLSG_EINVAL;
     if (epi == EPI_DC && !aty) return DLSG_EINVAL;
@@ -376,7 +377,14 @@ int run_lines(Op op, const float2* in, const float2* maps, const float* w, const
         const float2* maps_b = maps ? maps + b0 * m_slice : nullptr;
         const float* w_b = w + b0 * ws.b;
         if (op == OP_ADJ) {
-            DLSG_TRY((rows_lines<MODE_ADJ>(in + b0 * k_slice, tl, w_b, ws, scale, lp, d, s)));
+            if (gather_k) {      // k may be mapped host memory: copy its sampled lines, then transform them in place
+                const long long units = (long long)bc * T * C;
+                DLSG_TRY(launch(sense_gather_lines_kernel, dim3((unsigned)(units < kGatherCtas ? units : kGatherCtas)), dim3(256), 0, s,
+                                in + b0 * k_slice, tl, lp, d));
+                DLSG_TRY((rows_lines<MODE_ADJ>(tl, tl, w_b, ws, scale, lp, d, s, 1)));
+            } else {
+                DLSG_TRY((rows_lines<MODE_ADJ>(in + b0 * k_slice, tl, w_b, ws, scale, lp, d, s)));
+            }
             DLSG_TRY(cols_adj_lines(tl, maps_b, out + b0 * x_slice, nullptr, nullptr, 0.f, nullptr, EPI_PLAIN, lp, d, s));
             continue;
         }
@@ -507,6 +515,14 @@ int dlsg_sense_adjoint_lines_c64(const void* k, const void* maps, const float* w
                                  int B, int E, int C, int T, int Y, int X, void* stream) {
     return dlsg::run_lines(dlsg::OP_ADJ, (const float2*)k, (const float2*)maps, weights, w_strides, (const int*)plan, lmax,
                            (float2*)x_out, nullptr, 0.f, nullptr, dlsg::EPI_PLAIN, workspace, workspace_bytes, B, E, C, T, Y, X, stream);
+}
+
+int dlsg_sense_adjoint_lines_gather_c64(const void* k, const void* maps, const float* weights, const long long* w_strides,
+                                        const void* plan, int lmax, void* x_out, void* workspace, size_t workspace_bytes,
+                                        int B, int E, int C, int T, int Y, int X, void* stream) {
+    return dlsg::run_lines(dlsg::OP_ADJ, (const float2*)k, (const float2*)maps, weights, w_strides, (const int*)plan, lmax,
+                           (float2*)x_out, nullptr, 0.f, nullptr, dlsg::EPI_PLAIN, workspace, workspace_bytes, B, E, C, T, Y, X, stream,
+                           true);
 }
 
 int dlsg_sense_normal_lines_c64(const void* x, const void* aty, const void* maps, const float* weights,

@@ -332,13 +332,13 @@ DLSG_UNROLL(DLSG_LINES_ITEM_UNROLL)
 
 // ---------------------------------------------------------------------------- row pass on the sampled lines
 //   MODE_FWD   : k[b,c,t,ky_i,:] = W*scale * DFT_X(tl[b,c,t,i,:])
-//   MODE_ADJ   : tl[b,c,t,i,:]   = IDFT_X(W*scale * k[b,c,t,ky_i,:])
+//   MODE_ADJ   : tl[b,c,t,i,:]   = IDFT_X(W*scale * k[b,c,t,ky_i,:])      (src_lines: k already gathered to the tl layout, in place)
 //   MODE_NORMAL: tl              = IDFT_X((W*scale)^2 * DFT_X(tl))            in place
 // CTA (4 warps) = (b, t); the flattened (coil, line) items are walked in warp batches of NB = 32/RX rows.
 template <int RX, int MODE>
 DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(128, 3)
 sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict__ w, WeightStrides ws, float scale,
-                        LinePlan lp, SenseDims d) {
+                        LinePlan lp, SenseDims d, int src_lines) {
     using Cfg = RowCfg<RX>;
     constexpr int NB = Cfg::NB;
     constexpr int DIR = (MODE == MODE_ADJ) ? +1 : -1;
@@ -364,7 +364,7 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
             if (r < nrows) {
                 const int item = it0 + r, c = item / n, i = item - c * n;
                 const int ky = __ldg(list + i);
-                const float2* s = src + ((MODE == MODE_ADJ) ? idx_k(d, b, c, t, ky) : idx_lines(d, lp.lmax, b, c, t, i)) + lane;
+                const float2* s = src + ((MODE == MODE_ADJ && !src_lines) ? idx_k(d, b, c, t, ky) : idx_lines(d, lp.lmax, b, c, t, i)) + lane;
                 float2 v[RX];
 #pragma unroll
                 for (int j = 0; j < RX; ++j) {
@@ -417,6 +417,44 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
             }
         }
         __syncwarp();
+    }
+}
+
+// kl[b,c,t,i,:] = k[b,c,t,ky_i,:]: copies the sampled lines of a k-space that may live in pinned (mapped) host memory,
+// so that only those lines cross PCIe.  A few persistent CTAs walk the (c, t, b) images (the copy is PCIe-bound: a
+// small grid keeps enough 16-byte loads in flight and leaves the SMs to the kernels of other streams).
+constexpr int kGatherCtas = 48;
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(256)
+sense_gather_lines_kernel(const float2* __restrict__ k, float2* __restrict__ kl, LinePlan lp, SenseDims d) {
+    const long long units = (long long)d.B * d.t_count * d.C;
+    for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        long long u = unit;
+        const int c = (int)(u % d.C); u /= d.C;
+        const int tl = (int)(u % d.t_count);
+        const int b = (int)(u / d.t_count);
+        const int t = d.t_begin + tl;
+        const int bt = b * d.T + t;
+        const int n = __ldg(lp.counts + bt);
+        const int* list = lp.list + (size_t)bt * d.Y;
+        const float4* src = reinterpret_cast<const float4*>(k + idx_k(d, b, c, t, 0));
+        float4* dst = reinterpret_cast<float4*>(kl + idx_lines(d, lp.lmax, b, c, t, 0));
+        const int per_row = d.X / 2, total = n * per_row;
+        for (int q0 = threadIdx.x; q0 < total; q0 += 4 * blockDim.x) {
+            float4 v[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int q = q0 + m * blockDim.x;
+                if (q < total) {
+                    const int i = q / per_row, ch = q - i * per_row;
+                    v[m] = __ldg(src + (size_t)__ldg(list + i) * per_row + ch);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int q = q0 + m * blockDim.x;
+                if (q < total) dst[q] = v[m];
+            }
+        }
     }
 }
 

@@ -12,7 +12,9 @@ Sampled lines: when the weights are a k-t sampling mask (whole ky lines of W are
 `get_mask` of undersampled data gives, dl_cs/mri/utils.py:69-79) the operator runs the Y transform first and
 keeps only the lines that carry weight (csrc/sense_lines.cuh); same results, a fraction of the HBM traffic.
 The plan is built on first use (one pass over W and one scalar read-back) and cached with the weights.
-`DLSG_SAMPLED_LINES=0` forces the dense kernels.
+`DLSG_SAMPLED_LINES=0` forces the dense kernels.  On that path `A(y, adjoint=True)` also accepts a k-space that was
+left in *pinned host memory*: the kernels read its sampled lines straight over PCIe, so the zero-filled k-space
+(the bulk of a reconstruction's input, scripts/reconstruct.py:132-171) never needs a dense device copy.
 
 Beyond the reference interface the operator offers two fused entries the solvers may use
 when present (they fall back to two calls otherwise):
@@ -59,7 +61,7 @@ def _launch_lines(kind: str, data, maps5, wexp, dims, lines, aty=None, step=None
     """Same contract as _launch, through the sampled-line entry points; lines = (plan int32 tensor, lmax)."""
     lib = _lib.load()
     B, E, C, T, Y, X = dims
-    dev = data.device
+    dev = maps5.device                      # `data` may be pinned host memory for kind == "adj_host"
     plan, lmax = lines
     out = torch.empty((B, C, T, Y, X) if kind == "fwd" else (B, E, T, Y, X), dtype=torch.complex64, device=dev)
     wstr = (ctypes.c_longlong * 5)(*wexp.stride())
@@ -73,6 +75,8 @@ def _launch_lines(kind: str, data, maps5, wexp, dims, lines, aty=None, step=None
             st = lib.dlsg_sense_forward_lines_c64(data.data_ptr(), *head, out.data_ptr(), *tail)
         elif kind == "adj":
             st = lib.dlsg_sense_adjoint_lines_c64(data.data_ptr(), *head, out.data_ptr(), *tail)
+        elif kind == "adj_host":
+            st = lib.dlsg_sense_adjoint_lines_gather_c64(data.data_ptr(), *head, out.data_ptr(), *tail)
         else:
             epi = {"normal": 0, "dc": 1, "reg": 2}[kind]
             if isinstance(step, torch.Tensor):
@@ -337,7 +341,24 @@ class SenseModel(nn.Module):
         raise NotImplementedError(
             f"maps with a non-singleton 4th axis imply a {nd}-D FFT (transforms.py:76); the B200 kernels cover 1-D/2-D")
 
+    def _run_adjoint_from_host(self, data: torch.Tensor) -> torch.Tensor:
+        """A^H y for a zero-filled k-space left in pinned host memory: the kernels read its sampled lines over PCIe."""
+        if data.dtype != torch.complex64:
+            raise TypeError(f"SENSE input must be complex64 (got {data.dtype}); the B200 kernels compute in fp32")
+        dims = self._dims(data, "adj")
+        maps5 = self._prepared_maps()
+        wexp = self._prepared_weights(dims, maps5.device)
+        ndims = self._kernel_ndims(dims)
+        lines = self._line_plan(dims, wexp, ndims) if data.numel() else None
+        if lines is None:
+            raise RuntimeError(
+                "host-resident k-space is only read in place by the sampled-line kernels (weights with empty ky lines, "
+                "2-D, 32*R axes); move the k-space to the device for this operator")
+        return _launch_lines("adj_host", data.detach().contiguous(), maps5, wexp, dims, lines)
+
     def _run(self, kind: str, data: torch.Tensor, aty=None, step=None) -> torch.Tensor:
+        if kind == "adj" and not data.is_cuda and data.is_pinned():
+            return self._run_adjoint_from_host(data)
         _require_cuda_c64(data, "SENSE input")
         dims = self._dims(data, kind)
         maps5 = self._prepared_maps()

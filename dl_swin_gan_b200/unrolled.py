@@ -29,8 +29,11 @@ class ProximalGradientDescent(nn.Module):
         self.step_size = nn.Parameter(torch.tensor([step_init], dtype=torch.float32),
                                       requires_grad=(not fix_step_size))
 
-    def forward(self, y, A, x0=None):
-        ATy = A(y, adjoint=True)                       # unrolledswin.py:96
+    def forward(self, y, A, x0=None, ATy=None):
+        """Reference signature `forward(y, A, x0)`; `ATy` (extension) takes A^H y when the caller already has it,
+        e.g. computed on a transfer stream while the previous batch is reconstructed."""
+        if ATy is None:
+            ATy = A(y, adjoint=True)                   # unrolledswin.py:96
         xi = ATy if x0 is None else x0
         fused = getattr(A, "dc_step", None)
         for i in range(self.num_unrolls):

@@ -134,6 +134,14 @@ int dlsg_sense_adjoint_lines_c64(const void* k, const void* maps, const float* w
                                  const void* plan, int lmax, void* x_out, void* workspace, size_t workspace_bytes,
                                  int B, int E, int C, int T, int Y, int X, void* stream);
 
+/* Same adjoint for a k-space that need not be in device memory: `k` is any address the device can read, in
+ * particular pinned (mapped) host memory, i.e. the zero-filled k-space as the reference's loader leaves it on the
+ * host (scripts/reconstruct.py:132-171).  Its sampled lines are first copied into the workspace (16-byte loads
+ * straight from `k`), so only those lines cross PCIe and the dense k-space never needs a device copy. */
+int dlsg_sense_adjoint_lines_gather_c64(const void* k, const void* maps, const float* weights, const long long* w_strides,
+                                        const void* plan, int lmax, void* x_out, void* workspace, size_t workspace_bytes,
+                                        int B, int E, int C, int T, int Y, int X, void* stream);
+
 /* A^H A x with the epilogues of the dense entry points, selected by `epilogue`:
  *   0  x_out = A^H A x                                   (dlsg_sense_normal_c64)
  *   1  x_out = x + step * (A^H A x - aty)                (dlsg_sense_dc_step_c64, unrolledswin.py:109)

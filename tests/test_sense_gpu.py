@@ -133,6 +133,29 @@ def test_sampled_line_path_is_selected_and_agrees_with_dense(dev, monkeypatch):
     assert A._line_plans[(B, E, C, T, Y, X)] is None                      # more than half of the lines sampled: dense kernels
 
 
+def test_adjoint_reads_pinned_host_kspace_in_place(dev, monkeypatch):
+    """A(y, adjoint=True) with y in pinned host memory == the same with y copied to the device (bit for bit);
+    pageable host memory, dense weights and the dense kernels refuse instead of falling back to a CPU path."""
+    from dl_swin_gan_b200.mri import SenseModel
+    B, E, C, T, Y, X = 2, 1, 4, 5, 192, 160
+    maps, x, mask = so.synthetic_problem(B, E, C, T, Y, X, seed=21)
+    rng = np.random.default_rng(2)
+    k = (rng.standard_normal((B, C, T, Y, X)) + 1j * rng.standard_normal((B, C, T, Y, X))).astype(np.complex64)
+    A = make_model(maps, mask, dev)
+    hk = torch.from_numpy(k).pin_memory()
+    got = A(hk, adjoint=True)
+    assert got.is_cuda
+    assert torch.equal(got, A(hk.to(dev), adjoint=True))
+    assert rel_l2(to_np(got), so.sense_adjoint(k.astype(np.complex128), maps.astype(np.complex128), mask)) < TOL
+    with pytest.raises(RuntimeError):
+        A(torch.from_numpy(k), adjoint=True)                   # pageable memory: no CPU fallback
+    with pytest.raises(RuntimeError):
+        make_model(maps, np.ones_like(mask), dev)(hk, adjoint=True)      # every line sampled: dense kernels need a device copy
+    monkeypatch.setenv("DLSG_SAMPLED_LINES", "0")
+    with pytest.raises(RuntimeError):
+        make_model(maps, mask, dev)(hk, adjoint=True)
+
+
 def test_workspace_chunking_does_not_change_results(dev, monkeypatch):
     B, E, C, T, Y, X = 3, 2, 4, 5, 64, 96
     maps, x, mask = so.synthetic_problem(B, E, C, T, Y, X, seed=3)

@@ -141,6 +141,7 @@ def _lines_lib(sense_emu_lib):
     tail = [vp, sz] + [i] * 6 + [vp]
     lib.dlsg_sense_forward_lines_c64.argtypes = [vp, vp, vp, vp, vp, i, vp] + tail
     lib.dlsg_sense_adjoint_lines_c64.argtypes = [vp, vp, vp, vp, vp, i, vp] + tail
+    lib.dlsg_sense_adjoint_lines_gather_c64.argtypes = [vp, vp, vp, vp, vp, i, vp] + tail
     lib.dlsg_sense_normal_lines_c64.argtypes = [vp, vp, vp, vp, vp, vp, i, ctypes.c_float, vp, i, vp] + tail
     return lib
 
@@ -206,6 +207,9 @@ def test_emulated_sampled_line_path_matches_oracle(sense_emu_lib, B, E, C, T, Y,
     out = np.full((B, E, T, Y, X), np.nan, np.complex64)
     assert lib.dlsg_sense_adjoint_lines_c64(ptr(k), ptr(m5), ptr(w), ws, ptr(plan), lmax, ptr(out), *tail) == 0
     assert rel_l2(out, so.sense_adjoint(k128, m128, w)) < 1e-5
+    out2 = np.full((B, E, T, Y, X), np.nan, np.complex64)        # same through the line gather (host-resident k-space entry)
+    assert lib.dlsg_sense_adjoint_lines_gather_c64(ptr(k), ptr(m5), ptr(w), ws, ptr(plan), lmax, ptr(out2), *tail) == 0
+    assert np.array_equal(out, out2)
     want = {0: so.sense_normal(x128, m128, w), 1: so.dc_step(x128, a128, m128, w, -2.0),
             2: so.sense_normal(x128, m128, w) + (-2.0) * x128}
     for epi in (0, 1, 2):
