@@ -14,6 +14,7 @@ constexpr int kMaxDirectX = 4096;
 constexpr int kMaxDirectY = 1536;
 constexpr long long kTargetRowCtas = 148LL * 8;    // row pass: about two waves of 4-5 CTAs per SM
 constexpr long long kTargetColCtas = 148LL * 4;
+constexpr long long kTargetLineRowCtas = 148LL * 24;  // sampled-line row pass: ~6 waves of 4 CTAs per SM
 
 inline int radix_of(int n) {   // R if n == 32*R with a compiled radix, else 0
     if (n % 32) return 0;
@@ -335,8 +336,14 @@ int launch_rows_lines(const float2* src, float2* dst, const float* w, const Weig
                       const LinePlan& lp, const SenseDims& d, stream_t s, int src_lines) {
     using Cfg = RowCfg<RX>;
     const size_t smem = (size_t)Cfg::WARPS * (MODE == MODE_NORMAL ? 2 : 1) * Cfg::BUF * sizeof(float2);
-    const unsigned grid = (unsigned)((long long)d.B * d.t_count);
-    return launch(sense_rows_lines_kernel<RX, MODE>, dim3(grid), dim3(32 * Cfg::WARPS), smem, s, src, dst, w, ws, scale, lp, d, src_lines);
+    const long long units = (long long)d.B * d.t_count;
+    const long long batches = ((long long)d.C * lp.lmax + Cfg::NB - 1) / Cfg::NB;          // per (b, t), upper bound
+    long long nsplit = (kTargetLineRowCtas + units - 1) / units;
+    const long long max_split = (batches + Cfg::WARPS - 1) / Cfg::WARPS;                   // at least one batch per warp
+    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit < 1) nsplit = 1;
+    return launch(sense_rows_lines_kernel<RX, MODE>, dim3((unsigned)(units * nsplit)), dim3(32 * Cfg::WARPS), smem, s,
+                  src, dst, w, ws, scale, lp, d, src_lines, (int)nsplit);
 }
 template <int MODE>
 int rows_lines(const float2* src, float2* dst, const float* w, const WeightStrides& ws, float scale,

@@ -334,11 +334,12 @@ DLSG_UNROLL(DLSG_LINES_ITEM_UNROLL)
 //   MODE_FWD   : k[b,c,t,ky_i,:] = W*scale * DFT_X(tl[b,c,t,i,:])
 //   MODE_ADJ   : tl[b,c,t,i,:]   = IDFT_X(W*scale * k[b,c,t,ky_i,:])      (src_lines: k already gathered to the tl layout, in place)
 //   MODE_NORMAL: tl              = IDFT_X((W*scale)^2 * DFT_X(tl))            in place
-// CTA (4 warps) = (b, t); the flattened (coil, line) items are walked in warp batches of NB = 32/RX rows.
+// The flattened (coil, line) items of one (b, t) are walked in warp batches of NB = 32/RX rows by the 4 warps of
+// `nsplit` CTAs (the split keeps small batches, e.g. the chunks of a pipelined reconstruction, at several waves).
 template <int RX, int MODE>
 DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(128, 3)
 sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict__ w, WeightStrides ws, float scale,
-                        LinePlan lp, SenseDims d, int src_lines) {
+                        LinePlan lp, SenseDims d, int src_lines, int nsplit) {
     using Cfg = RowCfg<RX>;
     constexpr int NB = Cfg::NB;
     constexpr int DIR = (MODE == MODE_ADJ) ? +1 : -1;
@@ -347,7 +348,9 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* buf = smem + warp * (NBUF * Cfg::BUF);
     float2* buf2 = buf + (NBUF - 1) * Cfg::BUF;  // way back of the normal operator (aliases buf otherwise, unused)
-    const int tl = (int)(blockIdx.x % d.t_count), b = (int)(blockIdx.x / d.t_count);
+    const int split = (int)(blockIdx.x % nsplit);             // nsplit CTAs share the items of one (b, t)
+    const int unit = (int)(blockIdx.x / nsplit);
+    const int tl = unit % d.t_count, b = unit / d.t_count;
     const int t = d.t_begin + tl;
     const int bt = b * d.T + t;
     const int n = __ldg(lp.counts + bt);
@@ -356,8 +359,10 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
 
     float2 tw[RX];
     lane_twiddles<RX, DIR>(lane, tw);
+    const float* wbt = w + (b * ws.b + t * ws.t + lane * ws.x);      // weights of this lane's first column of (b, t)
+    auto wrow = [&](int c, int ky) { return wbt + (c * ws.c + ky * ws.y); };
 
-    for (int it0 = warp * NB; it0 < items; it0 += Cfg::WARPS * NB) {
+    for (int it0 = (split * Cfg::WARPS + warp) * NB; it0 < items; it0 += nsplit * Cfg::WARPS * NB) {
         const int nrows = min(NB, items - it0);
 #pragma unroll
         for (int r = 0; r < NB; ++r) {
@@ -369,7 +374,7 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
 #pragma unroll
                 for (int j = 0; j < RX; ++j) {
                     v[j] = s[32 * j];
-                    if (MODE == MODE_ADJ) v[j] = cscale(v[j], scale * load_w(w, ws, b, c, t, ky, lane + 32 * j));
+                    if (MODE == MODE_ADJ) v[j] = cscale(v[j], scale * __ldg(wrow(c, ky) + 32 * j * ws.x));
                 }
                 Dft<RX, DIR>::run(v);
                 float2* o = buf + (r * RX) * Cfg::S1 + lane;
@@ -388,7 +393,7 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
                     float2 v[RX];
 #pragma unroll
                     for (int j = 0; j < RX; ++j) {
-                        const float wv = scale * load_w(w, ws, b, c, t, ky, lane + 32 * j);
+                        const float wv = scale * __ldg(wrow(c, ky) + 32 * j * ws.x);
                         v[j] = cscale(buf[r * Cfg::S2 + lane + 32 * j], wv * wv);
                     }
                     Dft<RX, +1>::run(v);
@@ -411,7 +416,7 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
 #pragma unroll
                 for (int j = 0; j < RX; ++j) {
                     float2 q = sv[32 * j];
-                    if (MODE == MODE_FWD) q = cscale(q, scale * load_w(w, ws, b, c, t, ky, lane + 32 * j));
+                    if (MODE == MODE_FWD) q = cscale(q, scale * __ldg(wrow(c, ky) + 32 * j * ws.x));
                     o[32 * j] = q;
                 }
             }

@@ -12,7 +12,7 @@ Sampled lines: when the weights are a k-t sampling mask (whole ky lines of W are
 `get_mask` of undersampled data gives, dl_cs/mri/utils.py:69-79) the operator runs the Y transform first and
 keeps only the lines that carry weight (csrc/sense_lines.cuh); same results, a fraction of the HBM traffic.
 The plan is built on first use (one pass over W and one scalar read-back) and cached with the weights.
-`DLSG_SAMPLED_LINES=0` forces the dense kernels.  On that path `A(y, adjoint=True)` also accepts a k-space that was
+`DLSG_SAMPLED_LINES=0` forces the dense kernels (`=force` also takes the path for E > 1, where it is the slower one).  On that path `A(y, adjoint=True)` also accepts a k-space that was
 left in *pinned host memory*: the kernels read its sampled lines straight over PCIe, so the zero-filled k-space
 (the bulk of a reconstruction's input, scripts/reconstruct.py:132-171) never needs a dense device copy.
 
@@ -293,9 +293,15 @@ class SenseModel(nn.Module):
             raise ValueError(f"weights must broadcast to [batch, coils, t, y, x]; got {tuple(w32.shape)}")
         return w32.expand(B, C, T, Y, X)   # raises like torch broadcasting does when incompatible
 
-    def _line_plan(self, dims, wexp, ndims):
-        """-> (plan, lmax) when the weights leave at most half of the ky lines sampled, else None (dense kernels)."""
+    def _line_plan(self, dims, wexp, ndims, any_emaps=False):
+        """-> (plan, lmax) when the weights leave at most half of the ky lines sampled, else None (dense kernels).
+
+        With more than one ESPIRiT map set the sampled-line column kernels read the extra sets through the cache and
+        measure slower than the dense kernels (tools/compare_paths.py), so E > 1 stays dense unless `any_emaps`
+        (the host-resident k-space adjoint, which only exists on this path)."""
         if wexp is None or ndims != 2 or not isinstance(self.weights, torch.Tensor) or not _sampled_lines_enabled():
+            return None
+        if dims[1] != 1 and not any_emaps and os.environ.get("DLSG_SAMPLED_LINES") != "force":
             return None
         key = tuple(dims)
         if key not in self._line_plans:
@@ -349,7 +355,7 @@ class SenseModel(nn.Module):
         maps5 = self._prepared_maps()
         wexp = self._prepared_weights(dims, maps5.device)
         ndims = self._kernel_ndims(dims)
-        lines = self._line_plan(dims, wexp, ndims) if data.numel() else None
+        lines = self._line_plan(dims, wexp, ndims, any_emaps=True) if data.numel() else None
         if lines is None:
             raise RuntimeError(
                 "host-resident k-space is only read in place by the sampled-line kernels (weights with empty ky lines, "

@@ -38,7 +38,7 @@ def to_np(t):
 @pytest.fixture(params=["sampled-lines", "dense"])
 def kernel_path(request, monkeypatch):
     """Masks with empty ky lines take the sampled-line kernels by default; every parity case also runs on the dense kernels."""
-    monkeypatch.setenv("DLSG_SAMPLED_LINES", "1" if request.param == "sampled-lines" else "0")
+    monkeypatch.setenv("DLSG_SAMPLED_LINES", "force" if request.param == "sampled-lines" else "0")   # force: also for E > 1
     return request.param
 
 
@@ -147,6 +147,9 @@ def test_adjoint_reads_pinned_host_kspace_in_place(dev, monkeypatch):
     assert got.is_cuda
     assert torch.equal(got, A(hk.to(dev), adjoint=True))
     assert rel_l2(to_np(got), so.sense_adjoint(k.astype(np.complex128), maps.astype(np.complex128), mask)) < TOL
+    maps2, _, _ = so.synthetic_problem(B, 2, C, T, Y, X, seed=22)                  # two map sets through the same entry
+    got2 = make_model(maps2, mask, dev)(hk, adjoint=True)
+    assert rel_l2(to_np(got2), so.sense_adjoint(k.astype(np.complex128), maps2.astype(np.complex128), mask)) < TOL
     with pytest.raises(RuntimeError):
         A(torch.from_numpy(k), adjoint=True)                   # pageable memory: no CPU fallback
     with pytest.raises(RuntimeError):
