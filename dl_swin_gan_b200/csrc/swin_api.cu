@@ -2,6 +2,7 @@
 #include "../../include/dlsg_b200.h"
 #include "swin_kernels.cuh"
 #include "swin_linear_tc.cuh"
+#include "swin_mlp_tc.cuh"
 
 namespace dlsg {
 
@@ -200,6 +201,37 @@ int dlsg_swin_proj_scatter_f32(const float* attn_out, const float* weight, const
     (void)attn_out; (void)weight; (void)bias; (void)y; (void)B; (void)D; (void)H; (void)W; (void)C;
     (void)window; (void)shift; (void)stream;
     return DLSG_EUNSUPPORTED;
+#endif
+}
+
+int dlsg_swin_mlp_f32(const float* x, const float* gamma, const float* beta, float eps,
+                      const void* w1_f16, const float* b1, const void* w2_f16, const float* b2,
+                      void* hidden_f16, float* y, long long M, int C, int H, int residual, void* stream) {
+#if defined(__CUDACC__)
+    if (M <= 0 || C <= 0 || H <= 0) return DLSG_EINVAL;
+    if (!x || !gamma || !beta || !w1_f16 || !w2_f16 || !hidden_f16 || !y) return DLSG_EINVAL;
+    if (M > 0x7fffffffLL || C % 32 != 0 || C > 256 || H % C != 0) return DLSG_EUNSUPPORTED;
+    const size_t smem = dlsg::mlp_smem_bytes(C, H);
+    if (smem > 113 * 1024) return DLSG_EUNSUPPORTED;         // two CTAs per SM share the 512 TMEM columns
+    dlsg::MlpParams p{};
+    p.x = x; p.gamma = gamma; p.beta = beta; p.eps = eps;
+    p.w1h = static_cast<const half_t*>(w1_f16); p.b1 = b1;
+    p.w2h = static_cast<const half_t*>(w2_f16); p.b2 = b2;
+    p.hidden = static_cast<half_t*>(hidden_f16); p.y = y;
+    p.M = (int)M; p.C = C; p.H = H; p.residual = residual ? 1 : 0;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < C) p.tmem_cols *= 2;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = (p.M + dlsg::kLinTileM - 1) / dlsg::kLinTileM;
+    const unsigned grid = (unsigned)(ntiles < 2 * sms ? ntiles : 2 * sms);
+    if (dlsg::launch(dlsg::swin_mlp_kernel<1>, dim3(grid), dim3(dlsg::kLinThreads), smem, (dlsg::stream_t)stream, p) != 0) return DLSG_ELAUNCH;
+    if (dlsg::launch(dlsg::swin_mlp_kernel<2>, dim3(grid), dim3(dlsg::kLinThreads), smem, (dlsg::stream_t)stream, p) != 0) return DLSG_ELAUNCH;
+    return DLSG_OK;
+#else
+    (void)x; (void)gamma; (void)beta; (void)eps; (void)w1_f16; (void)b1; (void)w2_f16; (void)b2; (void)hidden_f16; (void)y;
+    (void)M; (void)C; (void)H; (void)residual; (void)stream;
+    return DLSG_EUNSUPPORTED;      // tcgen05 / TMEM have no host emulation
 #endif
 }
 

@@ -413,7 +413,53 @@ class SwinTransformerBlock3D(nn.Module):
             _lib.check(st, "dlsg_swin_proj_scatter")
         return y
 
+    def _inference(self, x) -> bool:
+        return not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())))
+
+    def _mlp_f16_weights(self):
+        """fc1 / fc2 weights as fp16, converted once and refreshed when the parameters change (constants at inference)."""
+        w1, w2 = self.mlp.fc1.weight, self.mlp.fc2.weight
+        key = (w1.data_ptr(), w1._version, w2.data_ptr(), w2._version, w1.device)
+        cache = getattr(self, "_mlp_f16", None)
+        if cache is None or cache[0] != key:
+            cache = (key, w1.detach().to(torch.float16).contiguous(), w2.detach().to(torch.float16).contiguous())
+            self._mlp_f16 = cache
+        return cache[1], cache[2]
+
+    def _part2_tensor_core(self, x, residual: bool):
+        """[x +] fc2(GELU(fc1(norm2(x)))) in two tcgen05 GEMM launches (inference).  None when outside what the kernels cover."""
+        mlp = self.mlp
+        C, Hd = mlp.fc1.in_features, mlp.fc1.out_features
+        ok = (self.attn.tc_linear and isinstance(self.norm2, nn.LayerNorm) and isinstance(mlp.act, nn.GELU)
+              and getattr(mlp.act, "approximate", "none") == "none"
+              and (mlp.drop.p == 0 or not self.training)
+              and (isinstance(self.drop_path, nn.Identity) or not self.training))
+        if not (ok and x.shape[-1] == C and mlp.fc2.in_features == Hd and mlp.fc2.out_features == C
+                and C % 32 == 0 and C <= 256 and Hd % C == 0 and self.norm2.weight is not None
+                and max(256 * C, 33792) + 2 * C * C + 4 * Hd + 2200 <= 113 * 1024):
+            return None
+        _require_cuda_f32(x, "SwinTransformerBlock3D input")
+        x = x.contiguous()
+        lib = _lib.load()
+        M = x.numel() // C
+        w1h, w2h = self._mlp_f16_weights()
+        hidden = torch.empty((M, Hd), dtype=torch.float16, device=x.device)
+        y = torch.empty_like(x)
+        if M == 0:
+            return y
+        opt = lambda t: t.detach().contiguous().data_ptr() if t is not None else None
+        with torch.cuda.device(x.device):
+            st = lib.dlsg_swin_mlp_f32(x.data_ptr(), opt(self.norm2.weight), opt(self.norm2.bias), float(self.norm2.eps),
+                                       w1h.data_ptr(), opt(mlp.fc1.bias), w2h.data_ptr(), opt(mlp.fc2.bias),
+                                       hidden.data_ptr(), y.data_ptr(), M, C, Hd, 1 if residual else 0, _stream())
+        _lib.check(st, "dlsg_swin_mlp")
+        return y
+
     def forward_part2(self, x):
+        if self._inference(x):
+            y = self._part2_tensor_core(x, residual=False)
+            if y is not None:
+                return y
         return self.drop_path(self.mlp(self.norm2(x)))
 
     def forward(self, x, mask_matrix):
@@ -423,6 +469,10 @@ class SwinTransformerBlock3D(nn.Module):
         else:
             x = self.forward_part1(x, mask_matrix)
         x = shortcut + self.drop_path(x)
+        if self._inference(x) and not self.use_checkpoint:
+            y = self._part2_tensor_core(x, residual=True)          # the residual add rides in the fc2 epilogue
+            if y is not None:
+                return y
         if self.use_checkpoint:
             x = x + checkpoint.checkpoint(self.forward_part2, x, use_reentrant=False)
         else:

@@ -206,6 +206,15 @@ int dlsg_swin_qkv_fused_f32(const float* x, const float* gamma, const float* bet
 int dlsg_swin_proj_scatter_f32(const float* attn_out, const float* weight, const float* bias, float* y,
                                int B, int D, int H, int W, int C, const int* window, const int* shift, void* stream);
 
+/* forward_part2 of the Swin block (:251-252; Mlp :20-38, norm2 :208) as two tcgen05 GEMM kernels:
+ *     y = [x +] fc2( GELU( fc1( LayerNorm(x) ) ) )        (residual != 0 gives the block's `x + forward_part2(x)`, :271)
+ * x, y [M, C] fp32 (tokens of [B,D,H,W,C]); gamma / beta [C]; w1_f16 [H, C] and w2_f16 [C, H] are the fc1 / fc2 weights
+ * converted to fp16 once by the caller (constants at inference), b1 [H], b2 [C] fp32 or NULL; hidden_f16 is a caller-owned
+ * [M, H] fp16 workspace.  GELU is the exact erf form (nn.GELU default).  C % 32 == 0, C <= 256, H % C == 0. */
+int dlsg_swin_mlp_f32(const float* x, const float* gamma, const float* beta, float eps,
+                      const void* w1_f16, const float* b1, const void* w2_f16, const float* b2,
+                      void* hidden_f16, float* y, long long M, int C, int H, int residual, void* stream);
+
 /* Linear layer on the tcgen05 tensor cores (qkv :146 and proj :168 of WindowAttention3D):
  *     y[M, N] = x[M, K] @ weight[N, K]^T + bias[N]       (torch.nn.functional.linear semantics)
  * fp32 in/out, fp16 operands, fp32 accumulation in tensor memory.  K % 16 == 0, N % 32 == 0, N <= 512,

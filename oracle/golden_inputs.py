@@ -67,4 +67,15 @@ def swin_case(name):
         "attn.proj.bias": (0.1 * rng.standard_normal(dim)).astype(f32),
     }
     x = rng.standard_normal((B, D, H, W, dim)).astype(f32)
+    # second half of the block (norm2 + Mlp, :208, :20-38): a separate stream so that the arrays above keep their values
+    rng2 = np.random.default_rng(3000 + sum(ord(ch) for ch in name))
+    hidden = 4 * dim
+    params.update({
+        "norm2.weight": (1 + 0.1 * rng2.standard_normal(dim)).astype(f32),
+        "norm2.bias": (0.1 * rng2.standard_normal(dim)).astype(f32),
+        "mlp.fc1.weight": (rng2.standard_normal((hidden, dim)) / np.sqrt(dim)).astype(f32),
+        "mlp.fc1.bias": (0.1 * rng2.standard_normal(hidden)).astype(f32),
+        "mlp.fc2.weight": (rng2.standard_normal((dim, hidden)) / np.sqrt(hidden)).astype(f32),
+        "mlp.fc2.bias": (0.1 * rng2.standard_normal(dim)).astype(f32),
+    })
     return dict(x=x, params=params, dim=dim, heads=heads, window=window, shift=shift)

@@ -71,10 +71,12 @@ def main():
             xw = ref.window_partition(xp, ws)
             attn_nomask = blk.attn(xw, mask=None)
             attn_mask = blk.attn(xw, mask=mask)
+            block = blk(x, mask)                 # whole block: x + part1, then + forward_part2 (:254-273)
         out = {"part1": part1.numpy(), "attn_nomask": attn_nomask.numpy(), "attn_mask": attn_mask.numpy(),
                "mask": mask.numpy().astype(np.float32), "ws": np.array(ws), "ss": np.array(ss),
                "relative_position_index": blk.attn.relative_position_index.numpy()}
         np.savez_compressed(os.path.join(OUT, f"swin_{name}.npz"), **out)
+        np.savez_compressed(os.path.join(OUT, f"swin_block_{name}.npz"), block=block.numpy())
         print(name, tuple(x.shape), "ws", ws, "ss", ss, "nW", mask.shape[0])
 
 

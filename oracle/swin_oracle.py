@@ -7,6 +7,7 @@ attention path, file /root/reference/dl_cs/models/video_swin_transformer_mri_dow
   WindowAttention3D.forward                :139-170   softmax(q*scale @ k^T + bias (+ mask)) @ v, proj
   SwinTransformerBlock3D.forward_part1     :215-249   LN -> pad -> roll -> partition -> attn -> reverse -> roll -> crop
   compute_mask                             :342-355   region ids -> {0, -100} mask per window
+  Mlp / forward_part2 / block forward      :20-38 / :251-252 / :254-273   x + part1, then + fc2(GELU(fc1(LN(x))))
 
 Third-party arithmetic delegated by the reference and absent from /root/reference: torch matmul / softmax /
 LayerNorm (eps 1e-5, biased variance) and timm's DropPath (identity in eval) — restated here from their
@@ -139,3 +140,22 @@ def block_part1(x, p, num_heads, window_size, shift_size, mask_matrix=None):
     if shifted:
         x = np.roll(x, shift=(ss[0], ss[1], ss[2]), axis=(1, 2, 3))
     return x[:, :D, :H, :W, :]
+
+
+def gelu(x):
+    """nn.GELU default (exact): 0.5 x (1 + erf(x / sqrt 2))."""
+    from math import erf
+    return 0.5 * x * (1.0 + np.vectorize(erf)(x / np.sqrt(2.0)))
+
+
+def block_part2(x, p):
+    """SwinTransformerBlock3D.forward_part2 (:251-252): Mlp(norm2(x)), Mlp = fc2(GELU(fc1(.))) (:20-38); dropouts are p = 0."""
+    h = layer_norm(x, p["norm2.weight"], p["norm2.bias"])
+    h = gelu(h @ p["mlp.fc1.weight"].T + p["mlp.fc1.bias"])
+    return h @ p["mlp.fc2.weight"].T + p["mlp.fc2.bias"]
+
+
+def block_forward(x, p, num_heads, window_size, shift_size, mask_matrix=None):
+    """SwinTransformerBlock3D.forward (:254-273) in eval mode (DropPath is the identity)."""
+    x = x + block_part1(x, p, num_heads, window_size, shift_size, mask_matrix)
+    return x + block_part2(x, p)

@@ -120,6 +120,9 @@ def test_swin_oracle_matches_reference_outputs(name):
     ap = {k[5:]: v for k, v in p.items() if k.startswith("attn.")}
     assert rel_l2(sw.window_attention(xw, ap, c["heads"], c["window"], None), ref["attn_nomask"]) < 5e-6
     assert rel_l2(sw.window_attention(xw, ap, c["heads"], c["window"], mask), ref["attn_mask"]) < 5e-6
+    # whole block (x + part1, then + fc2(GELU(fc1(norm2)))) against the reference block's output
+    blk = np.load(os.path.join(GOLDEN, f"swin_block_{name}.npz"))["block"]
+    assert rel_l2(sw.block_forward(x, p, c["heads"], c["window"], c["shift"], mask), blk) < 5e-6
 
 
 def test_swin_host_helpers_match_oracle():

@@ -58,6 +58,13 @@ def test_block_part1_and_attention_match_reference(dev, name):
     # differentiable route gives the same forward
     xg = x.clone().requires_grad_()
     assert rel_l2(blk.forward_part1(xg, mask).detach().cpu().numpy(), ref["part1"]) < TOL
+    # whole block and its MLP half (tcgen05 fc1 / fc2 kernels when dim % 32 == 0, i.e. the cine configuration)
+    ref_block = np.load(os.path.join(GOLDEN, f"swin_block_{name}.npz"))["block"]
+    p64 = {k: v.astype(np.float64) for k, v in c["params"].items()}
+    with torch.no_grad():
+        assert rel_l2(blk(x, mask).cpu().numpy(), ref_block) < TOL
+        assert rel_l2(blk.forward_part2(x).cpu().numpy(), sw.block_part2(c["x"].astype(np.float64), p64)) < TOL
+    assert rel_l2(blk(xg, mask).detach().cpu().numpy(), ref_block) < TOL          # differentiable route
 
 
 def test_fused_partition_and_reverse_are_exact(dev):
@@ -165,3 +172,25 @@ def test_error_behaviour(dev):
     big = wa.WindowAttention3D(128, (2, 4, 4), 2).to(dev)          # head_dim 64 > 32
     with pytest.raises(ValueError):
         big(torch.randn(2, 32, 128, device=dev))
+
+
+def test_mlp_kernels_at_cine_size_and_ragged_tiles(dev):
+    """forward_part2 on the tensor-core kernels vs fp32 torch: one cine slice of tokens, a token count that is not a
+    multiple of the 128-row tile, residual on/off, and the weight cache following a parameter update."""
+    from dl_swin_gan_b200.swin import window_attention as wa
+    torch.manual_seed(3)
+    blk = wa.SwinTransformerBlock3D(160, 8, (7, 8, 8), (0, 0, 0), qkv_bias=True).to(dev).eval()
+    with torch.no_grad():
+        blk.norm2.weight.normal_(1, 0.1); blk.norm2.bias.normal_(0, 0.1)
+        for shape in [(1, 7, 48, 40, 160), (1, 3, 5, 7, 160), (2, 1, 1, 1, 160)]:
+            x = torch.randn(*shape, device=dev)
+            want = blk.mlp(blk.norm2(x))
+            got = blk._part2_tensor_core(x, residual=False)
+            assert got is not None
+            assert rel_l2(got.cpu().numpy(), want.cpu().numpy()) < TOL
+            assert float((got - want).abs().max() / want.abs().max()) < 5e-3
+            got_r = blk._part2_tensor_core(x, residual=True)
+            assert rel_l2(got_r.cpu().numpy(), (x + want).cpu().numpy()) < TOL
+        blk.mlp.fc1.weight.mul_(0.5)                       # in-place update bumps the version: the fp16 copies are refreshed
+        x = torch.randn(1, 2, 8, 8, 160, device=dev)
+        assert rel_l2(blk.forward_part2(x).cpu().numpy(), blk.mlp(blk.norm2(x)).cpu().numpy()) < TOL
