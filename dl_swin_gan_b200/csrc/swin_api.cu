@@ -212,7 +212,7 @@ int dlsg_swin_mlp_f32(const float* x, const float* gamma, const float* beta, flo
     if (!x || !gamma || !beta || !w1_f16 || !w2_f16 || !hidden_f16 || !y) return DLSG_EINVAL;
     if (M > 0x7fffffffLL || C % 32 != 0 || C > 256 || H % C != 0) return DLSG_EUNSUPPORTED;
     const size_t smem = dlsg::mlp_smem_bytes(C, H);
-    if (smem > 113 * 1024) return DLSG_EUNSUPPORTED;         // two CTAs per SM share the 512 TMEM columns
+    if (smem > 113 * 1024 || dlsg::mlp_fc2_smem_bytes(C) > 227 * 1024) return DLSG_EUNSUPPORTED;   // fc1: two CTAs per SM; fc2: one
     dlsg::MlpParams p{};
     p.x = x; p.gamma = gamma; p.beta = beta; p.eps = eps;
     p.w1h = static_cast<const half_t*>(w1_f16); p.b1 = b1;
@@ -225,8 +225,10 @@ int dlsg_swin_mlp_f32(const float* x, const float* gamma, const float* beta, flo
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = (p.M + dlsg::kLinTileM - 1) / dlsg::kLinTileM;
     const unsigned grid = (unsigned)(ntiles < 2 * sms ? ntiles : 2 * sms);
-    if (dlsg::launch(dlsg::swin_mlp_kernel<1>, dim3(grid), dim3(dlsg::kLinThreads), smem, (dlsg::stream_t)stream, p) != 0) return DLSG_ELAUNCH;
-    if (dlsg::launch(dlsg::swin_mlp_kernel<2>, dim3(grid), dim3(dlsg::kLinThreads), smem, (dlsg::stream_t)stream, p) != 0) return DLSG_ELAUNCH;
+    if (dlsg::launch(dlsg::swin_mlp_fc1_kernel, dim3(grid), dim3(dlsg::kLinThreads), smem, (dlsg::stream_t)stream, p) != 0) return DLSG_ELAUNCH;
+    const unsigned grid2 = (unsigned)(ntiles < sms ? ntiles : sms);
+    if (dlsg::launch(dlsg::swin_mlp_fc2_kernel, dim3(grid2), dim3(dlsg::kLinThreads), dlsg::mlp_fc2_smem_bytes(C), (dlsg::stream_t)stream, p) != 0)
+        return DLSG_ELAUNCH;
     return DLSG_OK;
 #else
     (void)x; (void)gamma; (void)beta; (void)eps; (void)w1_f16; (void)b1; (void)w2_f16; (void)b2; (void)hidden_f16; (void)y;

@@ -9,9 +9,9 @@
 //                         land with cp.async directly in the canonical UMMA layout, tcgen05.mma accumulates over the
 //                         chunks in TMEM; epilogue adds bias (and the residual x) and writes fp32 rows
 //
-// Both operands use the no-swizzle K-major core-matrix layout of swin_linear_tc.cuh: a 16-byte cp.async is exactly one
-// core-matrix row (8 halves of one row), so no conversion pass is needed for fp16 sources.  The weights are converted
-// to fp16 once by the host module (they are constants at inference).  C = 160 is the reference's embedding width;
+// Both operands use the no-swizzle K-major core-matrix layout of swin_linear_tc.cuh ([k/8][row/8][8 rows][8 halves]).  The
+// weights are converted to fp16 and put in that order, chunk by chunk, once by the host module (constants at inference), and
+// fc1 writes the hidden layer in the same order per (tile, chunk), so every operand is staged by a contiguous block copy.  C = 160 is the reference's embedding width;
 // any C, H that are multiples of 32 with C <= 256 and H % C == 0 are accepted.
 // CUDA-only (tcgen05 / TMEM have no host model); validated on the B200 against torch (tests/test_swin_gpu.py).
 #pragma once
@@ -24,11 +24,11 @@ namespace dlsg {
 struct MlpParams {
     const float* x;        // [M, C] fp32 (tokens, channel fastest)
     const float* gamma; const float* beta; float eps;      // norm2
-    const half_t* w1h;     // [H, C] fp16
+    const half_t* w1h;     // fc1 weight [H, C], fp16, tiled: chunk nc = output rows nc*C..: [H/C][k/8][n/8][n%8][k%8]
     const float* b1;       // [H]
-    const half_t* w2h;     // [C, H] fp16
+    const half_t* w2h;     // fc2 weight [C, H], fp16, tiled: chunk kc = input columns kc*C..: [H/C][k/8][n/8][n%8][k%8]
     const float* b2;       // [C]
-    half_t* hidden;        // [M, H] fp16 workspace
+    half_t* hidden;        // fp16 workspace, ceil(M/128) * 128 * H elements: per (tile, chunk) a [128 x C] block in the same order
     float* y;              // [M, C]
     int M, C, H;
     int residual;          // 1: y = x + mlp(LN(x))  (the block's `x + forward_part2(x)`, :271);  0: y = mlp(LN(x))
@@ -47,6 +47,21 @@ inline size_t mlp_smem_bytes(int C, int H) {
     return a + w + bias + (size_t)kLinThreads * 8 + 64;
 }
 
+// exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16
+// rounding of the hidden layer): one MUFU.RCP, one MUFU.EX2 and a degree-5 polynomial instead of erff's ~3x longer sequence
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = poly * t * fast_exp2(-1.4426950408889634f * z * z);     // 1 - erf(z)
+    const float erf_abs = 1.0f - e;
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
 __device__ __forceinline__ void mbar_wait(unsigned long long* mbar, unsigned& phase) {
     unsigned done = 0;
     for (long long spin = 0; !done; ++spin) {
@@ -57,20 +72,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* mbar, unsigned& ph
     phase ^= 1u;
 }
 
-// copy a [rows x C] fp16 chunk (row stride ld halves, starting at column k0) into the canonical layout; rows >= nrows are zero
-__device__ __forceinline__ void stage_chunk_f16(unsigned char* dst, unsigned lbo, const half_t* src, size_t ld, int k0,
-                                                int rows, int nrows, int C, int tid) {
-    const int kc = C / 8;
-    for (int i = tid; i < rows * kc; i += kLinThreads) {
-        const int k8 = i / rows, r = i - k8 * rows;            // consecutive threads -> consecutive rows of one k chunk
-        unsigned char* d = dst + canon_off(r, k8, lbo);
-        if (r < nrows) cp_async16(d, src + (size_t)r * ld + k0 + 8 * k8);
-        else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
-    }
+// contiguous block copy global -> shared, 16 bytes per cp.async, consecutive threads on consecutive chunks (coalesced, conflict-free).
+// Every operand block below is stored in global memory already in the canonical core-matrix order, so staging is just this.
+__device__ __forceinline__ void copy_block_async(unsigned char* dst, const void* src, int nbytes, int tid) {
+    const unsigned char* s8 = static_cast<const unsigned char*>(src);
+#pragma unroll 4
+    for (int i = tid * 16; i < nbytes; i += kLinThreads * 16) cp_async16(dst + i, s8 + i);
 }
 
-template <int PHASE>    // 1: hidden = GELU(LN(x) W1^T + b1);  2: y = [x +] hidden W2^T + b2
-__global__ void __launch_bounds__(kLinThreads, 2) swin_mlp_kernel(MlpParams p) {
+// hidden = GELU(LN(x) W1^T + b1)
+__global__ void __launch_bounds__(kLinThreads, 2) swin_mlp_fc1_kernel(MlpParams p) {
+    constexpr int PHASE = 1;
     extern __shared__ __align__(128) unsigned char mlp_smem[];
     const int C = p.C, H = p.H, KC = C / 8;
     unsigned char* sA = mlp_smem;
@@ -109,7 +121,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_mlp_kernel(MlpParams p) {
         const int nrows = min(kLinTileM, p.M - row0);
         if (PHASE == 1) {
             // ---- A tile = LayerNorm(x rows), two threads per row (each one half of C), one pass with shifted sums
-            stage_chunk_f16(sW, lboW, p.w1h, (size_t)C, 0, C, C, C, tid);          // first W1 chunk: rows 0 .. C-1 of [H, C]
+            copy_block_async(sW, p.w1h, C * C * 2, tid);                           // first W1 chunk (output rows 0 .. C-1)
             cp_async_commit();
             const int trow = tid & (kLinTileM - 1), khalf = tid >> 7;
             const int kc0 = khalf * (KC / 2), kc1 = khalf ? KC : KC / 2;
@@ -117,6 +129,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_mlp_kernel(MlpParams p) {
             float s1 = 0.f, s2 = 0.f, x0 = 0.f;
             if (xr) {
                 x0 = __ldg(xr);
+#pragma unroll 5
                 for (int kc = kc0; kc < kc1; ++kc) {
                     const float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc));
                     const float4 b = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc + 4));
@@ -133,6 +146,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_mlp_kernel(MlpParams p) {
             const float m0 = s1 / (float)C;
             const float mu = x0 + m0;
             const float rstd = 1.0f / sqrtf(fmaxf(s2 / (float)C - m0 * m0, 0.f) + p.eps);
+#pragma unroll 5
             for (int kc = kc0; kc < kc1; ++kc) {
                 uint4 h = make_uint4(0u, 0u, 0u, 0u);
                 if (xr) {
@@ -162,7 +176,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_mlp_kernel(MlpParams p) {
                 mbar_wait(mbar, phase);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 if (nc + 1 < nchunks)                          // the MMA has consumed sW: the next chunk lands during the epilogue
-                    stage_chunk_f16(sW, lboW, p.w1h + (size_t)(nc + 1) * C * C, (size_t)C, 0, C, C, C, tid);
+                    copy_block_async(sW, p.w1h + (size_t)(nc + 1) * C * C, C * C * 2, tid);
                 cp_async_commit();
                 // epilogue: thread = token row; 32 columns at a time: bias, exact GELU (nn.GELU default), fp16
                 const int erow = quarter * 32 + lane;
@@ -173,55 +187,120 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_mlp_kernel(MlpParams p) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
                         const float a = v[j] + sBias[nc * C + c0 + j], b = v[j + 1] + sBias[nc * C + c0 + j + 1];
-                        hw[j / 2] = pack_h2(0.5f * a * (1.0f + erff(a * 0.70710678118654752f)),
-                                            0.5f * b * (1.0f + erff(b * 0.70710678118654752f)));
+                        hw[j / 2] = pack_h2(gelu_erf(a), gelu_erf(b));
                     }
-                    if (erow < nrows) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.hidden + (size_t)(row0 + erow) * H + nc * C + c0);
+                    // hidden is stored per (tile, chunk) in the canonical A layout of fc2: for one k8 the 32 rows of a warp are 512 contiguous bytes
+                    unsigned char* hb = reinterpret_cast<unsigned char*>(p.hidden + ((size_t)tile * nchunks + nc) * (size_t)(kLinTileM * C));
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(hw[4 * q4], hw[4 * q4 + 1], hw[4 * q4 + 2], hw[4 * q4 + 3]);
-                    }
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        *reinterpret_cast<uint4*>(hb + canon_off(erow, c0 / 8 + q4, lboA)) =
+                            make_uint4(hw[4 * q4], hw[4 * q4 + 1], hw[4 * q4 + 2], hw[4 * q4 + 3]);
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
                 __syncthreads();                               // TMEM drained before the next chunk's MMA overwrites it
             }
-        } else {
-            for (int kc = 0; kc < nchunks; ++kc) {
-                stage_chunk_f16(sA, lboA, p.hidden + (size_t)row0 * H, (size_t)H, kc * C, kLinTileM, nrows, C, tid);
-                stage_chunk_f16(sW, lboW, p.w2h, (size_t)H, kc * C, C, C, C, tid);
-                cp_async_commit();
-                cp_async_wait_group0();
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                __syncthreads();
-                if (tid == 0) {
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    for (int ks = 0; ks < C / 16; ++ks)
-                        umma_f16(tmem_base, umma_desc(smem_u32(sA) + (unsigned)(2 * ks) * lboA, lboA, 128u),
-                                 umma_desc(smem_u32(sW) + (unsigned)(2 * ks) * lboW, lboW, 128u), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(mbar)) : "memory");
-                }
-                mbar_wait(mbar, phase);                        // both operand buffers are free again
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            }
-            // epilogue: 32 columns at a time through a shared-memory transpose so that rows are read / written contiguously
-            float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);
+        }
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+inline size_t mlp_fc2_smem_bytes(int C) {
+    return 2 * (linear_a_region_bytes(C) + (size_t)C * C * 2) + (size_t)C * 4 + 64;
+}
+
+// y = [x +] hidden W2^T + b2.  One CTA per SM; the (tile, K chunk) items run through a two-stage ring: while the
+// tensor core works on one stage, the fp16 hidden rows and the W2 chunk of the next item (also the first chunk of the
+// next tile, during the epilogue) stream into the other stage with cp.async.
+__global__ void __launch_bounds__(kLinThreads, 1) swin_mlp_fc2_kernel(MlpParams p) {
+    extern __shared__ __align__(128) unsigned char mlp_smem[];
+    const int C = p.C, H = p.H;
+    const size_t a_bytes = linear_a_region_bytes(C), w_bytes = (size_t)C * C * 2;
+    auto stA = [&](int st) { return mlp_smem + (size_t)st * (a_bytes + w_bytes); };      // stage st: A region, then the W chunk
+    auto stW = [&](int st) { return mlp_smem + (size_t)st * (a_bytes + w_bytes) + a_bytes; };
+    float* sBias = reinterpret_cast<float*>(mlp_smem + 2 * (a_bytes + w_bytes));
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sBias + C);
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(mbar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned lboA = (unsigned)(kLinTileM / 8) * 128u, lboW = (unsigned)(C / 8) * 128u;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(smem_u32(mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = tid; i < C; i += kLinThreads) sBias[i] = p.b2 ? __ldg(p.b2 + i) : 0.f;
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+    const unsigned idesc = umma_idesc_f16(kLinTileM, C);
+    const int quarter = warp & 3, wsub = warp >> 2;
+    const unsigned tlane = tmem_base + ((unsigned)(quarter * 32) << 16);
+
+    const int nk = H / C;
+    const int ntiles = (p.M + kLinTileM - 1) / kLinTileM;
+    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int nitems = my_tiles * nk;
+    auto issue = [&](int item) {
+        const int tile = blockIdx.x + (item / nk) * gridDim.x, kc = item % nk, s = item & 1;
+        copy_block_async(stA(s), p.hidden + ((size_t)tile * nk + kc) * (size_t)(kLinTileM * C), kLinTileM * C * 2, tid);
+        copy_block_async(stW(s), p.w2h + (size_t)kc * C * C, C * C * 2, tid);
+        cp_async_commit();
+    };
+    if (nitems > 0) issue(0);
+    unsigned phase = 0;
+    bool pending = false;                                      // an MMA commit that has not been waited for
+    for (int i = 0; i < nitems; ++i) {
+        if (pending) {                                         // MMA(i-1) done: the other stage is free again
+            mbar_wait(mbar, phase);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            pending = false;
+        }
+        if (i + 1 < nitems) { issue(i + 1); cp_async_wait_group1(); }
+        else cp_async_wait_group0();
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncthreads();                                       // item i's operands are in place for every thread
+        const int s = i & 1, kc = i % nk;
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            for (int ks = 0; ks < C / 16; ++ks)
+                umma_f16(tmem_base, umma_desc(smem_u32(stA(s)) + (unsigned)(2 * ks) * lboA, lboA, 128u),
+                         umma_desc(smem_u32(stW(s)) + (unsigned)(2 * ks) * lboW, lboW, 128u), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(mbar)) : "memory");
+        }
+        pending = true;
+        if (kc == nk - 1) {
+            mbar_wait(mbar, phase);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            pending = false;
+            // epilogue: 32 columns at a time through a transpose in this stage's (now idle) A region: rows are read / written contiguously
+            const int row0 = (blockIdx.x + (i / nk) * gridDim.x) * kLinTileM;
+            float* stage = reinterpret_cast<float*>(stA(s)) + warp * (32 * 33);
             for (int c0 = wsub * 32; c0 < C; c0 += 64) {
+                // the residual rows of this 32 x 32 block: all 32 loads in flight before the accumulator is touched
+                float xr[32];
+                const float* xb = p.x + (size_t)(row0 + quarter * 32) * C + c0 + lane;
+                const int live = min(32, p.M - (row0 + quarter * 32));        // rows of this block inside the matrix (may be <= 0)
+#pragma unroll
+                for (int r = 0; r < 32; ++r) xr[r] = (p.residual && r < live) ? __ldg(xb + (size_t)r * C) : 0.f;
                 float v[32];
                 tmem_ld32(tlane + (unsigned)c0, v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j] + sBias[c0 + j];
                 __syncwarp();
-                for (int r = 0; r < 32; ++r) {
-                    const int row = row0 + quarter * 32 + r;
-                    if (row < p.M) {
-                        const size_t g = (size_t)row * C + c0 + lane;
-                        p.y[g] = stage[r * 33 + lane] + (p.residual ? __ldg(p.x + g) : 0.f);
-                    }
-                }
+                float* yb = p.y + (size_t)(row0 + quarter * 32) * C + c0 + lane;
+#pragma unroll
+                for (int r = 0; r < 32; ++r)
+                    if (r < live) yb[(size_t)r * C] = stage[r * 33 + lane] + xr[r];
                 __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            __syncthreads();                                   // TMEM drained, stage region free for the next tile's operands
+            __syncthreads();                                   // TMEM drained and the scratch free before the ring moves on
         }
     }
     if (warp == 0) {

@@ -417,12 +417,19 @@ class SwinTransformerBlock3D(nn.Module):
         return not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())))
 
     def _mlp_f16_weights(self):
-        """fc1 / fc2 weights as fp16, converted once and refreshed when the parameters change (constants at inference)."""
+        """fc1 / fc2 weights as fp16 in the kernels' chunked core-matrix order ([H/C][k/8][n/8][n%8][k%8], see
+        csrc/swin_mlp_tc.cuh), converted once and refreshed when the parameters change (constants at inference)."""
         w1, w2 = self.mlp.fc1.weight, self.mlp.fc2.weight
         key = (w1.data_ptr(), w1._version, w2.data_ptr(), w2._version, w1.device)
         cache = getattr(self, "_mlp_f16", None)
         if cache is None or cache[0] != key:
-            cache = (key, w1.detach().to(torch.float16).contiguous(), w2.detach().to(torch.float16).contiguous())
+            Hd, C = w1.shape
+            nk = Hd // C
+            # fc1 [H, C]: chunk = C output rows n;  [nc, n/8, n%8, k/8, k%8] -> [nc, k/8, n/8, n%8, k%8]
+            w1t = w1.detach().to(torch.float16).view(nk, C // 8, 8, C // 8, 8).permute(0, 3, 1, 2, 4).contiguous()
+            # fc2 [C, H]: chunk = C input columns k;  [n/8, n%8, kc, k/8, k%8] -> [kc, k/8, n/8, n%8, k%8]
+            w2t = w2.detach().to(torch.float16).view(C // 8, 8, nk, C // 8, 8).permute(2, 3, 0, 1, 4).contiguous()
+            cache = (key, w1t, w2t)
             self._mlp_f16 = cache
         return cache[1], cache[2]
 
@@ -443,7 +450,7 @@ class SwinTransformerBlock3D(nn.Module):
         lib = _lib.load()
         M = x.numel() // C
         w1h, w2h = self._mlp_f16_weights()
-        hidden = torch.empty((M, Hd), dtype=torch.float16, device=x.device)
+        hidden = torch.empty((-(-M // 128) * 128, Hd), dtype=torch.float16, device=x.device)    # tile-ordered workspace
         y = torch.empty_like(x)
         if M == 0:
             return y

@@ -208,9 +208,12 @@ int dlsg_swin_proj_scatter_f32(const float* attn_out, const float* weight, const
 
 /* forward_part2 of the Swin block (:251-252; Mlp :20-38, norm2 :208) as two tcgen05 GEMM kernels:
  *     y = [x +] fc2( GELU( fc1( LayerNorm(x) ) ) )        (residual != 0 gives the block's `x + forward_part2(x)`, :271)
- * x, y [M, C] fp32 (tokens of [B,D,H,W,C]); gamma / beta [C]; w1_f16 [H, C] and w2_f16 [C, H] are the fc1 / fc2 weights
- * converted to fp16 once by the caller (constants at inference), b1 [H], b2 [C] fp32 or NULL; hidden_f16 is a caller-owned
- * [M, H] fp16 workspace.  GELU is the exact erf form (nn.GELU default).  C % 32 == 0, C <= 256, H % C == 0. */
+ * x, y [M, C] fp32 (tokens of [B,D,H,W,C]); gamma / beta [C]; b1 [H], b2 [C] fp32 or NULL.  The weights are passed as fp16 in
+ * the tensor core's core-matrix order, prepared once by the caller (constants at inference): with nk = H / C chunks,
+ *   w1_f16[nc][k/8][n/8][n%8][k%8] = fc1.weight[nc*C + n, k]        (chunk = C output rows,    n, k < C)
+ *   w2_f16[kc][k/8][n/8][n%8][k%8] = fc2.weight[n, kc*C + k]        (chunk = C input columns,  n, k < C)
+ * hidden_f16 is a caller-owned fp16 workspace of ceil(M/128)*128*H elements.  GELU is the exact erf form (nn.GELU default).
+ * C % 32 == 0, C <= 256, H % C == 0. */
 int dlsg_swin_mlp_f32(const float* x, const float* gamma, const float* beta, float eps,
                       const void* w1_f16, const float* b1, const void* w2_f16, const float* b2,
                       void* hidden_f16, float* y, long long M, int C, int H, int residual, void* stream);

@@ -75,3 +75,22 @@ for shift in (False, True):
     print(json.dumps({"shift": shift, "slices": B, "windows": nwin, "part1_fused_ms": round(t_fused, 3), "core_ms": round(t_core, 3),
                       "part1_eager_ms": round(t_eager, 3), "core_useful_TFLOPs": round(flops_core / t_core / 1e9, 2),
                       "core_us_per_slice": round(1e3 * t_core / B, 1), "rel_err_vs_eager": err}), flush=True)
+
+# ---- second half of the block (forward_part2) and the whole block: tcgen05 MLP kernels vs torch eager (fp32 and TF32 cuBLAS)
+blk = wa.SwinTransformerBlock3D(C, heads, ws0, ss0, qkv_bias=True).to(dev).eval()
+x = torch.randn(B, D, H, W, C, device=dev)
+ws, ss = wa.get_window_size((D, H, W), ws0, ss0)
+mask = wa.compute_mask(7, 48, 40, ws, ss, dev)
+with torch.no_grad():
+    eager2 = lambda: x + blk.mlp(blk.norm2(x))
+    t_k = bench.time_op(lambda: blk._part2_tensor_core(x, residual=True), 10, dev)
+    t_e = bench.time_op(eager2, 10, dev)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    t_e_tf32 = bench.time_op(eager2, 10, dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    err2 = float((blk._part2_tensor_core(x, residual=True) - eager2()).norm() / eager2().norm())
+    t_blk = bench.time_op(lambda: blk(x, mask), 10, dev)
+tokens = x.numel() // C
+print(json.dumps({"what": "x + forward_part2(x)", "slices": B, "tokens": tokens, "kernels_ms": round(t_k, 4), "eager_fp32_ms": round(t_e, 4),
+                  "eager_tf32_ms": round(t_e_tf32, 4), "useful_TFLOPs": round(4.0 * tokens * C * 4 * C / t_k / 1e9, 1),
+                  "rel_err_vs_eager": err2, "whole_block_ms": round(t_blk, 4)}), flush=True)
