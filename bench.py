@@ -219,11 +219,15 @@ def swin_block_timing(dev, slices=8):
         n0 = _lib_launches()
         ms = time_op(lambda: blk.forward_part1(x, mask), 10, dev)
         launches = (_lib_launches() - n0) // 12
+        ms2 = time_op(lambda: blk._part2_tensor_core(x, residual=True), 10, dev)
+        ms_block = time_op(lambda: blk(x, mask), 10, dev)
     windows = slices * mask.shape[0]
     useful = windows * (2 * 448 * 160 * 480 + 4 * 448 * 448 * 160 + 2 * 448 * 160 * 160)      # qkv + QK^T/PV + proj
     return {"what": "SwinTransformerBlock3D.forward_part1, shifted, fp16 tensor-core operands", "slices": slices,
             "windows": windows, "ms": ms, "us_per_slice": 1e3 * ms / slices, "useful_TFLOPs": useful / (ms * 1e-3) / 1e12,
-            "launches_per_call": launches}
+            "launches_per_call": launches,
+            "part2_mlp_ms": ms2, "part2_useful_TFLOPs": 4.0 * x.numel() * 4 * C / (ms2 * 1e-3) / 1e12,
+            "whole_block_ms": ms_block, "whole_block_launches": 5}
 
 
 def _lib_launches():

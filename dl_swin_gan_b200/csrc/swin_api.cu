@@ -184,8 +184,8 @@ int dlsg_swin_qkv_fused_f32(const float* x, const float* gamma, const float* bet
 #endif
 }
 
-int dlsg_swin_proj_scatter_f32(const float* attn_out, const float* weight, const float* bias, float* y,
-                               int B, int D, int H, int W, int C, const int* window, const int* shift, void* stream) {
+int dlsg_swin_proj_scatter_residual_f32(const float* attn_out, const float* weight, const float* bias, const float* residual,
+                                        float* y, int B, int D, int H, int W, int C, const int* window, const int* shift, void* stream) {
 #if defined(__CUDACC__)
     dlsg::LinearParams p{};
     int st = dlsg::make_geom(p.g, B, D, H, W, C, window, shift);
@@ -195,13 +195,18 @@ int dlsg_swin_proj_scatter_f32(const float* attn_out, const float* weight, const
     st = linear_check((int)M, C, C, attn_out, weight);
     if (st != DLSG_OK) return st;
     if (!y) return DLSG_EINVAL;
-    p.x = attn_out; p.w = weight; p.bias = bias; p.y = y; p.M = (int)M; p.N = C; p.K = C;
+    p.x = attn_out; p.w = weight; p.bias = bias; p.y = y; p.resid = residual; p.M = (int)M; p.N = C; p.K = C;
     return linear_launch<dlsg::A_PLAIN, dlsg::E_SCATTER>(p, stream);
 #else
-    (void)attn_out; (void)weight; (void)bias; (void)y; (void)B; (void)D; (void)H; (void)W; (void)C;
+    (void)attn_out; (void)weight; (void)bias; (void)residual; (void)y; (void)B; (void)D; (void)H; (void)W; (void)C;
     (void)window; (void)shift; (void)stream;
     return DLSG_EUNSUPPORTED;
 #endif
+}
+
+int dlsg_swin_proj_scatter_f32(const float* attn_out, const float* weight, const float* bias, float* y,
+                               int B, int D, int H, int W, int C, const int* window, const int* shift, void* stream) {
+    return dlsg_swin_proj_scatter_residual_f32(attn_out, weight, bias, nullptr, y, B, D, H, W, C, window, shift, stream);
 }
 
 int dlsg_swin_mlp_f32(const float* x, const float* gamma, const float* beta, float eps,

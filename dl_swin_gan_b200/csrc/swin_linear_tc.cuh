@@ -79,6 +79,7 @@ struct LinearParams {
     const float* w;      // [N, K]
     const float* bias;   // [N] or NULL
     float* y;            // E_PLAIN: [M, N];  E_SCATTER: feature volume [B, D, H, W, N]
+    const float* resid;  // E_SCATTER: optional [B, D, H, W, N] added to the scattered rows (the block's shortcut, :262)
     int M, N, K;
     int tmem_cols;       // power of two >= N, >= 32
     // A_LN_GATHER / E_SCATTER: rows are window tokens of this geometry (M = B*nW*tokens)
@@ -273,6 +274,20 @@ __global__ void __launch_bounds__(kLinThreads, (EMODE == E_QKV16) ? 1 : 2) swin_
 #pragma unroll
                 for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j] + sBias[c0 + j];
                 __syncwarp();
+                if (EMODE == E_SCATTER && p.resid) {
+                    // shortcut rows of this 32 x 32 block: all loads in flight together, then add and store
+                    float xr[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const long long off = sRowOff[quarter * 32 + r];
+                        xr[r] = (off >= 0) ? __ldg(p.resid + (size_t)off * N + c0 + lane) : 0.f;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const long long off = sRowOff[quarter * 32 + r];
+                        if (off >= 0) p.y[(size_t)off * N + c0 + lane] = stage[r * 33 + lane] + xr[r];
+                    }
+                } else
                 for (int r = 0; r < 32; ++r) {
                     if (EMODE == E_SCATTER) {
                         const long long off = sRowOff[quarter * 32 + r];

@@ -363,7 +363,7 @@ class SwinTransformerBlock3D(nn.Module):
             shifted_x = torch.roll(shifted_x, shifts=(shift_size[0], shift_size[1], shift_size[2]), dims=(1, 2, 3))
         return shifted_x[:, :D, :H, :W, :].contiguous()
 
-    def _part1_tensor_core(self, x, window_size, shift_size, mask, rid):
+    def _part1_tensor_core(self, x, window_size, shift_size, mask, rid, residual=None):
         """Three launches for the whole of forward_part1 (inference):
         [LN + pad + roll + partition + qkv] tcgen05 GEMM -> attention core on fp16 q/k/v^T -> [proj + reverse + roll + crop]
         tcgen05 GEMM.  Returns None when the shape is outside what those kernels cover (the caller then takes the
@@ -408,8 +408,10 @@ class SwinTransformerBlock3D(nn.Module):
                 q16.data_ptr(), k16.data_ptr(), vt16.data_ptr(), opt(attn.relative_position_bias_table), core.data_ptr(),
                 B_, N, heads, hd, _i3(attn.window_size), mode, mptr, nW, _stream())
             _lib.check(st, "dlsg_swin_window_attention_f16")
-            st = lib.dlsg_swin_proj_scatter_f32(core.data_ptr(), opt(attn.proj.weight), opt(attn.proj.bias), y.data_ptr(),
-                                                B, D, H, W, C, _i3(window_size), _i3(shift_size), _stream())
+            st = lib.dlsg_swin_proj_scatter_residual_f32(
+                core.data_ptr(), opt(attn.proj.weight), opt(attn.proj.bias),
+                residual.data_ptr() if residual is not None else None, y.data_ptr(),
+                B, D, H, W, C, _i3(window_size), _i3(shift_size), _stream())
             _lib.check(st, "dlsg_swin_proj_scatter")
         return y
 
@@ -469,7 +471,27 @@ class SwinTransformerBlock3D(nn.Module):
                 return y
         return self.drop_path(self.mlp(self.norm2(x)))
 
+    def _forward_inference(self, x, mask_matrix):
+        """Whole block in five launches: qkv GEMM, attention core, proj GEMM (+ shortcut), fc1, fc2 (+ residual)."""
+        if not (isinstance(self.norm1, nn.LayerNorm) and (isinstance(self.drop_path, nn.Identity) or not self.training)):
+            return None
+        B, D, H, W, C = x.shape
+        window_size, shift_size = get_window_size((D, H, W), self.window_size, self.shift_size)
+        shifted = any(i > 0 for i in shift_size)
+        Dp, Hp, Wp = (-(-n // w) * w for n, w in zip((D, H, W), window_size))
+        _require_cuda_f32(x, "SwinTransformerBlock3D input")
+        x = x.contiguous()
+        rid = _region_ids_for(mask_matrix, Dp, Hp, Wp, window_size, shift_size, x.device) if shifted else None
+        y = self._part1_tensor_core(x, window_size, shift_size, mask_matrix if shifted else None, rid, residual=x)
+        if y is None:
+            return None
+        return self._part2_tensor_core(y, residual=True)
+
     def forward(self, x, mask_matrix):
+        if self._inference(x) and not self.use_checkpoint:
+            y = self._forward_inference(x, mask_matrix)
+            if y is not None:
+                return y
         shortcut = x
         if self.use_checkpoint:
             x = checkpoint.checkpoint(self.forward_part1, x, mask_matrix, use_reentrant=False)

@@ -206,6 +206,11 @@ int dlsg_swin_qkv_fused_f32(const float* x, const float* gamma, const float* bet
 int dlsg_swin_proj_scatter_f32(const float* attn_out, const float* weight, const float* bias, float* y,
                                int B, int D, int H, int W, int C, const int* window, const int* shift, void* stream);
 
+/* The same with the block's shortcut folded in (`x = shortcut + drop_path(part1)`, :262, DropPath = identity at inference):
+ * y[token] = residual[token] + proj(attn_out row); residual [B,D,H,W,C] or NULL. */
+int dlsg_swin_proj_scatter_residual_f32(const float* attn_out, const float* weight, const float* bias, const float* residual,
+                                        float* y, int B, int D, int H, int W, int C, const int* window, const int* shift, void* stream);
+
 /* forward_part2 of the Swin block (:251-252; Mlp :20-38, norm2 :208) as two tcgen05 GEMM kernels:
  *     y = [x +] fc2( GELU( fc1( LayerNorm(x) ) ) )        (residual != 0 gives the block's `x + forward_part2(x)`, :271)
  * x, y [M, C] fp32 (tokens of [B,D,H,W,C]); gamma / beta [C]; b1 [H], b2 [C] fp32 or NULL.  The weights are passed as fp16 in
