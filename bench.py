@@ -308,6 +308,14 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    # a fresh process / box needs more than three short steps to reach steady clocks and page everything in: keep warming up
+    # (untimed) until 0.5 s have passed; the JSON line reports the warm-up steps actually run
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 0.5:
+        step()
+        torch.cuda.synchronize(dev)
+        args.warmup += 1
+    barrier()
     n0 = lib.dlsg_launch_count()
     with ClockSampler(local_rank) as clocks:
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -335,7 +335,7 @@ template <int RX, int MODE>
 int launch_rows_lines(const float2* src, float2* dst, const float* w, const WeightStrides& ws, float scale,
                       const LinePlan& lp, const SenseDims& d, stream_t s, int src_lines) {
     using Cfg = RowCfg<RX>;
-    const size_t smem = (size_t)Cfg::WARPS * (MODE == MODE_NORMAL ? 2 : 1) * Cfg::BUF * sizeof(float2);
+    const size_t smem = RowLinesCfg<RX>::SMEM;
     const long long units = (long long)d.B * d.t_count;
     const long long batches = ((long long)d.C * lp.lmax + Cfg::NB - 1) / Cfg::NB;          // per (b, t), upper bound
     long long nsplit = (kTargetLineRowCtas + units - 1) / units;

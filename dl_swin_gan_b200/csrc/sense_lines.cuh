@@ -28,6 +28,9 @@
 #ifndef DLSG_LINES_ADJ_MINB
 #define DLSG_LINES_ADJ_MINB(RY) ColCfg<RY>::MINB
 #endif
+#ifndef DLSG_LINES_ROWS_MINB
+#define DLSG_LINES_ROWS_MINB 3
+#endif
 #define DLSG_PRAGMA(x) _Pragma(#x)
 #define DLSG_UNROLL(n) DLSG_PRAGMA(unroll n)
 
@@ -336,18 +339,25 @@ DLSG_UNROLL(DLSG_LINES_ITEM_UNROLL)
 //   MODE_NORMAL: tl              = IDFT_X((W*scale)^2 * DFT_X(tl))            in place
 // The flattened (coil, line) items of one (b, t) are walked in warp batches of NB = 32/RX rows by the 4 warps of
 // `nsplit` CTAs (the split keeps small batches, e.g. the chunks of a pipelined reconstruction, at several waves).
+// The raw rows of a warp's next batch arrive by cp.async in its staging buffer while the current batch is transformed;
+// the weights of a batch are fetched together (one exposed latency per batch, not per row).
+template <int RX>
+struct RowLinesCfg {
+    static constexpr int PER_WARP = RowCfg<RX>::BUF + RowCfg<RX>::NB * RowCfg<RX>::X;      // exchange buffer + staged rows (complex)
+    static constexpr size_t SMEM = (size_t)RowCfg<RX>::WARPS * PER_WARP * sizeof(float2);
+};
+
 template <int RX, int MODE>
-DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(128, 3)
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(128, DLSG_LINES_ROWS_MINB)
 sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict__ w, WeightStrides ws, float scale,
                         LinePlan lp, SenseDims d, int src_lines, int nsplit) {
     using Cfg = RowCfg<RX>;
-    constexpr int NB = Cfg::NB;
+    constexpr int NB = Cfg::NB, X = Cfg::X;
     constexpr int DIR = (MODE == MODE_ADJ) ? +1 : -1;
-    constexpr int NBUF = (MODE == MODE_NORMAL) ? 2 : 1;
     DLSG_DYN_SMEM(float2, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2* buf = smem + warp * (NBUF * Cfg::BUF);
-    float2* buf2 = buf + (NBUF - 1) * Cfg::BUF;  // way back of the normal operator (aliases buf otherwise, unused)
+    float2* buf = smem + warp * RowLinesCfg<RX>::PER_WARP;
+    float2* stg = buf + Cfg::BUF;                              // [r][X] raw rows of the batch being started
     const int split = (int)(blockIdx.x % nsplit);             // nsplit CTAs share the items of one (b, t)
     const int unit = (int)(blockIdx.x / nsplit);
     const int tl = unit % d.t_count, b = unit / d.t_count;
@@ -356,25 +366,55 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
     const int n = __ldg(lp.counts + bt);
     const int items = d.C * n;
     const int* list = lp.list + (size_t)bt * d.Y;
+    const bool from_k = (MODE == MODE_ADJ) && !src_lines;
 
     float2 tw[RX];
     lane_twiddles<RX, DIR>(lane, tw);
     const float* wbt = w + (b * ws.b + t * ws.t + lane * ws.x);      // weights of this lane's first column of (b, t)
-    auto wrow = [&](int c, int ky) { return wbt + (c * ws.c + ky * ws.y); };
 
-    for (int it0 = (split * Cfg::WARPS + warp) * NB; it0 < items; it0 += nsplit * Cfg::WARPS * NB) {
+    auto stage_batch = [&](int it0) {
         const int nrows = min(NB, items - it0);
+        for (int r = 0; r < nrows; ++r) {
+            const int item = it0 + r, c = item / n, i = item - c * n;
+            const float2* row = src + (from_k ? idx_k(d, b, c, t, __ldg(list + i)) : idx_lines(d, lp.lmax, b, c, t, i));
+#pragma unroll
+            for (int m = 0; m < (X / 2 + 31) / 32; ++m) {
+                const int q = lane + 32 * m;
+                if ((X / 2) % 32 == 0 || q < X / 2) cp_async16(stg + r * X + 2 * q, row + 2 * q);
+            }
+        }
+        cp_async_commit();
+    };
+    // scale * W of the lane's RX columns of every row of the batch
+    auto load_weights = [&](int it0, int nrows, float (&wv)[NB][RX]) {
 #pragma unroll
         for (int r = 0; r < NB; ++r) {
             if (r < nrows) {
                 const int item = it0 + r, c = item / n, i = item - c * n;
-                const int ky = __ldg(list + i);
-                const float2* s = src + ((MODE == MODE_ADJ && !src_lines) ? idx_k(d, b, c, t, ky) : idx_lines(d, lp.lmax, b, c, t, i)) + lane;
+                const float* wr = wbt + (c * ws.c + __ldg(list + i) * ws.y);
+#pragma unroll
+                for (int j = 0; j < RX; ++j) wv[r][j] = scale * __ldg(wr + 32 * j * ws.x);
+            }
+        }
+    };
+
+    const int stride = nsplit * Cfg::WARPS * NB;
+    int it0 = (split * Cfg::WARPS + warp) * NB;
+    if (it0 < items) stage_batch(it0);
+    for (; it0 < items; it0 += stride) {
+        const int nrows = min(NB, items - it0);
+        float wv[NB][RX];
+        if (MODE == MODE_ADJ) load_weights(it0, nrows, wv);
+        cp_async_wait_group0();
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
+            if (r < nrows) {
                 float2 v[RX];
 #pragma unroll
                 for (int j = 0; j < RX; ++j) {
-                    v[j] = s[32 * j];
-                    if (MODE == MODE_ADJ) v[j] = cscale(v[j], scale * __ldg(wrow(c, ky) + 32 * j * ws.x));
+                    v[j] = stg[r * X + lane + 32 * j];
+                    if (MODE == MODE_ADJ) v[j] = cscale(v[j], wv[r][j]);
                 }
                 Dft<RX, DIR>::run(v);
                 float2* o = buf + (r * RX) * Cfg::S1 + lane;
@@ -382,43 +422,39 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
                 for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmul(v[k2], tw[k2]);
             }
         }
-        __syncwarp();
+        __syncwarp();                                          // staging buffer consumed, view 1 complete
+        if (it0 + stride < items) stage_batch(it0 + stride);   // lands while the rest of this batch runs
         row_radix32<RX, DIR>(buf, lane, nrows);
         if (MODE == MODE_NORMAL) {
+            // way back in place: rows in reverse order, because view 1 of row r starts behind the end of view 2 of row r-1
+            // (34 RX r >= 33 RX r - RX) and only overlaps rows >= r, which have been consumed
+            load_weights(it0, nrows, wv);
 #pragma unroll
-            for (int r = 0; r < NB; ++r) {
+            for (int rr = 0; rr < NB; ++rr) {
+                const int r = NB - 1 - rr;
                 if (r < nrows) {
-                    const int item = it0 + r, c = item / n, i = item - c * n;
-                    const int ky = __ldg(list + i);
                     float2 v[RX];
 #pragma unroll
-                    for (int j = 0; j < RX; ++j) {
-                        const float wv = scale * __ldg(wrow(c, ky) + 32 * j * ws.x);
-                        v[j] = cscale(buf[r * Cfg::S2 + lane + 32 * j], wv * wv);
-                    }
+                    for (int j = 0; j < RX; ++j) v[j] = cscale(buf[r * Cfg::S2 + lane + 32 * j], wv[r][j] * wv[r][j]);
+                    __syncwarp();                              // every lane has read row r before its view 1 is written
                     Dft<RX, +1>::run(v);
-                    float2* o = buf2 + (r * RX) * Cfg::S1 + lane;
+                    float2* o = buf + (r * RX) * Cfg::S1 + lane;
 #pragma unroll
                     for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmulc(v[k2], tw[k2]);
                 }
             }
             __syncwarp();
-            row_radix32<RX, +1>(buf2, lane, nrows);
+            row_radix32<RX, +1>(buf, lane, nrows);
         }
-        const float2* res = (MODE == MODE_NORMAL) ? buf2 : buf;
+        if (MODE == MODE_FWD) load_weights(it0, nrows, wv);
 #pragma unroll
         for (int r = 0; r < NB; ++r) {
             if (r < nrows) {
                 const int item = it0 + r, c = item / n, i = item - c * n;
-                const int ky = __ldg(list + i);
-                float2* o = dst + ((MODE == MODE_FWD) ? idx_k(d, b, c, t, ky) : idx_lines(d, lp.lmax, b, c, t, i)) + lane;
-                const float2* sv = res + r * Cfg::S2 + lane;
+                float2* o = dst + ((MODE == MODE_FWD) ? idx_k(d, b, c, t, __ldg(list + i)) : idx_lines(d, lp.lmax, b, c, t, i)) + lane;
+                const float2* sv = buf + r * Cfg::S2 + lane;
 #pragma unroll
-                for (int j = 0; j < RX; ++j) {
-                    float2 q = sv[32 * j];
-                    if (MODE == MODE_FWD) q = cscale(q, scale * __ldg(wrow(c, ky) + 32 * j * ws.x));
-                    o[32 * j] = q;
-                }
+                for (int j = 0; j < RX; ++j) o[32 * j] = (MODE == MODE_FWD) ? cscale(sv[32 * j], wv[r][j]) : sv[32 * j];
             }
         }
         __syncwarp();
