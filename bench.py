@@ -73,7 +73,8 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self.recording = False        # the thread is started during warm-up (NVML's first calls are slow and can stall
+        self._stop = threading.Event()  # kernel launches); samples count only once the timed region has begun
         self._thread = None
         try:
             import pynvml
@@ -94,11 +95,13 @@ class ClockSampler:
         }
         while not self._stop.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                if self.recording:
+                    self.samples.append(mhz)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
             self._stop.wait(0.05)
@@ -310,20 +313,22 @@ def main():
     barrier()
     # a fresh process / box needs more than three short steps to reach steady clocks and page everything in: keep warming up
     # (untimed) until 0.5 s have passed; the JSON line reports the warm-up steps actually run
-    t_w = time.perf_counter()
-    while time.perf_counter() - t_w < 0.5:
-        step()
-        torch.cuda.synchronize(dev)
-        args.warmup += 1
-    barrier()
-    n0 = lib.dlsg_launch_count()
     with ClockSampler(local_rank) as clocks:
+        t_w = time.perf_counter()
+        while time.perf_counter() - t_w < 0.5:
+            step()
+            torch.cuda.synchronize(dev)
+            args.warmup += 1
+        barrier()
+        n0 = lib.dlsg_launch_count()
+        clocks.recording = True
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s_ev.record()
         for _ in range(args.steps):
             out = step()
         e_ev.record()
         barrier()
+        clocks.recording = False
     launches = int(lib.dlsg_launch_count() - n0)
     ms_per_step = max_over_ranks(s_ev.elapsed_time(e_ev), dev) / args.steps      # device-timed, max over ranks
     value = world * B / (ms_per_step * 1e-3)

@@ -250,10 +250,17 @@ DLSG_UNROLL(DLSG_LINES_ITEM_UNROLL)
             const int l = grp + i * RY;
             if (l < 32) {
                 float2 v[RY];
+                int any = -1;                        // stays negative when none of the RY lines l + 32 j is sampled
 #pragma unroll
                 for (int j = 0; j < RY; ++j) {
                     const int off = sp[l + 32 * j];
+                    any &= off;
                     v[j] = (off >= 0) ? cmp[off + col] : make_float2(0.f, 0.f);
+                }
+                if (any < 0) {                       // uniform over the warp (same l for all its columns): the DFT of zeros
+#pragma unroll
+                    for (int k2 = 0; k2 < RY; ++k2) work[(k2 * 32 + l) * SW + col] = make_float2(0.f, 0.f);
+                    continue;
                 }
                 Dft<RY, +1>::run(v);
 #pragma unroll
