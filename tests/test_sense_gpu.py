@@ -125,7 +125,23 @@ def test_sampled_line_path_is_selected_and_agrees_with_dense(dev, monkeypatch):
                 assert plan is None
         for a, b in zip(outs["1"], outs["0"]):
             assert rel_l2(to_np(a), to_np(b)) < 2e-6
+        monkeypatch.setenv("DLSG_SAMPLED_LINES", "1")
+        monkeypatch.setenv("DLSG_WORKSPACE_MB", "0.001")                   # one slice per workspace chunk: bit-identical results
+        A = SenseModel(maps, weights=w)
+        for a, b in zip([A(x), A(k, adjoint=True), A.dc_step(x, aty, -2.0)], [outs["1"][0], outs["1"][1], outs["1"][3]]):
+            assert torch.equal(a, b)
+        monkeypatch.delenv("DLSG_WORKSPACE_MB")
         assert not outs["1"][0][(w == 0).expand(B, C, T, Y, X)].any()     # forward: unsampled samples are exact zeros
+    # 35 % of the lines sampled: still the sampled-line path (larger line buffer, one column CTA per SM)
+    w40 = (torch.rand(B, 1, T, Y, 1, generator=g, device=dev) < 0.35).float().expand(B, 1, T, Y, X).contiguous()
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DLSG_SAMPLED_LINES", mode)
+        A = SenseModel(maps, weights=w40)
+        res[mode] = [A(x), A(k, adjoint=True), A.dc_step(x, aty, -2.0)]
+        assert (A._line_plans.get((B, E, C, T, Y, X)) is not None) == (mode == "1")
+    for a, b in zip(res["1"], res["0"]):
+        assert rel_l2(to_np(a), to_np(b)) < 2e-6
     monkeypatch.setenv("DLSG_SAMPLED_LINES", "1")
     dense = (torch.rand(B, 1, T, Y, 1, generator=g, device=dev) < 0.7).float().expand(B, 1, T, Y, X).contiguous()
     A = SenseModel(maps, weights=dense)
