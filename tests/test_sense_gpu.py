@@ -175,6 +175,28 @@ def test_adjoint_reads_pinned_host_kspace_in_place(dev, monkeypatch):
         make_model(maps, mask, dev)(hk, adjoint=True)
 
 
+def test_repeated_launches_are_bit_identical(dev, monkeypatch):
+    """No atomics and no order-dependent reductions in this path: 12 repeats of every operator give the same bits on both
+    kernel families (a shared-memory race or a missing barrier shows up here as run-to-run differences)."""
+    from dl_swin_gan_b200.mri import SenseModel
+    B, E, C, T, Y, X = 6, 1, 8, 20, 192, 160
+    g = torch.Generator(device=dev).manual_seed(9)
+
+    def cn(*s):
+        return torch.view_as_complex(torch.randn(*s, 2, generator=g, device=dev))
+
+    maps, x, k, aty = cn(B, E, C, 1, Y, X), cn(B, E, T, Y, X), cn(B, C, T, Y, X), cn(B, E, T, Y, X)
+    mask = (torch.rand(B, 1, T, Y, 1, generator=g, device=dev) < 1 / 8).float().expand(B, 1, T, Y, X).contiguous()
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DLSG_SAMPLED_LINES", mode)
+        A = SenseModel(maps, weights=mask)
+        first = [A(x), A(k, adjoint=True), A.normal(x), A.dc_step(x, aty, -2.0)]
+        for _ in range(12):
+            again = [A(x), A(k, adjoint=True), A.normal(x), A.dc_step(x, aty, -2.0)]
+            for a, b in zip(first, again):
+                assert torch.equal(a, b), mode
+
+
 def test_workspace_chunking_does_not_change_results(dev, monkeypatch):
     B, E, C, T, Y, X = 3, 2, 4, 5, 64, 96
     maps, x, mask = so.synthetic_problem(B, E, C, T, Y, X, seed=3)

@@ -194,3 +194,16 @@ def test_mlp_kernels_at_cine_size_and_ragged_tiles(dev):
         blk.mlp.fc1.weight.mul_(0.5)                       # in-place update bumps the version: the fp16 copies are refreshed
         x = torch.randn(1, 2, 8, 8, 160, device=dev)
         assert rel_l2(blk.forward_part2(x).cpu().numpy(), blk.mlp(blk.norm2(x)).cpu().numpy()) < TOL
+
+
+def test_block_launches_are_bit_identical(dev):
+    """The five launches of the block (tcgen05 GEMMs with cp.async rings, attention core) are deterministic: 10 repeats, same bits."""
+    from dl_swin_gan_b200.swin import window_attention as wa
+    torch.manual_seed(5)
+    blk = wa.SwinTransformerBlock3D(160, 8, (7, 8, 8), (3, 4, 4), qkv_bias=True).to(dev).eval()
+    x = torch.randn(2, 7, 48, 40, 160, device=dev)
+    mask = wa.compute_mask(7, 48, 40, (7, 8, 8), (0, 4, 4), dev)
+    with torch.no_grad():
+        first = blk(x, mask)
+        for _ in range(10):
+            assert torch.equal(blk(x, mask), first)
