@@ -1,5 +1,6 @@
 // C-ABI entry points of the shifted-window attention path (declared in include/dlsg_b200.h).
 #include "../../include/dlsg_b200.h"
+#include <cstdlib>
 #include "swin_kernels.cuh"
 #include "swin_linear_tc.cuh"
 #include "swin_mlp_tc.cuh"
@@ -217,7 +218,7 @@ int dlsg_swin_mlp_f32(const float* x, const float* gamma, const float* beta, flo
     if (!x || !gamma || !beta || !w1_f16 || !w2_f16 || !hidden_f16 || !y) return DLSG_EINVAL;
     if (M > 0x7fffffffLL || C % 32 != 0 || C > 256 || H % C != 0) return DLSG_EUNSUPPORTED;
     const size_t smem = dlsg::mlp_smem_bytes(C, H);
-    if (smem > 113 * 1024 || dlsg::mlp_fc2_smem_bytes(C) > 227 * 1024) return DLSG_EUNSUPPORTED;   // fc1: two CTAs per SM; fc2: one
+    if (smem > 113 * 1024 || dlsg::mlp_fc2_smem_bytes(C, 2) > 227 * 1024) return DLSG_EUNSUPPORTED;   // fc1: two CTAs per SM; fc2: one
     dlsg::MlpParams p{};
     p.x = x; p.gamma = gamma; p.beta = beta; p.eps = eps;
     p.w1h = static_cast<const half_t*>(w1_f16); p.b1 = b1;
@@ -231,8 +232,15 @@ int dlsg_swin_mlp_f32(const float* x, const float* gamma, const float* beta, flo
     const int ntiles = (p.M + dlsg::kLinTileM - 1) / dlsg::kLinTileM;
     const unsigned grid = (unsigned)(ntiles < 2 * sms ? ntiles : 2 * sms);
     if (dlsg::launch(dlsg::swin_mlp_fc1_kernel, dim3(grid), dim3(dlsg::kLinThreads), smem, (dlsg::stream_t)stream, p) != 0) return DLSG_ELAUNCH;
+    // measured (8 cine slices): two CTAs per SM covering each other's staging 0.188 ms, one CTA per SM with the two-stage ring 0.209 ms
+    static const int fc2_stages = (getenv("DLSG_MLP_FC2_STAGES") && atoi(getenv("DLSG_MLP_FC2_STAGES")) == 2) ? 2 : 1;   // tuning switch
+    if (fc2_stages == 1) {
+        if (dlsg::launch(dlsg::swin_mlp_fc2_kernel<1>, dim3(grid), dim3(dlsg::kLinThreads), dlsg::mlp_fc2_smem_bytes(C, 1), (dlsg::stream_t)stream, p) != 0)
+            return DLSG_ELAUNCH;
+        return DLSG_OK;
+    }
     const unsigned grid2 = (unsigned)(ntiles < sms ? ntiles : sms);
-    if (dlsg::launch(dlsg::swin_mlp_fc2_kernel, dim3(grid2), dim3(dlsg::kLinThreads), dlsg::mlp_fc2_smem_bytes(C), (dlsg::stream_t)stream, p) != 0)
+    if (dlsg::launch(dlsg::swin_mlp_fc2_kernel<2>, dim3(grid2), dim3(dlsg::kLinThreads), dlsg::mlp_fc2_smem_bytes(C, 2), (dlsg::stream_t)stream, p) != 0)
         return DLSG_ELAUNCH;
     return DLSG_OK;
 #else

@@ -206,20 +206,21 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_mlp_fc1_kernel(MlpParams 
     }
 }
 
-inline size_t mlp_fc2_smem_bytes(int C) {
-    return 2 * (linear_a_region_bytes(C) + (size_t)C * C * 2) + (size_t)C * 4 + 64;
+inline size_t mlp_fc2_smem_bytes(int C, int stages) {
+    return (size_t)stages * (linear_a_region_bytes(C) + (size_t)C * C * 2) + (size_t)C * 4 + 64;
 }
 
 // y = [x +] hidden W2^T + b2.  One CTA per SM; the (tile, K chunk) items run through a two-stage ring: while the
 // tensor core works on one stage, the fp16 hidden rows and the W2 chunk of the next item (also the first chunk of the
 // next tile, during the epilogue) stream into the other stage with cp.async.
-__global__ void __launch_bounds__(kLinThreads, 1) swin_mlp_fc2_kernel(MlpParams p) {
+template <int STAGES>     // 2: one CTA per SM with the ring;  1: two CTAs per SM cover each other's staging instead
+__global__ void __launch_bounds__(kLinThreads, 3 - STAGES) swin_mlp_fc2_kernel(MlpParams p) {
     extern __shared__ __align__(128) unsigned char mlp_smem[];
     const int C = p.C, H = p.H;
     const size_t a_bytes = linear_a_region_bytes(C), w_bytes = (size_t)C * C * 2;
     auto stA = [&](int st) { return mlp_smem + (size_t)st * (a_bytes + w_bytes); };      // stage st: A region, then the W chunk
     auto stW = [&](int st) { return mlp_smem + (size_t)st * (a_bytes + w_bytes) + a_bytes; };
-    float* sBias = reinterpret_cast<float*>(mlp_smem + 2 * (a_bytes + w_bytes));
+    float* sBias = reinterpret_cast<float*>(mlp_smem + STAGES * (a_bytes + w_bytes));
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sBias + C);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(mbar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -247,12 +248,12 @@ __global__ void __launch_bounds__(kLinThreads, 1) swin_mlp_fc2_kernel(MlpParams 
     const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int nitems = my_tiles * nk;
     auto issue = [&](int item) {
-        const int tile = blockIdx.x + (item / nk) * gridDim.x, kc = item % nk, s = item & 1;
+        const int tile = blockIdx.x + (item / nk) * gridDim.x, kc = item % nk, s = item % STAGES;
         copy_block_async(stA(s), p.hidden + ((size_t)tile * nk + kc) * (size_t)(kLinTileM * C), kLinTileM * C * 2, tid);
         copy_block_async(stW(s), p.w2h + (size_t)kc * C * C, C * C * 2, tid);
         cp_async_commit();
     };
-    if (nitems > 0) issue(0);
+    if (STAGES == 2 && nitems > 0) issue(0);
     unsigned phase = 0;
     bool pending = false;                                      // an MMA commit that has not been waited for
     for (int i = 0; i < nitems; ++i) {
@@ -261,11 +262,12 @@ __global__ void __launch_bounds__(kLinThreads, 1) swin_mlp_fc2_kernel(MlpParams 
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             pending = false;
         }
-        if (i + 1 < nitems) { issue(i + 1); cp_async_wait_group1(); }
+        if (STAGES == 1) { issue(i); cp_async_wait_group0(); }
+        else if (i + 1 < nitems) { issue(i + 1); cp_async_wait_group1(); }
         else cp_async_wait_group0();
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncthreads();                                       // item i's operands are in place for every thread
-        const int s = i & 1, kc = i % nk;
+        const int s = i % STAGES, kc = i % nk;
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             for (int ks = 0; ks < C / 16; ++ks)

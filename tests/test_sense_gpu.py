@@ -247,8 +247,9 @@ def test_full_size_properties_cine_batch(dev):
     assert abs(torch.linalg.norm(F(z)) / torch.linalg.norm(z) - 1) < 1e-5
 
 
-def test_autograd_vjp_is_the_adjoint(dev):
-    B, E, C, T, Y, X = 1, 2, 3, 2, 64, 32
+@pytest.mark.parametrize("E", [1, 2])          # E = 1 with a mask: the sampled-line kernels; E = 2: the dense ones
+def test_autograd_vjp_is_the_adjoint(dev, E):
+    B, C, T, Y, X = 1, 3, 2, 64, 32
     maps, x, mask = so.synthetic_problem(B, E, C, T, Y, X, seed=5)
     A = make_model(maps, mask, dev)
     xd = torch.from_numpy(x).to(dev).requires_grad_()
@@ -273,6 +274,7 @@ def test_autograd_vjp_is_the_adjoint(dev):
     want = torch.autograd.grad(ref, (x2, aty2, step2), grad_outputs=go)
     for a, b in zip(got, want):
         assert rel_l2(to_np(a), to_np(b)) < 1e-5
+    assert (A._line_plans.get((B, E, C, T, Y, X)) is not None) == (E == 1)
 
 
 def test_fft_module_matches_reference_vectors(dev):
