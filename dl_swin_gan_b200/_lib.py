@@ -53,6 +53,7 @@ SIGNATURES = {
     "dlsg_swin_window_attention_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "dlsg_swin_qkv_fused_f32": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _i, _f, _vp]),
     "dlsg_swin_mlp_f32": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_longlong, _i, _i, _i, _vp]),
+    "dlsg_swin_qkv_stream_f32": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _i, _f, _vp]),
     "dlsg_swin_proj_scatter_residual_f32": (_i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _vp]),
     "dlsg_swin_proj_scatter_f32": (_i, [_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _vp]),
 }

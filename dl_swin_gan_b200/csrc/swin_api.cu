@@ -185,6 +185,42 @@ int dlsg_swin_qkv_fused_f32(const float* x, const float* gamma, const float* bet
 #endif
 }
 
+int dlsg_swin_qkv_stream_f32(const float* x, const float* gamma, const float* beta, float eps,
+                             const void* wqkv_f16, const float* bias, void* q16, void* k16, void* v16,
+                             int B, int D, int H, int W, int C, const int* window, const int* shift,
+                             int heads, float scale, void* stream) {
+#if defined(__CUDACC__)
+    dlsg::MlpParams p{};
+    int st = dlsg::make_geom(p.g, B, D, H, W, C, window, shift);
+    if (st != DLSG_OK) return st;
+    if (heads <= 0 || C % heads != 0 || !x || !gamma || !beta || !wqkv_f16 || !q16 || !k16 || !v16) return DLSG_EINVAL;
+    const int hd = C / heads, ntok = window[0] * window[1] * window[2];
+    if (hd > 32 || hd % 4 != 0 || ntok % 8 != 0 || C % 32 != 0 || C > 256) return DLSG_EUNSUPPORTED;
+    const long long M = dlsg::geom_tokens(p.g);
+    if (M <= 0) return DLSG_EINVAL;
+    if (M > 0x7fffffffLL) return DLSG_EUNSUPPORTED;
+    const size_t smem = dlsg::mlp_smem_bytes(C, 3 * C);
+    if (smem > 113 * 1024) return DLSG_EUNSUPPORTED;
+    p.x = x; p.gamma = gamma; p.beta = beta; p.eps = eps;
+    p.w1h = static_cast<const half_t*>(wqkv_f16); p.b1 = bias;
+    p.M = (int)M; p.C = C; p.H = 3 * C;
+    p.q16 = static_cast<half_t*>(q16); p.k16 = static_cast<half_t*>(k16); p.vt16 = static_cast<half_t*>(v16);
+    p.heads = heads; p.hd = hd; p.ntok = ntok; p.qscale = scale * dlsg::kLog2e;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < C) p.tmem_cols *= 2;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = (p.M + dlsg::kLinTileM - 1) / dlsg::kLinTileM;
+    const unsigned grid = (unsigned)(ntiles < 2 * sms ? ntiles : 2 * sms);
+    return dlsg::launch(dlsg::swin_ln_gemm_stream_kernel<true>, dim3(grid), dim3(dlsg::kLinThreads), smem, (dlsg::stream_t)stream, p) == 0
+               ? DLSG_OK : DLSG_ELAUNCH;
+#else
+    (void)x; (void)gamma; (void)beta; (void)eps; (void)wqkv_f16; (void)bias; (void)q16; (void)k16; (void)v16;
+    (void)B; (void)D; (void)H; (void)W; (void)C; (void)window; (void)shift; (void)heads; (void)scale; (void)stream;
+    return DLSG_EUNSUPPORTED;
+#endif
+}
+
 int dlsg_swin_proj_scatter_residual_f32(const float* attn_out, const float* weight, const float* bias, const float* residual,
                                         float* y, int B, int D, int H, int W, int C, const int* window, const int* shift, void* stream) {
 #if defined(__CUDACC__)
@@ -231,7 +267,7 @@ int dlsg_swin_mlp_f32(const float* x, const float* gamma, const float* beta, flo
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = (p.M + dlsg::kLinTileM - 1) / dlsg::kLinTileM;
     const unsigned grid = (unsigned)(ntiles < 2 * sms ? ntiles : 2 * sms);
-    if (dlsg::launch(dlsg::swin_mlp_fc1_kernel, dim3(grid), dim3(dlsg::kLinThreads), smem, (dlsg::stream_t)stream, p) != 0) return DLSG_ELAUNCH;
+    if (dlsg::launch(dlsg::swin_ln_gemm_stream_kernel<false>, dim3(grid), dim3(dlsg::kLinThreads), smem, (dlsg::stream_t)stream, p) != 0) return DLSG_ELAUNCH;
     // measured (8 cine slices): two CTAs per SM covering each other's staging 0.188 ms, one CTA per SM with the two-stage ring 0.209 ms
     static const int fc2_stages = (getenv("DLSG_MLP_FC2_STAGES") && atoi(getenv("DLSG_MLP_FC2_STAGES")) == 2) ? 2 : 1;   // tuning switch
     if (fc2_stages == 1) {

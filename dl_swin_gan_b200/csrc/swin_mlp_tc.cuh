@@ -2,7 +2,7 @@
 // Mlp :20-38 and norm2 :208):      out = [x +] fc2( GELU( fc1( LayerNorm(x) ) ) )
 // on the 5th-generation tensor cores (fp16 operands, fp32 accumulation in TMEM), as two kernels:
 //
-//   swin_mlp_fc1_kernel   per 128-token tile: LayerNorm(x) -> fp16 A tile (once); the hidden layer is produced in
+//   swin_ln_gemm_stream_kernel<false> (fc1)   per 128-token tile: LayerNorm(x) -> fp16 A tile (once); the hidden layer is produced in
 //                         chunks of 160 columns: the chunk of W1 (fp16, [H, C] row-major) streams in with cp.async
 //                         while the previous chunk's epilogue (bias, exact erf GELU, fp16 store) runs
 //   swin_mlp_fc2_kernel   per tile: K = H is walked in chunks of 160: fp16 hidden rows and the W2 chunk ([C, H] row-major)
@@ -33,6 +33,12 @@ struct MlpParams {
     int M, C, H;
     int residual;          // 1: y = x + mlp(LN(x))  (the block's `x + forward_part2(x)`, :271);  0: y = mlp(LN(x))
     int tmem_cols;
+    // QKV mode of the streamed LN-GEMM (H = 3C; chunk 0 / 1 / 2 = q / k / v): rows are window tokens of this geometry, gathered from
+    // the feature volume x [B,D,H,W,C] through the cyclic shift (padded tokens are zero rows); outputs as in swin_linear_tc.cuh E_QKV16
+    SwinGeom g;
+    half_t* q16; half_t* k16; half_t* vt16;
+    int heads, hd, ntok;
+    float qscale;
 };
 
 // canonical layout helpers: element (row, k) of a [rows x K] K-major operand, in bytes
@@ -80,9 +86,14 @@ __device__ __forceinline__ void copy_block_async(unsigned char* dst, const void*
     for (int i = tid * 16; i < nbytes; i += kLinThreads * 16) cp_async16(dst + i, s8 + i);
 }
 
-// hidden = GELU(LN(x) W1^T + b1)
-__global__ void __launch_bounds__(kLinThreads, 2) swin_mlp_fc1_kernel(MlpParams p) {
-    constexpr int PHASE = 1;
+// Streamed LayerNorm-GEMM:  out chunk nc = epilogue( LN(rows of x) W[nc]^T + bias[nc] ),  nc < H / C.
+//   QKV = false (fc1):  rows are the tokens in order; epilogue = exact GELU -> fp16 hidden in fc2's tile order
+//   QKV = true        :  rows are window tokens gathered through the shift (norm1 + pad + roll + window_partition, :218-236);
+//                        chunks are q, k, v; epilogue writes the attention core's fp16 [B_,heads,N,32] rows (q pre-scaled, ones column in v)
+// The LayerNorm'ed fp16 A tile is built once per 128 rows; each weight chunk streams in by cp.async while the previous chunk's
+// epilogue runs; two CTAs per SM.
+template <bool QKV>
+__global__ void __launch_bounds__(kLinThreads, 2) swin_ln_gemm_stream_kernel(MlpParams p) {
     extern __shared__ __align__(128) unsigned char mlp_smem[];
     const int C = p.C, H = p.H, KC = C / 8;
     unsigned char* sA = mlp_smem;
@@ -102,9 +113,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_mlp_fc1_kernel(MlpParams 
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(smem_u32(mbar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    const int nb = (PHASE == 1) ? H : C;
-    const float* bsrc = (PHASE == 1) ? p.b1 : p.b2;
-    for (int i = tid; i < nb; i += kLinThreads) sBias[i] = bsrc ? __ldg(bsrc + i) : 0.f;
+    for (int i = tid; i < H; i += kLinThreads) sBias[i] = p.b1 ? __ldg(p.b1 + i) : 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -113,73 +122,112 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_mlp_fc1_kernel(MlpParams 
     const int quarter = warp & 3, wsub = warp >> 2;            // warps q and q+4 share TMEM lanes 32q .. 32q+31
     const unsigned tlane = tmem_base + ((unsigned)(quarter * 32) << 16);
     const int nchunks = H / C;
+    const int ntok = QKV ? swin_tokens(p.g) : 1, nwin = QKV ? swin_windows(p.g) : 1;
 
     const int ntiles = (p.M + kLinTileM - 1) / kLinTileM;
     unsigned phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int row0 = tile * kLinTileM;
         const int nrows = min(kLinTileM, p.M - row0);
-        if (PHASE == 1) {
-            // ---- A tile = LayerNorm(x rows), two threads per row (each one half of C), one pass with shifted sums
-            copy_block_async(sW, p.w1h, C * C * 2, tid);                           // first W1 chunk (output rows 0 .. C-1)
-            cp_async_commit();
-            const int trow = tid & (kLinTileM - 1), khalf = tid >> 7;
-            const int kc0 = khalf * (KC / 2), kc1 = khalf ? KC : KC / 2;
-            const float* xr = (trow < nrows) ? p.x + (size_t)(row0 + trow) * C : nullptr;
-            float s1 = 0.f, s2 = 0.f, x0 = 0.f;
-            if (xr) {
-                x0 = __ldg(xr);
-#pragma unroll 5
-                for (int kc = kc0; kc < kc1; ++kc) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc + 4));
-                    const float d0 = a.x - x0, d1 = a.y - x0, d2 = a.z - x0, d3 = a.w - x0;
-                    const float d4 = b.x - x0, d5 = b.y - x0, d6 = b.z - x0, d7 = b.w - x0;
-                    s1 += ((d0 + d1) + (d2 + d3)) + ((d4 + d5) + (d6 + d7));
-                    s2 += ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
-                }
+        // ---- A tile = LayerNorm(x rows), two threads per row (each one half of C), one pass with shifted sums
+        copy_block_async(sW, p.w1h, C * C * 2, tid);                               // first weight chunk (output rows 0 .. C-1)
+        cp_async_commit();
+        const int trow = tid & (kLinTileM - 1), khalf = tid >> 7;
+        const int kc0 = khalf * (KC / 2), kc1 = khalf ? KC : KC / 2;
+        const float* xr = nullptr;
+        if (trow < nrows) {
+            if (QKV) {
+                const int row = row0 + trow, tok = row % ntok, bw = row / ntok;
+                const int win = bw % nwin, b = bw / nwin;
+                int d, h, w;
+                if (swin_token_coords(p.g, win, tok, d, h, w))
+                    xr = p.x + ((((size_t)b * p.g.D + d) * p.g.H + h) * p.g.W + w) * C;
+            } else {
+                xr = p.x + (size_t)(row0 + trow) * C;
             }
-            sPart[tid] = make_float2(s1, s2);
-            __syncthreads();
-            const float2 o2 = sPart[tid ^ kLinTileM];
-            s1 += o2.x; s2 += o2.y;
-            const float m0 = s1 / (float)C;
-            const float mu = x0 + m0;
-            const float rstd = 1.0f / sqrtf(fmaxf(s2 / (float)C - m0 * m0, 0.f) + p.eps);
+        }
+        float s1 = 0.f, s2 = 0.f, x0 = 0.f;
+        if (xr) {
+            x0 = __ldg(xr);
 #pragma unroll 5
             for (int kc = kc0; kc < kc1; ++kc) {
-                uint4 h = make_uint4(0u, 0u, 0u, 0u);
-                if (xr) {
-                    float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc));
-                    float4 b = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc + 4));
-                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + 8 * kc)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + 8 * kc + 4));
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + 8 * kc)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + 8 * kc + 4));
-                    a.x = fmaf((a.x - mu) * rstd, g0.x, b0.x); a.y = fmaf((a.y - mu) * rstd, g0.y, b0.y);
-                    a.z = fmaf((a.z - mu) * rstd, g0.z, b0.z); a.w = fmaf((a.w - mu) * rstd, g0.w, b0.w);
-                    b.x = fmaf((b.x - mu) * rstd, g1.x, b1.x); b.y = fmaf((b.y - mu) * rstd, g1.y, b1.y);
-                    b.z = fmaf((b.z - mu) * rstd, g1.z, b1.z); b.w = fmaf((b.w - mu) * rstd, g1.w, b1.w);
-                    h.x = pack_h2(a.x, a.y); h.y = pack_h2(a.z, a.w); h.z = pack_h2(b.x, b.y); h.w = pack_h2(b.z, b.w);
-                }
-                *reinterpret_cast<uint4*>(sA + canon_off(trow, kc, lboA)) = h;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc + 4));
+                const float d0 = a.x - x0, d1 = a.y - x0, d2 = a.z - x0, d3 = a.w - x0;
+                const float d4 = b.x - x0, d5 = b.y - x0, d6 = b.z - x0, d7 = b.w - x0;
+                s1 += ((d0 + d1) + (d2 + d3)) + ((d4 + d5) + (d6 + d7));
+                s2 += ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
             }
-            for (int nc = 0; nc < nchunks; ++nc) {
-                cp_async_wait_group0();
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                __syncthreads();                               // A tile (first chunk) and this W1 chunk are in place
-                if (tid == 0) {
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    for (int ks = 0; ks < C / 16; ++ks)
-                        umma_f16(tmem_base, umma_desc(smem_u32(sA) + (unsigned)(2 * ks) * lboA, lboA, 128u),
-                                 umma_desc(smem_u32(sW) + (unsigned)(2 * ks) * lboW, lboW, 128u), idesc, ks > 0 ? 1u : 0u);
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(mbar)) : "memory");
-                }
-                mbar_wait(mbar, phase);
+        }
+        sPart[tid] = make_float2(s1, s2);
+        __syncthreads();
+        const float2 o2 = sPart[tid ^ kLinTileM];
+        s1 += o2.x; s2 += o2.y;
+        const float m0 = s1 / (float)C;
+        const float mu = x0 + m0;
+        const float rstd = 1.0f / sqrtf(fmaxf(s2 / (float)C - m0 * m0, 0.f) + p.eps);
+#pragma unroll 5
+        for (int kc = kc0; kc < kc1; ++kc) {
+            uint4 h = make_uint4(0u, 0u, 0u, 0u);
+            if (xr) {
+                float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc));
+                float4 b = __ldg(reinterpret_cast<const float4*>(xr + 8 * kc + 4));
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + 8 * kc)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + 8 * kc + 4));
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + 8 * kc)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + 8 * kc + 4));
+                a.x = fmaf((a.x - mu) * rstd, g0.x, b0.x); a.y = fmaf((a.y - mu) * rstd, g0.y, b0.y);
+                a.z = fmaf((a.z - mu) * rstd, g0.z, b0.z); a.w = fmaf((a.w - mu) * rstd, g0.w, b0.w);
+                b.x = fmaf((b.x - mu) * rstd, g1.x, b1.x); b.y = fmaf((b.y - mu) * rstd, g1.y, b1.y);
+                b.z = fmaf((b.z - mu) * rstd, g1.z, b1.z); b.w = fmaf((b.w - mu) * rstd, g1.w, b1.w);
+                h.x = pack_h2(a.x, a.y); h.y = pack_h2(a.z, a.w); h.z = pack_h2(b.x, b.y); h.w = pack_h2(b.z, b.w);
+            }
+            *reinterpret_cast<uint4*>(sA + canon_off(trow, kc, lboA)) = h;
+        }
+        for (int nc = 0; nc < nchunks; ++nc) {
+            cp_async_wait_group0();
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            __syncthreads();                                   // A tile (first chunk) and this weight chunk are in place
+            if (tid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                if (nc + 1 < nchunks)                          // the MMA has consumed sW: the next chunk lands during the epilogue
-                    copy_block_async(sW, p.w1h + (size_t)(nc + 1) * C * C, C * C * 2, tid);
-                cp_async_commit();
-                // epilogue: thread = token row; 32 columns at a time: bias, exact GELU (nn.GELU default), fp16
-                const int erow = quarter * 32 + lane;
+                for (int ks = 0; ks < C / 16; ++ks)
+                    umma_f16(tmem_base, umma_desc(smem_u32(sA) + (unsigned)(2 * ks) * lboA, lboA, 128u),
+                             umma_desc(smem_u32(sW) + (unsigned)(2 * ks) * lboW, lboW, 128u), idesc, ks > 0 ? 1u : 0u);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(mbar)) : "memory");
+            }
+            mbar_wait(mbar, phase);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (nc + 1 < nchunks)                              // the MMA has consumed sW: the next chunk lands during the epilogue
+                copy_block_async(sW, p.w1h + (size_t)(nc + 1) * C * C, C * C * 2, tid);
+            cp_async_commit();
+            const int erow = quarter * 32 + lane;              // thread = token row of the tile
+            if (QKV) {
+                // chunk nc is q (0), k (1) or v (2): per head, hd columns -> one fp16 row of 32 (zero padded; v carries a one at index hd)
+                const bool live = erow < nrows;                // tcgen05.ld is warp-collective: only the stores are predicated
+                const int grow = row0 + erow;
+                const int tok = live ? grow % p.ntok : 0, bw = live ? grow / p.ntok : 0;
+                half_t* base16 = (nc == 0) ? p.q16 : (nc == 1 ? p.k16 : p.vt16);
+                const float sc = (nc == 0) ? p.qscale : 1.0f;
+                for (int head = wsub; head < p.heads; head += 2) {
+                    const int c0 = head * p.hd;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        if (4 * j4 < p.hd) tmem_ld4(tlane + (unsigned)(c0 + 4 * j4), v + 4 * j4);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)               // index hd of v: a one (the attention core reads the softmax row sums off the PV MMA)
+                        v[j] = (j < p.hd) ? (v[j] + sBias[nc * C + c0 + (j < p.hd ? j : 0)]) * sc : ((nc == 2 && j == p.hd) ? 1.0f : 0.f);
+                    if (live) {
+                        uint4* dst = reinterpret_cast<uint4*>(base16 + (((size_t)bw * p.heads + head) * p.ntok + tok) * 32);
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            dst[q4] = make_uint4(pack_h2(v[8 * q4], v[8 * q4 + 1]), pack_h2(v[8 * q4 + 2], v[8 * q4 + 3]),
+                                                 pack_h2(v[8 * q4 + 4], v[8 * q4 + 5]), pack_h2(v[8 * q4 + 6], v[8 * q4 + 7]));
+                    }
+                }
+            } else {
+                // 32 columns at a time: bias, exact GELU (nn.GELU default), fp16
                 for (int c0 = wsub * 32; c0 < C; c0 += 64) {
                     float v[32];
                     tmem_ld32(tlane + (unsigned)c0, v);
@@ -196,9 +244,9 @@ __global__ void __launch_bounds__(kLinThreads, 2) swin_mlp_fc1_kernel(MlpParams 
                         *reinterpret_cast<uint4*>(hb + canon_off(erow, c0 / 8 + q4, lboA)) =
                             make_uint4(hw[4 * q4], hw[4 * q4 + 1], hw[4 * q4 + 2], hw[4 * q4 + 3]);
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                __syncthreads();                               // TMEM drained before the next chunk's MMA overwrites it
             }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncthreads();                                   // TMEM drained before the next chunk's MMA overwrites it
         }
     }
     if (warp == 0) {

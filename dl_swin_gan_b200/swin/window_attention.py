@@ -392,12 +392,19 @@ class SwinTransformerBlock3D(nn.Module):
         y = torch.empty((B, D, H, W, C), dtype=torch.float32, device=dev)
         n1 = self.norm1
         opt = lambda t: t.detach().contiguous().data_ptr() if t is not None else None
+        stream_qkv = C <= 256 and n1.weight is not None and n1.bias is not None      # weight streamed in q / k / v chunks, 2 CTAs/SM
         with torch.cuda.device(dev):
-            st = lib.dlsg_swin_qkv_fused_f32(
-                x.data_ptr(), opt(n1.weight), opt(n1.bias), float(n1.eps), opt(attn.qkv.weight), opt(attn.qkv.bias),
-                q16.data_ptr(), k16.data_ptr(), vt16.data_ptr(), B, D, H, W, C, _i3(window_size), _i3(shift_size),
-                heads, float(attn.scale), _stream())
-            _lib.check(st, "dlsg_swin_qkv_fused")
+            if stream_qkv:
+                st = lib.dlsg_swin_qkv_stream_f32(
+                    x.data_ptr(), opt(n1.weight), opt(n1.bias), float(n1.eps), self._qkv_f16_weight().data_ptr(), opt(attn.qkv.bias),
+                    q16.data_ptr(), k16.data_ptr(), vt16.data_ptr(), B, D, H, W, C, _i3(window_size), _i3(shift_size),
+                    heads, float(attn.scale), _stream())
+            else:
+                st = lib.dlsg_swin_qkv_fused_f32(
+                    x.data_ptr(), opt(n1.weight), opt(n1.bias), float(n1.eps), opt(attn.qkv.weight), opt(attn.qkv.bias),
+                    q16.data_ptr(), k16.data_ptr(), vt16.data_ptr(), B, D, H, W, C, _i3(window_size), _i3(shift_size),
+                    heads, float(attn.scale), _stream())
+            _lib.check(st, "dlsg_swin_qkv")
             if rid is not None:
                 mode, mptr = MASK_REGION, rid.data_ptr()
             elif mask is not None:
@@ -417,6 +424,18 @@ class SwinTransformerBlock3D(nn.Module):
 
     def _inference(self, x) -> bool:
         return not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())))
+
+    def _qkv_f16_weight(self):
+        """qkv.weight [3C, C] as fp16 in chunked core-matrix order ([3][k/8][n/8][n%8][k%8]); refreshed when the parameter changes."""
+        w = self.attn.qkv.weight
+        key = (w.data_ptr(), w._version, w.device)
+        cache = getattr(self, "_qkv_f16", None)
+        if cache is None or cache[0] != key:
+            C = w.shape[1]
+            wt = w.detach().to(torch.float16).view(3, C // 8, 8, C // 8, 8).permute(0, 3, 1, 2, 4).contiguous()
+            cache = (key, wt)
+            self._qkv_f16 = cache
+        return cache[1]
 
     def _mlp_f16_weights(self):
         """fc1 / fc2 weights as fp16 in the kernels' chunked core-matrix order ([H/C][k/8][n/8][n%8][k%8], see

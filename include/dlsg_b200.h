@@ -201,6 +201,14 @@ int dlsg_swin_qkv_fused_f32(const float* x, const float* gamma, const float* bet
                             int B, int D, int H, int W, int C, const int* window, const int* shift,
                             int heads, float scale, void* stream);
 
+/* The same operation with the qkv weight streamed in three chunks (q, k, v) instead of held whole in shared memory, so that two
+ * CTAs share an SM: wqkv_f16 is qkv.weight [3C, C] as fp16 in the chunked core-matrix order of dlsg_swin_mlp_f32's w1_f16
+ * (wqkv_f16[nc][k/8][n/8][n%8][k%8] = weight[nc*C + n, k]), prepared once by the caller.  gamma / beta required.  C % 32 == 0, C <= 256. */
+int dlsg_swin_qkv_stream_f32(const float* x, const float* gamma, const float* beta, float eps,
+                             const void* wqkv_f16, const float* bias, void* q16, void* k16, void* v16,
+                             int B, int D, int H, int W, int C, const int* window, const int* shift,
+                             int heads, float scale, void* stream);
+
 /* proj Linear (:168) + window_reverse + reverse shift + crop (:238-248) as ONE tcgen05 GEMM: rows of attn_out [B*nW*N, C]
  * are projected and written to their place in y [B,D,H,W,C]; rows of padded tokens are dropped. */
 int dlsg_swin_proj_scatter_f32(const float* attn_out, const float* weight, const float* bias, float* y,
