@@ -175,7 +175,7 @@ def cpu_port_rate(cfg, seconds_target=12.0):
         st.dc_path(y, maps, mask, cfg["unrolls"], cfg["step"])
         n += nb
         el = time.perf_counter() - t0
-        if el > seconds_target or n >= 16:
+        if el > seconds_target or n >= 4096:
             break
     return n / el, threads, f"{n} slice(s) of the batch through A^H y + {cfg['unrolls']} DC updates, {el:.1f} s"
 
