@@ -382,11 +382,16 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
     lane_twiddles<RX, DIR>(lane, tw);
     const float* wbt = w + (b * ws.b + t * ws.t + lane * ws.x);      // weights of this lane's first column of (b, t)
 
+    // rows of a batch are consecutive (coil, line) items, line fastest: one division per batch, then an incremental walk
+    struct Walk { int c, i; };
+    auto walk_begin = [&](int it0) { Walk wk; wk.c = it0 / n; wk.i = it0 - wk.c * n; return wk; };
+    auto walk_next = [&](Walk& wk) { if (++wk.i == n) { wk.i = 0; ++wk.c; } };
+
     auto stage_batch = [&](int it0) {
         const int nrows = min(NB, items - it0);
-        for (int r = 0; r < nrows; ++r) {
-            const int item = it0 + r, c = item / n, i = item - c * n;
-            const float2* row = src + (from_k ? idx_k(d, b, c, t, __ldg(list + i)) : idx_lines(d, lp.lmax, b, c, t, i));
+        Walk wk = walk_begin(it0);
+        for (int r = 0; r < nrows; ++r, walk_next(wk)) {
+            const float2* row = src + (from_k ? idx_k(d, b, wk.c, t, __ldg(list + wk.i)) : idx_lines(d, lp.lmax, b, wk.c, t, wk.i));
 #pragma unroll
             for (int m = 0; m < (X / 2 + 31) / 32; ++m) {
                 const int q = lane + 32 * m;
@@ -395,17 +400,26 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
         }
         cp_async_commit();
     };
-    // scale * W of the lane's RX columns of every row of the batch
-    auto load_weights = [&](int it0, int nrows, float (&wv)[NB][RX]) {
+    // scale * W of the lane's RX columns of the rows [r0, r1) of the batch: all loads are issued before the first one is used
+    auto load_weights = [&](int it0, int nrows, float (&wv)[NB][RX], int r0, int r1) {
+        Walk wk = walk_begin(it0);
 #pragma unroll
         for (int r = 0; r < NB; ++r) {
             if (r < nrows) {
-                const int item = it0 + r, c = item / n, i = item - c * n;
-                const float* wr = wbt + (c * ws.c + __ldg(list + i) * ws.y);
+                if (r >= r0 && r < r1) {
+                    const float* wr = wbt + (wk.c * ws.c + __ldg(list + wk.i) * ws.y);
 #pragma unroll
-                for (int j = 0; j < RX; ++j) wv[r][j] = scale * __ldg(wr + 32 * j * ws.x);
+                    for (int j = 0; j < RX; ++j) wv[r][j] = __ldg(wr + 32 * j * ws.x);
+                }
+                walk_next(wk);
             }
         }
+#pragma unroll
+        for (int r = 0; r < NB; ++r)
+            if (r >= r0 && r < r1) {
+#pragma unroll
+                for (int j = 0; j < RX; ++j) wv[r][j] *= scale;
+            }
     };
 
     const int stride = nsplit * Cfg::WARPS * NB;
@@ -414,7 +428,7 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
     for (; it0 < items; it0 += stride) {
         const int nrows = min(NB, items - it0);
         float wv[NB][RX];
-        if (MODE == MODE_ADJ) load_weights(it0, nrows, wv);
+        if (MODE == MODE_ADJ) load_weights(it0, nrows, wv, 0, NB);
         cp_async_wait_group0();
         __syncwarp();
 #pragma unroll
@@ -438,7 +452,7 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
         if (MODE == MODE_NORMAL) {
             // way back in place: rows in reverse order, because view 1 of row r starts behind the end of view 2 of row r-1
             // (34 RX r >= 33 RX r - RX) and only overlaps rows >= r, which have been consumed
-            load_weights(it0, nrows, wv);
+            load_weights(it0, nrows, wv, 0, NB);
 #pragma unroll
             for (int rr = 0; rr < NB; ++rr) {
                 const int r = NB - 1 - rr;
@@ -456,11 +470,13 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
             __syncwarp();
             row_radix32<RX, +1>(buf, lane, nrows);
         }
-        if (MODE == MODE_FWD) load_weights(it0, nrows, wv);
+        if (MODE == MODE_FWD) load_weights(it0, nrows, wv, 0, NB);
+        Walk wo = walk_begin(it0);
 #pragma unroll
         for (int r = 0; r < NB; ++r) {
             if (r < nrows) {
-                const int item = it0 + r, c = item / n, i = item - c * n;
+                const int c = wo.c, i = wo.i;
+                walk_next(wo);
                 float2* o = dst + ((MODE == MODE_FWD) ? idx_k(d, b, c, t, __ldg(list + i)) : idx_lines(d, lp.lmax, b, c, t, i)) + lane;
                 const float2* sv = buf + r * Cfg::S2 + lane;
 #pragma unroll
