@@ -488,9 +488,13 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
 }
 
 // kl[b,c,t,i,:] = k[b,c,t,ky_i,:]: copies the sampled lines of a k-space that may live in pinned (mapped) host memory,
-// so that only those lines cross PCIe.  A few persistent CTAs walk the (c, t, b) images (the copy is PCIe-bound: a
-// small grid keeps enough 16-byte loads in flight and leaves the SMs to the kernels of other streams).
-constexpr int kGatherCtas = 48;
+// so that only those lines cross PCIe.  Persistent CTAs walk the (c, t, b) images; the copy is PCIe-bound (51 GB/s alone).
+// Grid size measured inside the pipelined end-to-end step, where it shares the SMs with the DC kernels of the previous chunk:
+// 8 / 16 / 24 / 48 / 96 / 148 / 296 CTAs -> 2560 / 3040 / 3100 / 3500 / 3885 / 3845 / 3640 slices/s.
+#ifndef DLSG_GATHER_CTAS
+#define DLSG_GATHER_CTAS 96
+#endif
+constexpr int kGatherCtas = DLSG_GATHER_CTAS;
 DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(256)
 sense_gather_lines_kernel(const float2* __restrict__ k, float2* __restrict__ kl, LinePlan lp, SenseDims d) {
     const long long units = (long long)d.B * d.t_count * d.C;

@@ -304,6 +304,9 @@ class SenseModel(nn.Module):
         if dims[1] != 1 and not any_emaps and os.environ.get("DLSG_SAMPLED_LINES") != "force":
             return None
         key = tuple(dims)
+        stamp = (self._w32.data_ptr(), self._w32._version)             # weights modified in place: rebuild the plan
+        if self._line_plans.get("stamp") != stamp:
+            self._line_plans = {"stamp": stamp}
         if key not in self._line_plans:
             lib = _lib.load()
             B, E, C, T, Y, X = dims

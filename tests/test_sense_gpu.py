@@ -142,6 +142,16 @@ def test_sampled_line_path_is_selected_and_agrees_with_dense(dev, monkeypatch):
         assert (A._line_plans.get((B, E, C, T, Y, X)) is not None) == (mode == "1")
     for a, b in zip(res["1"], res["0"]):
         assert rel_l2(to_np(a), to_np(b)) < 2e-6
+    # weights edited in place after first use: the plan follows (the tensor's version counter is part of the cache key)
+    monkeypatch.setenv("DLSG_SAMPLED_LINES", "1")
+    wmut = mask.clone()
+    A = SenseModel(maps, weights=wmut)
+    before = A(x)
+    wmut[:, :, :, 7, X // 2:] = 1.0                                        # a line that was (almost surely) empty becomes sampled
+    after = A(x)
+    monkeypatch.setenv("DLSG_SAMPLED_LINES", "0")
+    assert rel_l2(to_np(after), to_np(SenseModel(maps, weights=wmut)(x))) < 2e-6
+    assert after[:, :, :, 7, X // 2:].abs().sum() > 0 and not torch.equal(before, after)
     monkeypatch.setenv("DLSG_SAMPLED_LINES", "1")
     dense = (torch.rand(B, 1, T, Y, 1, generator=g, device=dev) < 0.7).float().expand(B, 1, T, Y, X).contiguous()
     A = SenseModel(maps, weights=dense)
