@@ -357,8 +357,11 @@ struct RowLinesCfg {
     static constexpr size_t SMEM = (size_t)RowCfg<RX>::WARPS * PER_WARP * sizeof(float2);
 };
 
+#ifndef DLSG_LINES_ROWS_NORMAL_MINB
+#define DLSG_LINES_ROWS_NORMAL_MINB 2       // the normal-operator variant spills at the 168-register cap of 3 CTAs/SM: 2 CTAs (216 registers) measured 14 % faster
+#endif
 template <int RX, int MODE>
-DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(128, DLSG_LINES_ROWS_MINB)
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(128, (MODE == MODE_NORMAL ? DLSG_LINES_ROWS_NORMAL_MINB : DLSG_LINES_ROWS_MINB))
 sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict__ w, WeightStrides ws, float scale,
                         LinePlan lp, SenseDims d, int src_lines, int nsplit) {
     using Cfg = RowCfg<RX>;
