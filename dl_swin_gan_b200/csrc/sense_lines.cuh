@@ -498,6 +498,10 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
 #define DLSG_GATHER_CTAS 96
 #endif
 constexpr int kGatherCtas = DLSG_GATHER_CTAS;
+#ifndef DLSG_GATHER_ILP
+#define DLSG_GATHER_ILP 4
+#endif
+constexpr int kGatherIlp = DLSG_GATHER_ILP;    // 16-byte loads in flight per thread
 DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(256)
 sense_gather_lines_kernel(const float2* __restrict__ k, float2* __restrict__ kl, LinePlan lp, SenseDims d) {
     const long long units = (long long)d.B * d.t_count * d.C;
@@ -513,10 +517,10 @@ sense_gather_lines_kernel(const float2* __restrict__ k, float2* __restrict__ kl,
         const float4* src = reinterpret_cast<const float4*>(k + idx_k(d, b, c, t, 0));
         float4* dst = reinterpret_cast<float4*>(kl + idx_lines(d, lp.lmax, b, c, t, 0));
         const int per_row = d.X / 2, total = n * per_row;
-        for (int q0 = threadIdx.x; q0 < total; q0 += 4 * blockDim.x) {
-            float4 v[4];
+        for (int q0 = threadIdx.x; q0 < total; q0 += kGatherIlp * blockDim.x) {
+            float4 v[kGatherIlp];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < kGatherIlp; ++m) {
                 const int q = q0 + m * blockDim.x;
                 if (q < total) {
                     const int i = q / per_row, ch = q - i * per_row;
@@ -524,7 +528,7 @@ sense_gather_lines_kernel(const float2* __restrict__ k, float2* __restrict__ kl,
                 }
             }
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < kGatherIlp; ++m) {
                 const int q = q0 + m * blockDim.x;
                 if (q < total) dst[q] = v[m];
             }
