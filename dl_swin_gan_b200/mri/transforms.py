@@ -308,6 +308,10 @@ class SenseModel(nn.Module):
         if self._line_plans.get("stamp") != stamp:
             self._line_plans = {"stamp": stamp}
         if key not in self._line_plans:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError(
+                    "SenseModel builds its sampled-line plan on first use (one scalar read-back), which is not allowed while a CUDA "
+                    "graph is being captured: call the operator once before the capture")
             lib = _lib.load()
             B, E, C, T, Y, X = dims
             plan = None
