@@ -59,13 +59,14 @@ sense_line_plan_kernel(const float* __restrict__ w, WeightStrides ws, int C, int
     for (int y = threadIdx.x; y < Y; y += blockDim.x) flag[y] = 0;
     __syncthreads();
     const int nc = ws.c ? C : 1, nx = ws.x ? X : 1, ny = ws.y ? Y : 1;   // broadcast axes are visited once
-    const long long total = (long long)nc * ny * nx;
     const float* base = w + (b * ws.b + t * ws.t);
-    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-        const int x = (int)(i % nx);
-        const long long r = i / nx;
-        const int y = (int)(r % ny), c = (int)(r / ny);
-        if (__ldg(base + (c * ws.c + y * ws.y + x * ws.x)) != 0.f) flag[y] = 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int row = warp; row < nc * ny; row += nwarps) {                  // one (coil, line) row per warp, lanes along kx
+        const int c = row / ny, y = row - c * ny;
+        const float* wr = base + (c * ws.c + y * ws.y);
+        bool nz = false;
+        for (int x = lane; x < nx; x += 32) nz |= (__ldg(wr + x * ws.x) != 0.f);
+        if (nz) flag[y] = 1;                                              // same value from every writer
     }
     __syncthreads();
     if (threadIdx.x == 0) {
