@@ -309,7 +309,7 @@ def main():
         step()
     barrier()
     # a fresh process / box needs more than three short steps to reach steady clocks and page everything in: keep warming up
-    # (untimed) until 0.5 s have passed; the JSON line reports the warm-up steps actually run
+    # (untimed) until 0.5 s have passed; config.warmup_extra_steps reports how many steps that added to the W requested
     clocks = ClockSampler(local_rank)
     # The timed steps are replays of ONE CUDA graph captured from the same public-API calls: a host-side hiccup (GC, CPU
     # throttling of the container; seen as 10-50 ms gaps in eager launches on this pool, tools/stability_probe.py) then cannot
@@ -333,11 +333,12 @@ def main():
             nonlocal out
             out = step()
     out = out if use_graph else step()
+    extra_warmup = 0
     t_w = time.perf_counter()
     while time.perf_counter() - t_w < 0.5:
         run_step()
         torch.cuda.synchronize(dev)
-        args.warmup += 1
+        extra_warmup += 1
     barrier()
     n0 = lib.dlsg_launch_count()
     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -486,7 +487,8 @@ def main():
                        "workspace_MB": float(os.environ.get("DLSG_WORKSPACE_MB", 4096)),
                        "kernel_path": path, "sampled_ky_lines_max": (plan[1] if plan is not None else Y),
                        "launch": ("one CUDA graph of the step (captured from the public API calls), replayed K times" if use_graph
-                                  else "eager launches")},
+                                  else "eager launches"),
+                       "warmup_extra_steps": extra_warmup},
             "roofline": roofline, "ops": ops, "ops_dense_kernels": ops_dense, "swin_window_attention": swin, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks.summary(),
         }
