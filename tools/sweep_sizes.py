@@ -16,7 +16,7 @@ def cn(*s):
     return torch.view_as_complex(torch.randn(*s, 2, generator=g, device=dev))
 
 
-E = 2
+E = int(os.environ.get("SWEEP_E", 2))
 for (Y, X) in [(128, 128), (160, 160), (192, 160), (192, 192), (256, 256), (320, 320)]:
     for C in (8, 16, 32):
         for T in (10, 20, 40, 60):
