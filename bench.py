@@ -123,17 +123,12 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- synthetic data
 def make_mask(B, T, Y, X, accel, seed):
-    """0/1 k-t mask [B,1,T,Y,X]: every accel-th ky line shifted per frame, centre lines, first quarter of kx empty."""
-    rng = np.random.default_rng(seed)
-    mask = np.zeros((B, 1, T, Y, X), dtype=np.float32)
-    for b in range(B):
-        off = int(rng.integers(0, accel))
-        for t in range(T):
-            rows = (np.arange(Y) + 5 * t + off) % accel == 0
-            centre = np.abs(np.arange(Y) - Y // 2) < max(1, Y // 32)
-            mask[b, 0, t, np.roll(rows | centre, -(Y // 2)), :] = 1.0
-    mask[..., : X // 4] = 0.0
-    return mask
+    """0/1 k-t masks [B,1,T,Y,X] from the reference's generator (VDktMaskFunc, dl_cs/mri/subsample.py:65-117, mirrored
+    bit-exactly in dl_swin_gan_b200/mri/subsample.py): variable-density ky-t pattern at R = accel, golden-ratio shift per
+    phase, partial readout and partial phase encoding 0.25; slice b uses seed + b."""
+    from dl_swin_gan_b200.mri.subsample import VDktMaskFunc
+    f = VDktMaskFunc((accel, accel), sim_partial_kx=0.25, sim_partial_ky=0.25)
+    return np.concatenate([f((1, 1, T, Y, X), seed=seed + b).numpy() for b in range(B)], axis=0)
 
 
 def device_problem(cfg, dev, seed):

@@ -24,6 +24,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(gmem_src) : "memory");
 }
+// 8-byte variant (one complex64), through L1: used for thread-private staging slots
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(sa), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
 }
@@ -208,6 +213,7 @@ static inline void mma_m16n8k16_f16(float* c, const unsigned* a, unsigned b0, un
 
 
 static inline void cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
+static inline void cp_async8(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 8); }
 static inline void cp_async_wait_all() {}
 static inline void cp_async_commit() {}
 static inline void cp_async_wait_group0() {}

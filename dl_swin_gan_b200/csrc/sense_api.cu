@@ -4,8 +4,11 @@
 #include "../../include/dlsg_b200.h"
 #include "sense_kernels.cuh"
 #include "sense_lines.cuh"
+#include "sense_lines_p.cuh"
 
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 namespace dlsg {
 namespace {
@@ -310,7 +313,14 @@ int launch_cols_fwd_lines(const float2* x, const float2* maps, float2* tl, const
 #endif
     return launch(sense_cols_fwd_lines_kernel<RY, false>, dim3(grid), dim3(Cfg::NT), Cfg::smem_fwd(0), s, x, maps, tl, lp, d);
 }
+bool pcols_supported(int E, int Y, int X, int lmax);
+inline bool pcols_disabled();
+int pcols_fwd(const float2* x, const float2* maps, float2* tl, const LinePlan& lp, const SenseDims& d, stream_t s);
+int pcols_adj(const float2* tl, const float2* maps, float2* out, const float2* xin, const float2* aty,
+              float step, const float* step_dev, int epi, const LinePlan& lp, const SenseDims& d, stream_t s);
+
 int cols_fwd_lines(const float2* x, const float2* maps, float2* tl, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    if (!pcols_disabled() && pcols_supported(d.E, d.Y, d.X, lp.lmax)) return pcols_fwd(x, maps, tl, lp, d, s);
     DLSG_RADIX_SWITCH(radix_of(d.Y), (launch_cols_fwd_lines<R>(x, maps, tl, lp, d, s)))
 }
 
@@ -324,6 +334,8 @@ int launch_cols_adj_lines(const float2* tl, const float2* maps, float2* out, con
 }
 int cols_adj_lines(const float2* tl, const float2* maps, float2* out, const float2* xin, const float2* aty,
                    float step, const float* step_dev, int epi, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    if (!pcols_disabled() && pcols_supported(d.E, d.Y, d.X, lp.lmax))
+        return pcols_adj(tl, maps, out, xin, aty, step, step_dev, epi, lp, d, s);
     DLSG_RADIX_SWITCH(radix_of(d.Y), (launch_cols_adj_lines<R>(tl, maps, out, xin, aty, step, step_dev, epi, lp, d, s)))
 }
 size_t cols_adj_lines_smem(int E, int Y, int lmax) {     // ColLinesCfg<RY>::smem_adj without the template argument
@@ -351,9 +363,68 @@ int rows_lines(const float2* src, float2* dst, const float* w, const WeightStrid
     DLSG_RADIX_SWITCH(radix_of(d.X), (launch_rows_lines<R, MODE>(src, dst, w, ws, scale, lp, d, s, src_lines)))
 }
 
+// ---- second-generation column kernels (sense_lines_p.cuh): Y = 16 * R2, E <= 2
+inline int pradix_of(int y) {      // R2 if y == 16*R2 with a compiled R2, else 0
+    if (y % 16) return 0;
+    const int r = y / 16;
+#ifdef DLSG_FAST_BUILD
+    return (r == 10 || r == 12) ? r : 0;
+#else
+    switch (r) { case 8: case 10: case 12: case 16: case 20: return r; default: return 0; }
+#endif
+}
+#define DLSG_PRADIX_CASE(n, EXPR) case n: { constexpr int R2 = n; return EXPR; }
+#ifdef DLSG_FAST_BUILD
+#define DLSG_PRADIX_SWITCH(r, EXPR) switch (r) { DLSG_PRADIX_CASE(10, EXPR) DLSG_PRADIX_CASE(12, EXPR) default: return -1; }
+#else
+#define DLSG_PRADIX_SWITCH(r, EXPR) switch (r) { DLSG_PRADIX_CASE(8, EXPR) DLSG_PRADIX_CASE(10, EXPR) DLSG_PRADIX_CASE(12, EXPR) \
+                                                  DLSG_PRADIX_CASE(16, EXPR) DLSG_PRADIX_CASE(20, EXPR) default: return -1; }
+#endif
+
+// DLSG_LINES_KERNELS=v1 keeps the first-generation column kernels (A/B measurements, tests of both families)
+inline bool pcols_disabled() {
+    const char* v = std::getenv("DLSG_LINES_KERNELS");
+    return v && std::strcmp(v, "v1") == 0;
+}
+bool pcols_supported(int E, int Y, int X, int lmax) {
+    if (E < 1 || E > 2 || !pradix_of(Y) || X % 16) return false;
+    const int r2 = Y / 16;
+    const size_t adj = (size_t)(E + 2) * 16 * 16 * r2 * sizeof(float2) + (size_t)2 * lmax * 16 * sizeof(float2)
+                       + (size_t)lmax * (2 * sizeof(float4) + sizeof(int)) + 51 * sizeof(int);
+    return adj <= kSmemMax;
+}
+
+template <int R2>
+int launch_pcols_fwd(const float2* x, const float2* maps, float2* tl, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    using Cfg = PColCfg<R2>;
+    const unsigned grid = (unsigned)((long long)(d.X / 16) * d.t_count * d.B);
+    const size_t smem = Cfg::smem_fwd(d.E, lp.lmax);
+    if (d.E == 1) return launch(sense_cols_fwd_lines_p_kernel<R2, 1>, dim3(grid), dim3(Cfg::NT), smem, s, x, maps, tl, lp, d);
+    return launch(sense_cols_fwd_lines_p_kernel<R2, 2>, dim3(grid), dim3(Cfg::NT), smem, s, x, maps, tl, lp, d);
+}
+template <int R2>
+int launch_pcols_adj(const float2* tl, const float2* maps, float2* out, const float2* xin, const float2* aty,
+                     float step, const float* step_dev, int epi, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    using Cfg = PColCfg<R2>;
+    const unsigned grid = (unsigned)((long long)(d.X / 16) * d.t_count * d.B);
+    const size_t smem = Cfg::smem_adj(d.E, lp.lmax);
+    if (d.E == 1)
+        return launch(sense_cols_adj_lines_p_kernel<R2, 1>, dim3(grid), dim3(Cfg::NT), smem, s, tl, maps, out, xin, aty, step, step_dev, epi, lp, d);
+    return launch(sense_cols_adj_lines_p_kernel<R2, 2>, dim3(grid), dim3(Cfg::NT), smem, s, tl, maps, out, xin, aty, step, step_dev, epi, lp, d);
+}
+
+int pcols_fwd(const float2* x, const float2* maps, float2* tl, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    DLSG_PRADIX_SWITCH(pradix_of(d.Y), (launch_pcols_fwd<R2>(x, maps, tl, lp, d, s)))
+}
+int pcols_adj(const float2* tl, const float2* maps, float2* out, const float2* xin, const float2* aty,
+              float step, const float* step_dev, int epi, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    DLSG_PRADIX_SWITCH(pradix_of(d.Y), (launch_pcols_adj<R2>(tl, maps, out, xin, aty, step, step_dev, epi, lp, d, s)))
+}
+
 bool lines_supported(int E, int Y, int X, int lmax) {
     if (E <= 0 || lmax <= 0 || lmax > Y) return false;
     if (!radix_of(Y) || !radix_of(X)) return false;
+    if (!pcols_disabled() && pcols_supported(E, Y, X, lmax)) return true;
     return cols_adj_lines_smem(E, Y, lmax) <= kSmemMax;
 }
 

@@ -30,6 +30,7 @@
 
 #include "cuda_compat.h"
 #include "fft_radix.cuh"
+#include "fft_packed.cuh"
 
 // Occupancy knobs (resident CTAs per SM the register allocator must allow); tuned on the B200, see DESIGN.md.
 #ifndef DLSG_ROWS_MINB
@@ -46,6 +47,14 @@
 #endif
 
 namespace dlsg {
+
+// In-register DFTs of the kernels below: the packed-pair butterflies (FFMA2 / FADD2, fft_packed.cuh) unless
+// DLSG_SCALAR_DFT selects the scalar ones of fft_radix.cuh (kept for A/B measurements).
+#ifdef DLSG_SCALAR_DFT
+template <int N, int DIR> using XDft = Dft<N, DIR>;
+#else
+template <int N, int DIR> using XDft = PDft<N, DIR>;
+#endif
 
 struct SenseDims {
     int B, E, C, T, Y, X;   // B = slices in this launch (chunk), the rest full extents
@@ -130,7 +139,7 @@ DLSG_DEVICE void row_radix32(float2* buf, int lane, int nrows) {
     }
     __syncwarp();
     if (act) {
-        Dft<32, DIR>::run(u);
+        XDft<32, DIR>::run(u);
         const int row = lane / RX, k2 = lane - row * RX;
         float2* o = buf + row * Cfg::S2 + k2;
 #pragma unroll
@@ -240,7 +249,7 @@ sense_rows_fwd_kernel(const float2* __restrict__ x, const float2* __restrict__ m
                         }
                     }
                 }
-                Dft<RX, -1>::run(v);
+                XDft<RX, -1>::run(v);
                 float2* o = buf + (r * RX) * Cfg::S1 + lane;
 #pragma unroll
                 for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmul(v[k2], tw[k2]);
@@ -391,7 +400,7 @@ sense_rows_adj_kernel(const float2* __restrict__ tmp, const float2* __restrict__
                     float2 v[RX];
 #pragma unroll
                     for (int j = 0; j < RX; ++j) v[j] = stg[r * X + lane + 32 * j];
-                    Dft<RX, +1>::run(v);
+                    XDft<RX, +1>::run(v);
                     float2* o = buf + (r * RX) * Cfg::S1 + lane;
 #pragma unroll
                     for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmul(v[k2], tw[k2]);
@@ -539,7 +548,7 @@ sense_cols_kernel(const float2* __restrict__ src, float2* __restrict__ dst,
                     if (MODE == MODE_ADJ) a = cscale(a, wreg[i * RY + j]);
                     v[j] = a;
                 }
-                Dft<RY, DIR>::run(v);
+                XDft<RY, DIR>::run(v);
 #pragma unroll
                 for (int k2 = 0; k2 < RY; ++k2) {
                     float2 q = v[k2];
@@ -556,7 +565,7 @@ sense_cols_kernel(const float2* __restrict__ src, float2* __restrict__ dst,
         float2 r[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) r[i] = slab[(grp * 32 + i) * SW + col];
-        Dft<32, DIR>::run(r);
+        XDft<32, DIR>::run(r);
         if (MODE == MODE_FWD) {
 #pragma unroll
             for (int k1 = 0; k1 < 32; ++k1) {
@@ -571,7 +580,7 @@ sense_cols_kernel(const float2* __restrict__ src, float2* __restrict__ dst,
             // exp(+2*pi*i*n2*k1'/Y), exchange, radix-RY over n2 -> y = k1' + 32*k2'.
 #pragma unroll
             for (int k1 = 0; k1 < 32; ++k1) r[k1] = cscale(r[k1], wreg[k1] * wreg[k1]);
-            Dft<32, +1>::run(r);
+            XDft<32, +1>::run(r);
             __syncthreads();                     // every phase-B read of the slab is done
 #pragma unroll
             for (int k1 = 0; k1 < 32; ++k1) {
@@ -587,7 +596,7 @@ sense_cols_kernel(const float2* __restrict__ src, float2* __restrict__ dst,
                     float2 g[RY];
 #pragma unroll
                     for (int n2 = 0; n2 < RY; ++n2) g[n2] = slab[(n2 * 32 + k1) * SW + col];
-                    Dft<RY, +1>::run(g);
+                    XDft<RY, +1>::run(g);
 #pragma unroll
                     for (int k2 = 0; k2 < RY; ++k2) outp[(k1 + 32 * k2) * Xs] = g[k2];
                 }

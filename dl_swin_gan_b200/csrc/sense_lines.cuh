@@ -172,7 +172,7 @@ DLSG_UNROLL(DLSG_LINES_FWD_ITEM_UNROLL)
                                  XS ? xs[(size_t)e * Cfg::SLAB + yy * SW + col] : __ldg(x + idx_x(d, b, e, t, yy) + kx), a);
                     v[j] = a;
                 }
-                Dft<RY, -1>::run(v);
+                XDft<RY, -1>::run(v);
 #pragma unroll
                 for (int k2 = 0; k2 < RY; ++k2)
                     work[(k2 * 32 + l) * SW + col] = (k2 == 0) ? v[0] : cmul(v[k2], twy[l * RY + k2]);
@@ -186,7 +186,7 @@ DLSG_UNROLL(DLSG_LINES_FWD_ITEM_UNROLL)
         __syncthreads();                         // the work slab is free: the next coil's maps land during the radix-32
         if (c + 1 < d.C) fetch_slab<RY>(work, maps + idx_maps(d, b, 0, c + 1, 0) + kx0, d.X, Y, tid);
         cp_async_commit();
-        Dft<32, -1>::run(r);
+        XDft<32, -1>::run(r);
         float2* outp = tl_out + idx_lines(d, lp.lmax, b, c, t, 0) + kx;
 #pragma unroll
         for (int k1 = 0; k1 < 32; ++k1) {
@@ -266,7 +266,7 @@ DLSG_UNROLL(DLSG_LINES_ADJ_ITEM_UNROLL)
                     for (int k2 = 0; k2 < RY; ++k2) work[(k2 * 32 + l) * SW + col] = make_float2(0.f, 0.f);
                     continue;
                 }
-                Dft<RY, +1>::run(v);
+                XDft<RY, +1>::run(v);
 #pragma unroll
                 for (int k2 = 0; k2 < RY; ++k2)
                     work[(k2 * 32 + l) * SW + col] = (k2 == 0) ? v[0] : cmulc(v[k2], twy[l * RY + k2]);
@@ -279,7 +279,7 @@ DLSG_UNROLL(DLSG_LINES_ADJ_ITEM_UNROLL)
         float2 r[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) r[i] = work[(grp * 32 + i) * SW + col];
-        Dft<32, +1>::run(r);
+        XDft<32, +1>::run(r);
         cp_async_wait_group1();                  // this coil's maps (committed before the lines of the next coil)
         __syncthreads();
         {
@@ -444,7 +444,7 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
                     v[j] = stg[r * X + lane + 32 * j];
                     if (MODE == MODE_ADJ) v[j] = cscale(v[j], wv[r][j]);
                 }
-                Dft<RX, DIR>::run(v);
+                XDft<RX, DIR>::run(v);
                 float2* o = buf + (r * RX) * Cfg::S1 + lane;
 #pragma unroll
                 for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmul(v[k2], tw[k2]);
@@ -465,7 +465,7 @@ sense_rows_lines_kernel(const float2* src, float2* dst, const float* __restrict_
 #pragma unroll
                     for (int j = 0; j < RX; ++j) v[j] = cscale(buf[r * Cfg::S2 + lane + 32 * j], wv[r][j] * wv[r][j]);
                     __syncwarp();                              // every lane has read row r before its view 1 is written
-                    Dft<RX, +1>::run(v);
+                    XDft<RX, +1>::run(v);
                     float2* o = buf + (r * RX) * Cfg::S1 + lane;
 #pragma unroll
                     for (int k2 = 0; k2 < RX; ++k2) o[k2 * Cfg::S1] = (k2 == 0) ? v[0] : cmulc(v[k2], tw[k2]);

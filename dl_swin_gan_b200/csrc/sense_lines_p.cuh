@@ -1,0 +1,335 @@
+// Sampled-line column passes, second generation (sm_100a): packed-pair arithmetic and pruned transforms.
+// Same operator as sense_lines.cuh (SenseModel._forward_op / _adjoint_op, dl_cs/mri/transforms.py:84-98; DC update
+// dl_cs/models/unrolledswin.py:109) and the same intermediate `tl` [B,C,T,lmax,X], so the row pass on the sampled
+// lines (sense_rows_lines_kernel) is shared.
+//
+// Why a second generation.  The first one was issue-bound (profiles/r1q_lines_ncu_summary.csv: 12 warps/SM,
+// issue-active 56 %, 1594 instructions per thread and coil for ~900 of FP32 work).  Here
+//   * every complex add / multiply / fma is one packed instruction on a register pair (FADD2 / FFMA2,
+//     fft_packed.cuh): the same FP32 pipe time in half the issue slots;
+//   * Y = 16 * R2 is split as an in-register radix-16 DFT (one thread, 16 complex registers instead of 32) and a
+//     radix-R2 stage that is only evaluated for the sampled lines ("pruned"):
+//       forward  y = R2 l + j :  Z_j[k1] = DFT16_l( img[R2 l + j] ),   tl[i] = sum_j W_Y^(j ky_i) Z_j[ky_i mod 16]
+//       adjoint                  U_j[k1] = sum_{i : ky_i mod 16 = k1} conj(W_Y^(j ky_i)) tl[i],
+//                                out[R2 l + j] = IDFT16_k1( U_j )[l]
+//     so the dense part of a column transform is R2 DFT16s and the rest is n * R2 complex fmas per column;
+//   * a CTA is a 16-column slab x R2 threads per column (192 threads for Y = 192), 3-4 CTAs per SM;
+//   * each thread's coil-sensitivity values are its own: they are staged by 8-byte cp.async into thread-private
+//     shared-memory slots one coil ahead (no CTA barrier, no registers held during the flight), x stays in registers.
+#pragma once
+
+#include "sense_lines.cuh"
+
+namespace dlsg {
+
+template <int R2>
+struct PColCfg {
+    static constexpr int R1 = 16, Y = 16 * R2, SW = 16, NT = SW * R2;
+    static constexpr size_t SLAB = (size_t)16 * NT;                              // complex elements of one [16][NT] block
+    static size_t tables(int lmax) { return (size_t)lmax * (2 * sizeof(float4) + sizeof(int)) + (17 + 16 + 2 + 16) * sizeof(int); }
+    static size_t smem_fwd(int E, int lmax) { return (size_t)(E + 2) * SLAB * sizeof(float2) + tables(lmax); }
+    static size_t smem_adj(int E, int lmax) {
+        return (size_t)(E + 2) * SLAB * sizeof(float2) + (size_t)2 * lmax * SW * sizeof(float2) + tables(lmax);
+    }
+};
+
+// block index -> (16-column slab, frame, slice)
+struct PColWho { int b, t, bt, kx0; };
+DLSG_DEVICE PColWho pcol_who(const SenseDims& d) {
+    const int ncolblk = d.X / 16;
+    long long u = blockIdx.x;
+    const int colblk = (int)(u % ncolblk); u /= ncolblk;
+    const int tl = (int)(u % d.t_count);
+    PColWho w;
+    w.b = (int)(u / d.t_count);
+    w.t = d.t_begin + tl;
+    w.bt = w.b * d.T + w.t;
+    w.kx0 = colblk * 16;
+    return w;
+}
+
+// (cos, sin) of 2 pi m / Y with the integer reduced to |angle| <= pi first
+DLSG_DEVICE float2 unit_root(int m, int Y) {
+    m %= Y;
+    if (2 * m > Y) m -= Y;
+    float sn, cs;
+    sincospif((float)(2 * m) / (float)Y, &sn, &cs);
+    return make_float2(cs, sn);
+}
+
+// ---------------------------------------------------------------------------- per-CTA line tables
+// The sampled lines of one (b, t), grouped by class k1 = ky mod 16 (the DFT16 bin they meet):
+//   seg[k1] .. seg[k1+1]  sorted positions of class k1 (ascending ky inside a class)
+//   order[q]              line index i (row of `tl`) at sorted position q
+//   wq[2q], wq[2q+1]      (c, s, -s, c) of w = exp(SIGN * 2 pi i ky / Y) and of w^2
+//   clist[0..m)           the non-empty classes, meta[0] = m, meta[1] = bit mask of the non-empty classes
+struct LineTables { float4* wq; int* order; int* seg; int* clist; int* meta; int* ccnt; };
+DLSG_DEVICE LineTables line_tables_at(void* p, int lmax) {
+    LineTables t;
+    t.wq = reinterpret_cast<float4*>(p);
+    t.order = reinterpret_cast<int*>(t.wq + 2 * lmax);
+    t.seg = t.order + lmax;
+    t.clist = t.seg + 17;
+    t.meta = t.clist + 16;
+    t.ccnt = t.meta + 2;
+    return t;
+}
+// all threads of the CTA call it; ends with a barrier
+template <int SIGN>
+DLSG_DEVICE void build_line_tables(const LineTables& lt, const int* __restrict__ list, int n, int Y, int tid, int nt) {
+    if (tid < 16) {
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) cnt += ((__ldg(list + i) & 15) == tid);
+        lt.ccnt[tid] = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0, m = 0, mask = 0;
+        for (int k = 0; k < 16; ++k) {
+            lt.seg[k] = s;
+            if (lt.ccnt[k] > 0) { lt.clist[m++] = k; mask |= 1 << k; }
+            s += lt.ccnt[k];
+        }
+        lt.seg[16] = s;
+        lt.meta[0] = m; lt.meta[1] = mask;
+    }
+    __syncthreads();
+    if (tid < 16) {
+        int q = lt.seg[tid];
+        for (int i = 0; i < n; ++i)
+            if ((__ldg(list + i) & 15) == tid) lt.order[q++] = i;
+    }
+    __syncthreads();
+    for (int q = tid; q < n; q += nt) {
+        const int ky = __ldg(list + lt.order[q]);
+        const float2 w = unit_root(ky, Y), w2 = unit_root(2 * ky, Y);      // (cos, sin)
+        const float s1 = (SIGN < 0) ? -w.y : w.y, s2 = (SIGN < 0) ? -w2.y : w2.y;
+        lt.wq[2 * q] = make_float4(w.x, s1, -s1, w.x);
+        lt.wq[2 * q + 1] = make_float4(w2.x, s2, -s2, w2.x);
+    }
+    __syncthreads();
+}
+
+// this thread's 16 map values of coil c, map set e: staged by 8-byte cp.async into slots only this thread reads
+// (no CTA barrier, no registers held while the loads are in flight)
+template <int NT, int R2, int E>
+DLSG_DEVICE void stage_maps_private(float2* mstg, const float2* mbase, int c, int C, size_t img, size_t rstride, int tid) {
+#ifdef DLSG_DEBUG_SAME_MAPS
+    c = 0;          // timing experiment only (wrong results): every coil reads coil 0, so the map traffic hits in L1/L2
+#endif
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const float2* src = mbase + ((size_t)e * C + c) * img;
+#pragma unroll
+        for (int l = 0; l < 16; ++l) cp_async8(mstg + (e * 16 + l) * NT + tid, src + l * rstride);
+    }
+}
+
+// tl[b,c,t,i,kx] = DFT_Y( sum_e maps[b,e,c,:,kx] * x[b,e,t,:,kx] )[ky_i]   for the sampled lines of (b,t).
+// Per coil: product with the thread's x values, DFT16, the bins of the non-empty classes go to shared memory (double
+// buffered: one CTA barrier per coil), then one thread per (class, column) reads the R2 bins of its class once and
+// evaluates sum_j w^j Z_j for every line of the class (w = W_Y^ky; Horner's rule on the even and the odd terms).
+template <int R2, int E>
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(16 * R2, (E == 1 ? 3 : 2))
+sense_cols_fwd_lines_p_kernel(const float2* __restrict__ x, const float2* __restrict__ maps,
+                              float2* __restrict__ tl_out, LinePlan lp, SenseDims d) {
+    using Cfg = PColCfg<R2>;
+    constexpr int NT = Cfg::NT, Y = Cfg::Y;
+    static_assert(R2 % 2 == 0, "even R2");
+    DLSG_DYN_SMEM(float2, smem);
+    float2* mstg = smem;                                         // [E][16][NT] private map slots (l, tid)
+    float2* exch = mstg + (size_t)E * Cfg::SLAB;                 // [2][16][NT] Z_j[k1] at (k1, tid = j*16 + col)
+    const LineTables lt = line_tables_at(exch + 2 * Cfg::SLAB, lp.lmax);
+    const int tid = threadIdx.x, col = tid & 15, j = tid >> 4;
+    const PColWho who = pcol_who(d);
+    const int b = who.b, t = who.t, kx = who.kx0 + col;
+    const int n = __ldg(lp.counts + who.bt);
+    if (n == 0) return;                                          // nothing sampled in this frame (uniform over the CTA)
+
+    const size_t img = (size_t)Y * d.X, rstride = (size_t)R2 * d.X;
+    const float2* mbase = maps + idx_maps(d, b, 0, 0, j) + kx;   // + (e*C + c) * img + l * R2 * X
+    stage_maps_private<NT, R2, E>(mstg, mbase, 0, d.C, img, rstride, tid);
+    cp_async_commit();
+    float2 xr[E][16];                                            // x[b,e,t, R2 l + j, kx]: the same for every coil
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+#pragma unroll
+        for (int l = 0; l < 16; ++l) xr[e][l] = __ldg(x + idx_x(d, b, e, t, j) + kx + l * rstride);
+    build_line_tables<-1>(lt, lp.list + (size_t)who.bt * Y, n, Y, tid, NT);
+    const int m = lt.meta[0], mask = lt.meta[1];
+
+#pragma unroll 1
+    for (int c = 0; c < d.C; ++c) {
+        cp_async_wait_group0();
+        float2 v[16];
+#pragma unroll
+        for (int l = 0; l < 16; ++l) {
+            v[l] = pc_mul(mstg[l * NT + tid], xr[0][l]);
+#pragma unroll
+            for (int e = 1; e < E; ++e) v[l] = pc_fma(mstg[(e * 16 + l) * NT + tid], xr[e][l], v[l]);
+        }
+        if (c + 1 < d.C) stage_maps_private<NT, R2, E>(mstg, mbase, c + 1, d.C, img, rstride, tid);   // slots already read
+        cp_async_commit();
+        PDft<16, -1>::run(v);
+        float2* ex = exch + (size_t)(c & 1) * Cfg::SLAB;        // the other buffer may still be read by slower threads
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1)
+            if ((mask >> k1) & 1) ex[k1 * NT + tid] = v[k1];
+        __syncthreads();
+        float2* outp = tl_out + idx_lines(d, lp.lmax, b, c, t, 0) + kx;
+#ifdef DLSG_DEBUG_NO_GATHER
+        if (m > 1000)   // timing experiment only (wrong results): the pruned stage is skipped
+#endif
+        for (int wi = j; wi < m; wi += R2) {                     // this thread's (class, column) items
+            const int k1 = lt.clist[wi];
+            const float2* zp = ex + k1 * NT + col;
+            float2 z[R2];
+#pragma unroll
+            for (int jj = 0; jj < R2; ++jj) z[jj] = zp[jj * 16];
+            const int qe = lt.seg[k1 + 1];
+#pragma unroll 1
+            for (int q = lt.seg[k1]; q < qe; ++q) {
+                const float4 wa = lt.wq[2 * q], wb = lt.wq[2 * q + 1];
+                const float2 w1 = make_float2(wa.x, wa.y), w2 = make_float2(wa.z, wa.w);      // w
+                const float2 v1 = make_float2(wb.x, wb.y), v2 = make_float2(wb.z, wb.w);      // w^2
+                float2 ae = z[R2 - 2], ao = z[R2 - 1];
+#pragma unroll
+                for (int jj = R2 - 4; jj >= 0; jj -= 2) {
+                    ae = pc_fma_w(v1, v2, ae, z[jj]);            // ae <- z[jj] + w^2 ae
+                    ao = pc_fma_w(v1, v2, ao, z[jj + 1]);
+                }
+                outp[(size_t)lt.order[q] * d.X] = pc_fma_w(w1, w2, ao, ae);                   // even + w * odd
+            }
+        }
+    }
+}
+
+// out_e[b,t,y,kx] = EPI( sum_c conj(maps[b,e,c,y,kx]) * IDFT_Y( scatter of tl[b,c,t,:,kx] to its ky lines )[y] )
+// Per coil: one thread per (class, column) forms U_j[k1] = sum_{lines of the class} conj(w)^j tl (powers by repeated
+// multiplication with w^2 on the even and odd terms, each line read once), the R2 values go to shared memory (double
+// buffered: one CTA barrier per coil); then every thread takes its 16 bins (zeros for the empty classes), IDFT16, and
+// accumulates conj(S) * out in registers.
+template <int R2, int E>
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(16 * R2, (E == 1 ? 3 : 2))
+sense_cols_adj_lines_p_kernel(const float2* __restrict__ tl_in, const float2* __restrict__ maps, float2* __restrict__ out,
+                              const float2* __restrict__ xin, const float2* __restrict__ aty,
+                              float step_host, const float* __restrict__ step_dev, int epi, LinePlan lp, SenseDims d) {
+    using Cfg = PColCfg<R2>;
+    constexpr int NT = Cfg::NT, Y = Cfg::Y, SW = 16;
+    DLSG_DYN_SMEM(float2, smem);
+    float2* mstg = smem;                                         // [E][16][NT] private map slots
+    float2* exch = mstg + (size_t)E * Cfg::SLAB;                 // [2][16][NT] U_j[k1] at (k1, j*16 + col)
+    float2* tbuf = exch + 2 * Cfg::SLAB;                         // [2][lmax][SW] sampled lines of a coil in sorted order
+    const LineTables lt = line_tables_at(tbuf + (size_t)2 * lp.lmax * SW, lp.lmax);
+    const int tid = threadIdx.x, col = tid & 15, j = tid >> 4;
+    const PColWho who = pcol_who(d);
+    const int b = who.b, t = who.t, kx = who.kx0 + col;
+    const int n = __ldg(lp.counts + who.bt);
+    const float step = step_dev ? __ldg(step_dev) : step_host;
+
+    const size_t img = (size_t)Y * d.X, rstride = (size_t)R2 * d.X;
+    const float2* mbase = maps + idx_maps(d, b, 0, 0, j) + kx;
+    auto fetch_lines = [&](int c) {                              // sorted position q <- line order[q]
+        const float2* src = tl_in + idx_lines(d, lp.lmax, b, c, t, 0) + who.kx0;
+        float2* dst = tbuf + (size_t)(c & 1) * lp.lmax * SW;
+        for (int u = tid; u < n * 8; u += NT) {
+            const int q = u >> 3, ch = u & 7;
+            cp_async16(dst + q * SW + 2 * ch, src + (size_t)lt.order[q] * d.X + 2 * ch);
+        }
+    };
+
+    float2 acc[E][16];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+#pragma unroll
+        for (int l = 0; l < 16; ++l) acc[e][l] = make_float2(0.f, 0.f);
+
+    int m = 0, mask = 0;
+    if (n > 0) {
+        stage_maps_private<NT, R2, E>(mstg, mbase, 0, d.C, img, rstride, tid);
+        build_line_tables<+1>(lt, lp.list + (size_t)who.bt * Y, n, Y, tid, NT);
+        m = lt.meta[0]; mask = lt.meta[1];
+        fetch_lines(0);
+        cp_async_commit();
+        cp_async_wait_group0();
+        __syncthreads();                                         // lines of coil 0 visible
+        if (d.C > 1) fetch_lines(1);
+    }
+    cp_async_commit();
+
+#pragma unroll 1
+    for (int c = 0; c < d.C && n > 0; ++c) {
+        // (1) class phase: lines of coil c (visible since the previous barrier) -> U_j[k1] in exch[c & 1]
+        const float2* tb = tbuf + (size_t)(c & 1) * lp.lmax * SW + col;
+        float2* ex = exch + (size_t)(c & 1) * Cfg::SLAB;
+        for (int wi = j; wi < m; wi += R2) {
+            const int k1 = lt.clist[wi];
+            float2 uj[R2];
+#pragma unroll
+            for (int jj = 0; jj < R2; ++jj) uj[jj] = make_float2(0.f, 0.f);
+            const int qe = lt.seg[k1 + 1];
+#pragma unroll 1
+            for (int q = lt.seg[k1]; q < qe; ++q) {
+                const float4 wa = lt.wq[2 * q], wb = lt.wq[2 * q + 1];
+                const float2 w1 = make_float2(wa.x, wa.y), w2 = make_float2(wa.z, wa.w);      // w
+                const float2 v1 = make_float2(wb.x, wb.y), v2 = make_float2(wb.z, wb.w);      // w^2
+                const float2 zero = make_float2(0.f, 0.f);
+                float2 pe = tb[q * SW];                                                       // w^0 T
+                float2 po = pc_fma_w(w1, w2, pe, zero);                                       // w^1 T
+                uj[0] = p_add(uj[0], pe);
+                uj[1] = p_add(uj[1], po);
+#pragma unroll
+                for (int jj = 2; jj < R2; jj += 2) {
+                    pe = pc_fma_w(v1, v2, pe, zero);
+                    po = pc_fma_w(v1, v2, po, zero);
+                    uj[jj] = p_add(uj[jj], pe);
+                    uj[jj + 1] = p_add(uj[jj + 1], po);
+                }
+            }
+            float2* up = ex + k1 * NT + col;
+#pragma unroll
+            for (int jj = 0; jj < R2; ++jj) up[jj * 16] = uj[jj];
+        }
+        cp_async_wait_group0();                                  // this thread's chunks of the next coil's lines and maps
+        __syncthreads();                                         // (2) bins of coil c and lines of coil c+1 visible; everyone is done with tbuf[c & 1]
+        if (c + 2 < d.C) fetch_lines(c + 2);
+        cp_async_commit();
+        float2 u[16];
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) u[k1] = ((mask >> k1) & 1) ? ex[k1 * NT + tid] : make_float2(0.f, 0.f);
+        PDft<16, +1>::run(u);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+#pragma unroll
+            for (int l = 0; l < 16; ++l) acc[e][l] = pc_fmac(mstg[(e * 16 + l) * NT + tid], u[l], acc[e][l]);
+        if (c + 1 < d.C) stage_maps_private<NT, R2, E>(mstg, mbase, c + 1, d.C, img, rstride, tid);
+        cp_async_commit();
+    }
+    // ---- epilogue: this thread owns y = R2 l + j of column kx
+    // out = a * (acc - av) + bx * xv :  PLAIN (a, bx) = (1, 0);  DC (step, 1) with av = aty;  REG (1, step)
+    const float ea = (epi == EPI_DC) ? step : 1.f;
+    const float eb = (epi == EPI_DC) ? 1.f : (epi == EPI_REG ? step : 0.f);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                            // two batches of 8 rows: all loads of a batch in flight together
+            const size_t g0 = idx_x(d, b, e, t, j) + kx + (size_t)(8 * h) * rstride;
+            float2 xv[8], av[8];
+#pragma unroll
+            for (int l = 0; l < 8; ++l) xv[l] = av[l] = make_float2(0.f, 0.f);
+            if (epi != EPI_PLAIN) {
+#pragma unroll
+                for (int l = 0; l < 8; ++l) xv[l] = __ldg(xin + g0 + l * rstride);
+            }
+            if (epi == EPI_DC) {
+#pragma unroll
+                for (int l = 0; l < 8; ++l) av[l] = __ldg(aty + g0 + l * rstride);
+            }
+#pragma unroll
+            for (int l = 0; l < 8; ++l)
+                out[g0 + l * rstride] = p_fma(p_bc(ea), p_sub(acc[e][8 * h + l], av[l]), p_mul(p_bc(eb), xv[l]));
+        }
+    }
+}
+
+}  // namespace dlsg

@@ -1,0 +1,146 @@
+"""Convolutional building blocks of the denoisers: mirror of the shared definitions in dl_cs/models/swin3D.py:16-302
+(== dl_cs/models/resnet3d.py:14-241): Normalization, Activation, Conv3d, ComplexConv3d, ConvBlock, ResBlock.
+
+These are the cuDNN part of the reconstruction (97 % of the denoiser's FLOPs): library convolutions,
+kept in PyTorch with the reference's module tree and parameter names (`layers.2.conv.weight` ...) so state dicts load.
+On the device they run channels-last-3d; TF32 for fp32 tensors is cuDNN's default (as it is for the reference on a GPU),
+`conv_dtype=torch.bfloat16` (models.set_conv_dtype) trades precision for tensor-core throughput.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+_CONV_DTYPE = None          # None: the tensor's own dtype (fp32, TF32 inside cuDNN); torch.bfloat16 / float16: autocast the convolutions
+
+
+def set_conv_dtype(dtype) -> None:
+    """Precision of the denoiser convolutions on CUDA tensors (None = fp32 storage)."""
+    global _CONV_DTYPE
+    if dtype not in (None, torch.bfloat16, torch.float16):
+        raise ValueError("conv dtype must be None, torch.bfloat16 or torch.float16")
+    _CONV_DTYPE = dtype
+
+
+def get_conv_dtype():
+    return _CONV_DTYPE
+
+
+class Normalization(nn.Module):
+    def __init__(self, in_chans, type):
+        super().__init__()
+        if type == "none":
+            self.norm = nn.Identity()
+        elif type == "instance":
+            self.norm = nn.InstanceNorm3d(in_chans, affine=False)
+        elif type == "batch":
+            self.norm = nn.BatchNorm3d(in_chans, affine=False)
+        else:
+            raise ValueError("Invalid normalization type: %s" % type)
+
+    def forward(self, input):
+        if input.is_complex():
+            return torch.complex(self.norm(input.real), self.norm(input.imag))
+        return self.norm(input)
+
+
+class Activation(nn.Module):
+    def __init__(self, type):
+        super().__init__()
+        if type == "none":
+            self.activ = nn.Identity()
+        elif type == "relu":
+            # inplace=True is part of the reference's arithmetic, not an optimisation: in `ResBlock.forward`
+            # (`self.layers(input) + input`, resnet3d.py:240) the first ConvBlock rectifies `input` itself, so the skip
+            # connection adds relu(input).  Kept bit for bit.
+            self.activ = nn.ReLU(inplace=True)
+        elif type == "leaky_relu":
+            self.activ = nn.LeakyReLU(inplace=True)
+        elif type == "sigmoid":
+            self.activ = nn.Sigmoid()
+        else:
+            raise ValueError("Invalid activation type: %s" % type)
+
+    def forward(self, input):
+        if input.is_complex():
+            return torch.complex(self.activ(input.real), self.activ(input.imag))
+        return self.activ(input)
+
+
+def _conv(conv: nn.Conv3d, x: torch.Tensor) -> torch.Tensor:
+    if x.is_cuda:
+        x = x.contiguous(memory_format=torch.channels_last_3d)
+        if _CONV_DTYPE is not None:
+            with torch.autocast("cuda", dtype=_CONV_DTYPE):
+                return conv(x).float()
+    return conv(x)
+
+
+class Conv3d(nn.Module):
+    """nn.Conv3d with 'same' zero padding (swin3D.py:120-134)."""
+
+    def __init__(self, in_chans, out_chans, kernel_size):
+        super().__init__()
+        self.conv = nn.Conv3d(in_chans, out_chans, kernel_size, padding=(kernel_size - 1) // 2)
+
+    def forward(self, input):
+        return _conv(self.conv, input)
+
+
+class ComplexConv3d(nn.Module):
+    """(X + iY) * (a + ib) = (X*a - Y*b) + i (X*b + Y*a) with two real convolutions (swin3D.py:137-168)."""
+
+    def __init__(self, in_chans, out_chans, kernel_size):
+        super().__init__()
+        padding = (kernel_size - 1) // 2
+        self.conv_r = nn.Conv3d(in_chans, out_chans, kernel_size, padding=padding)
+        self.conv_i = nn.Conv3d(in_chans, out_chans, kernel_size, padding=padding)
+
+    def forward(self, input):
+        re = _conv(self.conv_r, input.real) - _conv(self.conv_i, input.imag)
+        im = _conv(self.conv_r, input.imag) + _conv(self.conv_i, input.real)
+        return torch.complex(re, im)
+
+
+class ConvBlock(nn.Module):
+    """Pre-activation block Norm -> activation -> Conv (swin3D.py:225-273); children sit in `layers` at 0, 1, 2."""
+
+    def __init__(self, in_chans, out_chans, kernel_size, act_type="relu", norm_type="none", is_complex=False):
+        super().__init__()
+        self.in_chans, self.out_chans, self.is_complex = in_chans, out_chans, is_complex
+        self.name = "ComplexConv3D" if is_complex else "Conv3D"
+        conv = (ComplexConv3d if is_complex else Conv3d)(in_chans, out_chans, kernel_size=kernel_size)
+        self.layers = nn.Sequential(Normalization(in_chans, norm_type), Activation(act_type), conv)
+
+    def forward(self, input):
+        return self.layers(input)
+
+    def __repr__(self):
+        return f"{self.name}(in_chans={self.in_chans}, out_chans={self.out_chans})"
+
+
+class ResBlock(nn.Module):
+    """Two ConvBlocks and a residual connection (swin3D.py:276-302)."""
+
+    def __init__(self, chans, kernel_size, act_type="relu", is_complex=False):
+        super().__init__()
+        self.layers = nn.Sequential(ConvBlock(chans, chans, kernel_size, act_type=act_type, is_complex=is_complex),
+                                    ConvBlock(chans, chans, kernel_size, act_type=act_type, is_complex=is_complex))
+
+    def forward(self, input):
+        return self.layers(input) + input
+
+
+def time_pad_circular(x: torch.Tensor, pad: int) -> torch.Tensor:
+    """Circular padding of axis 2 (time) by `pad` on both sides (swin3D.py:401-404)."""
+    return nn.functional.pad(x, (0, 0, 0, 0, pad, pad), mode="circular")
+
+
+def complex_to_channels(x: torch.Tensor) -> torch.Tensor:
+    """[N, C, T, Y, X] complex -> [N, 2C, T, Y, X] real: real parts first, then imaginary parts (swin3D.py:399)."""
+    return torch.cat((x.real, x.imag), dim=1)
+
+
+def channels_to_complex(x: torch.Tensor) -> torch.Tensor:
+    c = x.shape[1]
+    return torch.complex(x[:, :(c // 2)].contiguous(), x[:, (c // 2):].contiguous())

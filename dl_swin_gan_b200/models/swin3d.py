@@ -1,0 +1,90 @@
+"""Swin denoiser of the unrolled network: mirror of dl_cs/models/swin3D.py
+(SwinTransformer3DBlock :304-325, ResSwinTransformer3DBlock :327-340, DeepFeatureExtraction :342-369,
+SwinTransformer3DNet :371-435) with the B200 window-attention backbone inside.
+
+Module tree and parameter names equal the reference's (`SFE.layers.2.conv.*`, `DFE.resswin_blocks.N.layers.0.transformer.*`,
+`DFE.layers.N.*` - the reference registers the ResSwin blocks twice, in `resswin_blocks` and in `layers`, and so does this
+mirror - `final_layer.*`), so `load_state_dict` of a reference checkpoint works.  The Swin hyper-parameters are the
+hard-coded ones of the reference (`depths=[6], num_heads=[8], window_size=(7,8,8)`, swin3D.py:315): the constructor
+arguments `window_size / num_heads / num_layers` are accepted and ignored exactly as there.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from ..mri.utils import center_crop
+from ..swin.backbone import SwinTransformer3D
+from .layers import ConvBlock, channels_to_complex, complex_to_channels, time_pad_circular
+
+
+class SwinTransformer3DBlock(nn.Module):
+    def __init__(self, in_chans, chans, window_size, num_heads, num_layers, is_complex=False):
+        super().__init__()
+        self.is_complex = is_complex
+        self.transformer = SwinTransformer3D(in_chans=in_chans, embed_dim=chans, depths=[6], num_heads=[8], window_size=(7, 8, 8))
+
+    def forward(self, input):
+        return self.transformer(input)
+
+
+class ResSwinTransformer3DBlock(nn.Module):
+    def __init__(self, in_chans, chans, window_size, num_heads, num_layers, act_type="relu", is_complex=False):
+        super().__init__()
+        self.layers = nn.Sequential(
+            SwinTransformer3DBlock(in_chans, chans, window_size, num_heads, num_layers, is_complex=is_complex),
+            ConvBlock(chans, chans, kernel_size=3, act_type=act_type, is_complex=is_complex))
+
+    def forward(self, input):
+        return self.layers(input) + input
+
+
+class DeepFeatureExtraction(nn.Module):
+    def __init__(self, in_chans, chans, window_size, num_heads, num_layers, num_swinblocks, act_type="relu", is_complex=False):
+        super().__init__()
+        self.resswin_blocks = nn.ModuleList(
+            [ResSwinTransformer3DBlock(in_chans, chans, window_size, num_heads, num_layers, act_type=act_type, is_complex=is_complex)
+             for _ in range(num_swinblocks)])
+        self.layers = nn.Sequential(*self.resswin_blocks,
+                                    ConvBlock(chans, chans, kernel_size=3, act_type=act_type, is_complex=is_complex))
+
+    def forward(self, input):
+        return self.layers(input) + input
+
+
+class SwinTransformer3DNet(nn.Module):
+    """SwinMR-style denoiser on [N, emaps, T, Y, X] complex64 series."""
+
+    def __init__(self, num_swinblocks, in_chans, chans, kernel_size, window_size, act_type="relu", num_heads=[4],
+                 num_layers=[4], use_complex_layers=False, circular_pad=True):
+        super().__init__()
+        if use_complex_layers:
+            raise NotImplementedError("the Swin backbone is real-valued; the reference's complex-layer variant cannot run either "
+                                      "(LayerNorm / Linear on complex tensors) - use CONV_BLOCK.COMPLEX: False (config_swin.yaml:19)")
+        self.use_complex_layers = use_complex_layers
+        self.circular_pad = circular_pad
+        self.pad_size = (2 * num_swinblocks + 2) * (kernel_size - 1) // 2
+        self.SFE = ConvBlock(in_chans, chans, kernel_size=3, act_type="none", is_complex=use_complex_layers)      # shallow features
+        self.DFE = DeepFeatureExtraction(chans, chans, window_size, num_heads, num_layers, num_swinblocks, act_type=act_type,
+                                         is_complex=use_complex_layers)
+        self.final_layer = ConvBlock(chans, in_chans, kernel_size=3, act_type=act_type, is_complex=use_complex_layers)
+
+    def _preprocess(self, input):
+        if not self.use_complex_layers:
+            input = complex_to_channels(input)
+        if self.circular_pad:
+            input = time_pad_circular(input, self.pad_size)
+        return input
+
+    def _postprocess(self, output):
+        output = center_crop(output, dims=[2], shapes=[output.shape[2] - 2 * self.pad_size])
+        if not self.use_complex_layers:
+            output = channels_to_complex(output)
+        return output
+
+    def forward(self, x):
+        x = self._preprocess(x)
+        x = self.SFE(x)
+        x = x + self.DFE(x)
+        x = self.final_layer(x)
+        return self._postprocess(x)

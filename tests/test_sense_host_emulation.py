@@ -166,6 +166,11 @@ LINE_CASES = [
     (2, 2, 3, 3, 64, 96, "coil", 0),
     (2, 1, 2, 3, 96, 64, "ragged", 1),                      # one slice per workspace chunk, a frame without lines
     (1, 3, 2, 2, 64, 160, "mask", 0),                       # E = 3: maps of e >= 1 read through the cache
+    # Y = 16 * R2 with R2 >= 8: the packed, pruned column kernels of sense_lines_p.cuh
+    (1, 1, 3, 2, 128, 32, "mask", 0),
+    (2, 2, 2, 3, 128, 32, "coil", 1),                       # E = 2, one slice per workspace chunk
+    (1, 1, 2, 3, 160, 32, "ragged", 0),                     # R2 = 10, a frame without lines
+    (1, 3, 2, 1, 128, 32, "mask", 0),                       # E = 3 stays on the first-generation kernels
 ]
 
 
