@@ -15,7 +15,7 @@
 #define DLSG_KERNEL __global__
 #define DLSG_DEVICE __device__ __forceinline__
 #define DLSG_DYN_SMEM(type, name)                                       \
-    extern __shared__ __align__(16) unsigned char dlsg_dyn_smem_raw[];  \
+    extern __shared__ __align__(128) unsigned char dlsg_dyn_smem_raw[];  \
     type* name = reinterpret_cast<type*>(dlsg_dyn_smem_raw)
 #define DLSG_LAUNCH_BOUNDS(...) __launch_bounds__(__VA_ARGS__)
 
@@ -36,6 +36,35 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_group0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 // all but the most recently committed group have landed
 __device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+
+
+// ---- TMA (bulk tensor copy) + mbarrier: a 2-D tile of a row-major fp32 matrix lands in shared memory as
+// [box_rows][box_cols] (no swizzle), completion is counted in bytes on a shared-memory mbarrier.
+#include <cuda.h>
+namespace dlsg {
+typedef CUtensorMap TileMap;            // built on the host by make_tile_map (sense_api.cu)
+typedef unsigned long long mbar_t;
+}
+#define DLSG_GRID_CONSTANT __grid_constant__
+__device__ __forceinline__ void mbar_init(dlsg::mbar_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+// makes the mbarrier initialisation visible to the async proxy (TMA engine)
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(dlsg::mbar_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                 :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(dlsg::mbar_t* bar, unsigned parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+                 :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+// tile whose first element is (row0, col0) of the matrix described by `tm` (col0 in fp32 elements) -> smem_dst (128-byte aligned)
+__device__ __forceinline__ void tile_load_2d(void* smem_dst, const dlsg::TileMap* tm, int col0, int row0, dlsg::mbar_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                 :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(tm), "r"(col0), "r"(row0),
+                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 
 #include <cuda_fp16.h>
 typedef __half half_t;
@@ -212,6 +241,28 @@ static inline void mma_m16n8k16_f16(float* c, const unsigned* a, unsigned b0, un
 
 
 
+
+// ---- TMA + mbarrier under the emulation: the copy happens at issue time; the mbarrier word holds
+// (completed phases << 32) | pending bytes, so that waiters really wait for the issuing thread
+namespace dlsg {
+struct TileMap { const float* base; long long pitch; long long rows; int box_cols, box_rows; };   // fp32 elements
+typedef unsigned long long mbar_t;
+}
+#define DLSG_GRID_CONSTANT
+static inline void mbar_init(dlsg::mbar_t* bar, unsigned) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
+static inline void mbar_fence_init() {}
+static inline void mbar_expect_tx(dlsg::mbar_t* bar, unsigned bytes) { __atomic_fetch_add(bar, (unsigned long long)bytes, __ATOMIC_SEQ_CST); }
+static inline void mbar_wait(dlsg::mbar_t* bar, unsigned parity) {
+    while (((__atomic_load_n(bar, __ATOMIC_SEQ_CST) >> 32) & 1ull) == (unsigned long long)parity) std::this_thread::yield();
+}
+static inline void tile_load_2d(void* smem_dst, const dlsg::TileMap* tm, int col0, int row0, dlsg::mbar_t* bar) {
+    float* dst = static_cast<float*>(smem_dst);
+    for (int r = 0; r < tm->box_rows; ++r)
+        std::memcpy(dst + (size_t)r * tm->box_cols, tm->base + (size_t)(row0 + r) * tm->pitch + col0, sizeof(float) * tm->box_cols);
+    const unsigned long long bytes = (unsigned long long)tm->box_rows * tm->box_cols * sizeof(float);
+    const unsigned long long left = __atomic_sub_fetch(bar, bytes, __ATOMIC_SEQ_CST) & 0xffffffffull;
+    if (left == 0) __atomic_fetch_add(bar, 1ull << 32, __ATOMIC_SEQ_CST);      // all bytes of the phase have landed
+}
 static inline void cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
 static inline void cp_async8(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 8); }
 static inline void cp_async_wait_all() {}

@@ -386,31 +386,102 @@ inline bool pcols_disabled() {
     const char* v = std::getenv("DLSG_LINES_KERNELS");
     return v && std::strcmp(v, "v1") == 0;
 }
+// buffers of the map slab (mb) and of the exchange (xb) in the forward kernel: DLSG_PCOLS_CFG="mb,xb" overrides
+inline void pcols_fwd_cfg(int E, int Y, int lmax, int& mb, int& xb) {
+    mb = 2; xb = (E == 1) ? 1 : 1;
+    if (const char* v = std::getenv("DLSG_PCOLS_CFG")) {
+        if (v[0] == '1' || v[0] == '2') mb = v[0] - '0';
+        if (v[1] == ',' && (v[2] == '1' || v[2] == '2')) xb = v[2] - '0';
+    }
+    const size_t slab = (size_t)16 * Y * sizeof(float2);
+    const size_t tables = 16 + (size_t)lmax * (2 * sizeof(float4) + sizeof(int)) + 51 * sizeof(int);
+    while ((size_t)(E * mb + xb) * slab + tables > kSmemMax && (mb > 1 || xb > 1)) { if (xb > 1) --xb; else --mb; }
+}
+inline int pcols_adj_xb(int E, int Y, int lmax) {
+    int xb = 1;
+    if (const char* v = std::getenv("DLSG_PCOLS_ADJ_XB")) xb = (v[0] == '2') ? 2 : 1;
+    const size_t slab = (size_t)16 * Y * sizeof(float2);
+    const size_t rest = 16 + (size_t)2 * lmax * 16 * sizeof(float2) + (size_t)lmax * (2 * sizeof(float4) + sizeof(int)) + 51 * sizeof(int);
+    if ((size_t)(2 * E + xb) * slab + rest > kSmemMax) xb = 1;
+    return xb;
+}
 bool pcols_supported(int E, int Y, int X, int lmax) {
     if (E < 1 || E > 2 || !pradix_of(Y) || X % 16) return false;
-    const int r2 = Y / 16;
-    const size_t adj = (size_t)(E + 2) * 16 * 16 * r2 * sizeof(float2) + (size_t)2 * lmax * 16 * sizeof(float2)
-                       + (size_t)lmax * (2 * sizeof(float4) + sizeof(int)) + 51 * sizeof(int);
-    return adj <= kSmemMax;
+    const size_t slab = (size_t)16 * Y * sizeof(float2);
+    const size_t tables = 16 + (size_t)lmax * (2 * sizeof(float4) + sizeof(int)) + 51 * sizeof(int);
+    const size_t fwd = (size_t)(E + 1) * slab + tables;
+    const size_t adj = (size_t)(2 * E + 1) * slab + (size_t)2 * lmax * 16 * sizeof(float2) + tables;
+    return fwd <= kSmemMax && adj <= kSmemMax;
 }
 
-template <int R2>
-int launch_pcols_fwd(const float2* x, const float2* maps, float2* tl, const LinePlan& lp, const SenseDims& d, stream_t s) {
+// TMA descriptor of the coil maps of one chunk seen as a row-major fp32 matrix [rows = B*E*C*Y][2X]; a tile is
+// box_rows rows of 16 complex columns
+#if defined(__CUDACC__)
+}  // namespace
+}  // namespace dlsg
+#include <cudaTypedefs.h>
+namespace dlsg {
+namespace {
+bool make_tile_map(TileMap* tm, const float2* base, long long rows, int X, int box_rows) {
+    static const PFN_cuTensorMapEncodeTiled_v12000 encode = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }();
+    if (!encode) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)2 * X, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)X * sizeof(float2)};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estride[2] = {1u, 1u};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(base), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+#else
+bool make_tile_map(TileMap* tm, const float2* base, long long rows, int X, int box_rows) {
+    tm->base = reinterpret_cast<const float*>(base); tm->pitch = 2LL * X; tm->rows = rows; tm->box_cols = 32; tm->box_rows = box_rows;
+    return true;
+}
+#endif
+
+template <int R2, int E>
+int launch_pcols_fwd_e(const float2* x, const TileMap& tm, float2* tl, const LinePlan& lp, const SenseDims& d, stream_t s) {
     using Cfg = PColCfg<R2>;
     const unsigned grid = (unsigned)((long long)(d.X / 16) * d.t_count * d.B);
-    const size_t smem = Cfg::smem_fwd(d.E, lp.lmax);
-    if (d.E == 1) return launch(sense_cols_fwd_lines_p_kernel<R2, 1>, dim3(grid), dim3(Cfg::NT), smem, s, x, maps, tl, lp, d);
-    return launch(sense_cols_fwd_lines_p_kernel<R2, 2>, dim3(grid), dim3(Cfg::NT), smem, s, x, maps, tl, lp, d);
+    int mb, xb;
+    pcols_fwd_cfg(E, d.Y, lp.lmax, mb, xb);
+    const size_t smem = Cfg::smem_fwd(E, lp.lmax, mb, xb);
+    if (mb == 2 && xb == 2) return launch(sense_cols_fwd_lines_p_kernel<R2, E, 2, 2>, dim3(grid), dim3(Cfg::NT), smem, s, x, tm, tl, lp, d);
+    if (mb == 2) return launch(sense_cols_fwd_lines_p_kernel<R2, E, 2, 1>, dim3(grid), dim3(Cfg::NT), smem, s, x, tm, tl, lp, d);
+    if (xb == 2) return launch(sense_cols_fwd_lines_p_kernel<R2, E, 1, 2>, dim3(grid), dim3(Cfg::NT), smem, s, x, tm, tl, lp, d);
+    return launch(sense_cols_fwd_lines_p_kernel<R2, E, 1, 1>, dim3(grid), dim3(Cfg::NT), smem, s, x, tm, tl, lp, d);
+}
+template <int R2>
+int launch_pcols_fwd(const float2* x, const float2* maps, float2* tl, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    TileMap tm;
+    if (!make_tile_map(&tm, maps, (long long)d.B * d.E * d.C * d.Y, d.X, d.Y / PColCfg<R2>::NBOX)) return -1;
+    if (d.E == 1) return launch_pcols_fwd_e<R2, 1>(x, tm, tl, lp, d, s);
+    return launch_pcols_fwd_e<R2, 2>(x, tm, tl, lp, d, s);
+}
+template <int R2, int E>
+int launch_pcols_adj_e(const float2* tl, const TileMap& tm, float2* out, const float2* xin, const float2* aty,
+                       float step, const float* step_dev, int epi, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    using Cfg = PColCfg<R2>;
+    const unsigned grid = (unsigned)((long long)(d.X / 16) * d.t_count * d.B);
+    const int xb = pcols_adj_xb(E, d.Y, lp.lmax);
+    const size_t smem = Cfg::smem_adj(E, lp.lmax, xb);
+    if (xb == 2)
+        return launch(sense_cols_adj_lines_p_kernel<R2, E, 2>, dim3(grid), dim3(Cfg::NT), smem, s, tl, tm, out, xin, aty, step, step_dev, epi, lp, d);
+    return launch(sense_cols_adj_lines_p_kernel<R2, E, 1>, dim3(grid), dim3(Cfg::NT), smem, s, tl, tm, out, xin, aty, step, step_dev, epi, lp, d);
 }
 template <int R2>
 int launch_pcols_adj(const float2* tl, const float2* maps, float2* out, const float2* xin, const float2* aty,
                      float step, const float* step_dev, int epi, const LinePlan& lp, const SenseDims& d, stream_t s) {
-    using Cfg = PColCfg<R2>;
-    const unsigned grid = (unsigned)((long long)(d.X / 16) * d.t_count * d.B);
-    const size_t smem = Cfg::smem_adj(d.E, lp.lmax);
-    if (d.E == 1)
-        return launch(sense_cols_adj_lines_p_kernel<R2, 1>, dim3(grid), dim3(Cfg::NT), smem, s, tl, maps, out, xin, aty, step, step_dev, epi, lp, d);
-    return launch(sense_cols_adj_lines_p_kernel<R2, 2>, dim3(grid), dim3(Cfg::NT), smem, s, tl, maps, out, xin, aty, step, step_dev, epi, lp, d);
+    TileMap tm;
+    if (!make_tile_map(&tm, maps, (long long)d.B * d.E * d.C * d.Y, d.X, d.Y / PColCfg<R2>::NBOX)) return -1;
+    if (d.E == 1) return launch_pcols_adj_e<R2, 1>(tl, tm, out, xin, aty, step, step_dev, epi, lp, d, s);
+    return launch_pcols_adj_e<R2, 2>(tl, tm, out, xin, aty, step, step_dev, epi, lp, d, s);
 }
 
 int pcols_fwd(const float2* x, const float2* maps, float2* tl, const LinePlan& lp, const SenseDims& d, stream_t s) {
@@ -448,10 +519,14 @@ int run_lines(Op op, const float2* in, const float2* maps, const float* w, const
     const int* counts = plan;
     const int* list = plan + (size_t)B * T;
     const int* pos = list + (size_t)B * T * Y;
+    const int* order = pos + (size_t)B * T * Y;
+    const int* cls = order + (size_t)B * T * Y;
+    const float* wq = reinterpret_cast<const float*>(cls + (size_t)B * T * kPlanClsInts);
     for (long long b0 = 0; b0 < B; b0 += bchunk) {
         const int bc = (int)((B - b0 < bchunk) ? (B - b0) : bchunk);
         const SenseDims d{bc, E, C, T, Y, X, 0, T};
-        const LinePlan lp{counts + b0 * T, list + b0 * T * Y, pos + b0 * T * Y, lmax};
+        const LinePlan lp{counts + b0 * T, list + b0 * T * Y, pos + b0 * T * Y, lmax,
+                          order + b0 * T * Y, cls + b0 * T * kPlanClsInts, wq + b0 * T * Y * 8};
         const float2* maps_b = maps ? maps + b0 * m_slice : nullptr;
         const float* w_b = w + b0 * ws.b;
         if (op == OP_ADJ) {
@@ -554,7 +629,7 @@ int dlsg_sense_dc_step_c64(const void* x, const void* aty, const void* maps, con
 // ---- sampled-line entry points ---------------------------------------------------------------
 size_t dlsg_sense_line_plan_bytes(int B, int T, int Y) {
     if (B <= 0 || T <= 0 || Y <= 0) return 0;
-    return sizeof(int) * (size_t)B * T * (1 + 2 * (size_t)Y);
+    return sizeof(int) * (size_t)B * T * dlsg::line_plan_ints_per_bt(Y);
 }
 
 int dlsg_sense_line_plan_build(const float* weights, const long long* w_strides, int B, int C, int T, int Y, int X,
@@ -565,8 +640,11 @@ int dlsg_sense_line_plan_build(const float* weights, const long long* w_strides,
     int* counts = static_cast<int*>(plan);
     int* list = counts + (size_t)B * T;
     int* pos = list + (size_t)B * T * Y;
+    int* order = pos + (size_t)B * T * Y;
+    int* cls = order + (size_t)B * T * Y;
+    float* wq = reinterpret_cast<float*>(cls + (size_t)B * T * dlsg::kPlanClsInts);
     const int rc = dlsg::launch(dlsg::sense_line_plan_kernel, dim3((unsigned)((long long)B * T)), dim3(256), (size_t)Y * sizeof(int),
-                                static_cast<dlsg::stream_t>(stream), weights, ws, C, T, Y, X, counts, list, pos);
+                                static_cast<dlsg::stream_t>(stream), weights, ws, C, T, Y, X, counts, list, pos, order, cls, wq);
     return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
 }
 

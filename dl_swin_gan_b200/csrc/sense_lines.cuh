@@ -43,7 +43,13 @@ namespace dlsg {
 //   counts[b*T + t]          n(b,t)
 //   list  [(b*T + t)*Y + i]  ky of the i-th sampled line, ascending
 //   pos   [(b*T + t)*Y + ky] i with list[i] == ky, or -1
-struct LinePlan { const int* counts; const int* list; const int* pos; int lmax; };
+//   order [(b*T + t)*Y + q]  line index i at sorted position q, lines grouped by class ky mod 16 (ascending ky inside a class)
+//   cls   [(b*T + t)*36 + .] seg[17] (first sorted position of each class), clist[16] (the non-empty classes), m, bit mask, pad
+//   wq    [((b*T + t)*Y + q)*8 + .] floats (c, s, -s, c) of w = exp(-2 pi i ky / Y) and of w^2, sorted order
+// (the last three serve the pruned column kernels of sense_lines_p.cuh)
+struct LinePlan { const int* counts; const int* list; const int* pos; int lmax; const int* order; const int* cls; const float* wq; };
+constexpr int kPlanClsInts = 36;
+DLSG_HD_CE size_t line_plan_ints_per_bt(int Y) { return 1 + 3 * (size_t)Y + kPlanClsInts + 8 * (size_t)Y; }
 
 DLSG_DEVICE size_t idx_lines(const SenseDims& d, int lmax, int b, int c, int t, int i) {
     return ((((size_t)b * d.C + c) * d.t_count + (t - d.t_begin)) * lmax + i) * (size_t)d.X;
@@ -53,7 +59,7 @@ DLSG_DEVICE size_t idx_lines(const SenseDims& d, int lmax, int b, int c, int t, 
 // CTA = (b, t): flags the ky lines that carry any non-zero (or NaN) weight, then one thread compacts them.
 DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(256)
 sense_line_plan_kernel(const float* __restrict__ w, WeightStrides ws, int C, int T, int Y, int X,
-                       int* counts, int* list, int* pos) {
+                       int* counts, int* list, int* pos, int* order, int* cls, float* wq) {
     DLSG_DYN_SMEM(int, flag);                    // [Y]
     const int bt = blockIdx.x, b = bt / T, t = bt - b * T;
     for (int y = threadIdx.x; y < Y; y += blockDim.x) flag[y] = 0;
@@ -78,6 +84,46 @@ sense_line_plan_kernel(const float* __restrict__ w, WeightStrides ws, int C, int
         }
         for (int i = n; i < Y; ++i) list[(size_t)bt * Y + i] = 0;
         counts[bt] = n;
+        // classes ky mod 16: counting sort (stable), the non-empty classes and their bit mask
+        int* seg = cls + (size_t)bt * kPlanClsInts;
+        int* clist = seg + 17;
+        int cnt[16];
+        for (int k = 0; k < 16; ++k) cnt[k] = 0;
+        const int* lst = list + (size_t)bt * Y;
+        for (int i = 0; i < n; ++i) ++cnt[lst[i] & 15];
+        int s = 0, m = 0, mask = 0;
+        for (int k = 0; k < 16; ++k) {
+            seg[k] = s;
+            clist[k] = 0;
+            if (cnt[k] > 0) { clist[m++] = k; mask |= 1 << k; }
+            s += cnt[k];
+            cnt[k] = seg[k];                         // running write position of the class
+        }
+        seg[16] = s;
+        clist[16] = m; clist[17] = mask; clist[18] = 0;
+        int* ord = order + (size_t)bt * Y;
+        for (int i = 0; i < n; ++i) ord[cnt[lst[i] & 15]++] = i;
+        for (int i = n; i < Y; ++i) ord[i] = 0;
+        flag[0] = n;                                 // hand n to the other threads
+    }
+    __syncthreads();
+    {
+        const int n = flag[0];
+        const int* lst = list + (size_t)bt * Y;
+        const int* ord = order + (size_t)bt * Y;
+        float* wo = wq + (size_t)bt * Y * 8;
+        for (int q = threadIdx.x; q < n; q += blockDim.x) {
+            const int ky = lst[ord[q]];
+            int m1 = ky % Y, m2 = (2 * ky) % Y;
+            if (2 * m1 > Y) m1 -= Y;
+            if (2 * m2 > Y) m2 -= Y;
+            float s1, c1, s2, c2;
+            sincospif((float)(2 * m1) / (float)Y, &s1, &c1);
+            sincospif((float)(2 * m2) / (float)Y, &s2, &c2);
+            float* o = wo + (size_t)q * 8;           // forward sign: w = cos - i sin
+            o[0] = c1; o[1] = -s1; o[2] = s1; o[3] = c1;
+            o[4] = c2; o[5] = -s2; o[6] = s2; o[7] = c2;
+        }
     }
 }
 

@@ -26,10 +26,11 @@ template <int R2>
 struct PColCfg {
     static constexpr int R1 = 16, Y = 16 * R2, SW = 16, NT = SW * R2;
     static constexpr size_t SLAB = (size_t)16 * NT;                              // complex elements of one [16][NT] block
-    static size_t tables(int lmax) { return (size_t)lmax * (2 * sizeof(float4) + sizeof(int)) + (17 + 16 + 2 + 16) * sizeof(int); }
-    static size_t smem_fwd(int E, int lmax) { return (size_t)(E + 2) * SLAB * sizeof(float2) + tables(lmax); }
-    static size_t smem_adj(int E, int lmax) {
-        return (size_t)(E + 2) * SLAB * sizeof(float2) + (size_t)2 * lmax * SW * sizeof(float2) + tables(lmax);
+    static constexpr int NBOX = (Y > 256) ? 2 : 1;                               // TMA boxes per slab (a box has at most 256 rows)
+    static size_t tables(int lmax) { return 16 + (size_t)lmax * (2 * sizeof(float4) + sizeof(int)) + (17 + 16 + 2 + 16) * sizeof(int); }
+    static size_t smem_fwd(int E, int lmax, int mb, int xb) { return (size_t)(E * mb + xb) * SLAB * sizeof(float2) + tables(lmax); }
+    static size_t smem_adj(int E, int lmax, int xb) {
+        return (size_t)(E * 2 + xb) * SLAB * sizeof(float2) + (size_t)2 * lmax * SW * sizeof(float2) + tables(lmax);
     }
 };
 
@@ -74,112 +75,100 @@ DLSG_DEVICE LineTables line_tables_at(void* p, int lmax) {
     t.ccnt = t.meta + 2;
     return t;
 }
-// all threads of the CTA call it; ends with a barrier
+// copies the tables of (b, t) from the plan (built once per weights tensor by sense_line_plan_kernel) into shared
+// memory; SIGN = +1 conjugates the coefficients.  All threads of the CTA call it; the caller's next barrier publishes them.
 template <int SIGN>
-DLSG_DEVICE void build_line_tables(const LineTables& lt, const int* __restrict__ list, int n, int Y, int tid, int nt) {
-    if (tid < 16) {
-        int cnt = 0;
-        for (int i = 0; i < n; ++i) cnt += ((__ldg(list + i) & 15) == tid);
-        lt.ccnt[tid] = cnt;
+DLSG_DEVICE void load_line_tables(const LineTables& lt, const LinePlan& lp, int bt, int n, int Y, int tid, int nt) {
+    const float4* src = reinterpret_cast<const float4*>(lp.wq + (size_t)bt * Y * 8);
+    for (int i = tid; i < 2 * n; i += nt) {
+        const float4 w = __ldg(src + i);
+        lt.wq[i] = (SIGN < 0) ? w : make_float4(w.x, w.z, w.y, w.w);       // conj: (c, s, -s, c) -> (c, -s, s, c)
     }
-    __syncthreads();
-    if (tid == 0) {
-        int s = 0, m = 0, mask = 0;
-        for (int k = 0; k < 16; ++k) {
-            lt.seg[k] = s;
-            if (lt.ccnt[k] > 0) { lt.clist[m++] = k; mask |= 1 << k; }
-            s += lt.ccnt[k];
-        }
-        lt.seg[16] = s;
-        lt.meta[0] = m; lt.meta[1] = mask;
-    }
-    __syncthreads();
-    if (tid < 16) {
-        int q = lt.seg[tid];
-        for (int i = 0; i < n; ++i)
-            if ((__ldg(list + i) & 15) == tid) lt.order[q++] = i;
-    }
-    __syncthreads();
-    for (int q = tid; q < n; q += nt) {
-        const int ky = __ldg(list + lt.order[q]);
-        const float2 w = unit_root(ky, Y), w2 = unit_root(2 * ky, Y);      // (cos, sin)
-        const float s1 = (SIGN < 0) ? -w.y : w.y, s2 = (SIGN < 0) ? -w2.y : w2.y;
-        lt.wq[2 * q] = make_float4(w.x, s1, -s1, w.x);
-        lt.wq[2 * q + 1] = make_float4(w2.x, s2, -s2, w2.x);
-    }
-    __syncthreads();
+    const int* ord = lp.order + (size_t)bt * Y;
+    for (int i = tid; i < n; i += nt) lt.order[i] = __ldg(ord + i);
+    const int* cls = lp.cls + (size_t)bt * kPlanClsInts;
+    for (int i = tid; i < 35; i += nt) lt.seg[i] = __ldg(cls + i);          // seg[17], clist[16], meta[2] are contiguous
 }
 
-// this thread's 16 map values of coil c, map set e: staged by 8-byte cp.async into slots only this thread reads
-// (no CTA barrier, no registers held while the loads are in flight)
-template <int NT, int R2, int E>
-DLSG_DEVICE void stage_maps_private(float2* mstg, const float2* mbase, int c, int C, size_t img, size_t rstride, int tid) {
-#ifdef DLSG_DEBUG_SAME_MAPS
-    c = 0;          // timing experiment only (wrong results): every coil reads coil 0, so the map traffic hits in L1/L2
-#endif
+// The coil's map slab [Y rows][16 columns] of every map set arrives by TMA (one bulk tensor copy per map set, issued by
+// one thread, completion counted on an mbarrier): no per-thread global loads, no registers held while in flight.
+template <int R2, int E>
+DLSG_DEVICE void tma_maps(float2* slab, const TileMap* tm, int b, int c, int C, int kx0, mbar_t* bar) {
+    constexpr int Y = 16 * R2, NBOX = PColCfg<R2>::NBOX, BR = Y / NBOX;
+    mbar_expect_tx(bar, (unsigned)(E * Y * 16 * sizeof(float2)));
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const float2* src = mbase + ((size_t)e * C + c) * img;
+    for (int e = 0; e < E; ++e)
 #pragma unroll
-        for (int l = 0; l < 16; ++l) cp_async8(mstg + (e * 16 + l) * NT + tid, src + l * rstride);
-    }
+        for (int h = 0; h < NBOX; ++h)
+            tile_load_2d(slab + (size_t)e * PColCfg<R2>::SLAB + (size_t)h * BR * 16, tm, 2 * kx0,
+                         ((b * E + e) * C + c) * Y + h * BR, bar);
 }
 
 // tl[b,c,t,i,kx] = DFT_Y( sum_e maps[b,e,c,:,kx] * x[b,e,t,:,kx] )[ky_i]   for the sampled lines of (b,t).
-// Per coil: product with the thread's x values, DFT16, the bins of the non-empty classes go to shared memory (double
-// buffered: one CTA barrier per coil), then one thread per (class, column) reads the R2 bins of its class once and
-// evaluates sum_j w^j Z_j for every line of the class (w = W_Y^ky; Horner's rule on the even and the odd terms).
-template <int R2, int E>
-DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(16 * R2, (E == 1 ? 3 : 2))
-sense_cols_fwd_lines_p_kernel(const float2* __restrict__ x, const float2* __restrict__ maps,
+// Per coil: product of the TMA-staged map slab with the thread's x values, DFT16, the bins of the non-empty classes go
+// to shared memory, then one thread per (class, column) reads the R2 bins of its class once and evaluates
+// sum_j w^j Z_j for every line of the class (w = W_Y^ky; Horner's rule on the even and the odd terms).
+// MB / XB: buffers of the map slab / of the exchange (XB = 2: one CTA barrier per coil, XB = 1: two).
+template <int R2, int E, int MB, int XB>
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(16 * R2, ((E + 0) * MB + XB <= 3 ? 3 : 2))
+sense_cols_fwd_lines_p_kernel(const float2* __restrict__ x, const DLSG_GRID_CONSTANT TileMap maps_tm,
                               float2* __restrict__ tl_out, LinePlan lp, SenseDims d) {
     using Cfg = PColCfg<R2>;
     constexpr int NT = Cfg::NT, Y = Cfg::Y;
     static_assert(R2 % 2 == 0, "even R2");
     DLSG_DYN_SMEM(float2, smem);
-    float2* mstg = smem;                                         // [E][16][NT] private map slots (l, tid)
-    float2* exch = mstg + (size_t)E * Cfg::SLAB;                 // [2][16][NT] Z_j[k1] at (k1, tid = j*16 + col)
-    const LineTables lt = line_tables_at(exch + 2 * Cfg::SLAB, lp.lmax);
+    float2* mslab = smem;                                        // [MB][E][Y][16] map slabs (TMA destinations)
+    float2* exch = mslab + (size_t)MB * E * Cfg::SLAB;           // [XB][16][NT] Z_j[k1] at (k1, tid = j*16 + col)
+    mbar_t* bars = reinterpret_cast<mbar_t*>(exch + (size_t)XB * Cfg::SLAB);   // [MB]
+    const LineTables lt = line_tables_at(bars + 2, lp.lmax);
     const int tid = threadIdx.x, col = tid & 15, j = tid >> 4;
     const PColWho who = pcol_who(d);
     const int b = who.b, t = who.t, kx = who.kx0 + col;
     const int n = __ldg(lp.counts + who.bt);
     if (n == 0) return;                                          // nothing sampled in this frame (uniform over the CTA)
 
-    const size_t img = (size_t)Y * d.X, rstride = (size_t)R2 * d.X;
-    const float2* mbase = maps + idx_maps(d, b, 0, 0, j) + kx;   // + (e*C + c) * img + l * R2 * X
-    stage_maps_private<NT, R2, E>(mstg, mbase, 0, d.C, img, rstride, tid);
-    cp_async_commit();
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < MB; ++i) mbar_init(bars + i, 1);
+        mbar_fence_init();
+    }
+    const size_t rstride = (size_t)R2 * d.X;
     float2 xr[E][16];                                            // x[b,e,t, R2 l + j, kx]: the same for every coil
 #pragma unroll
     for (int e = 0; e < E; ++e)
 #pragma unroll
         for (int l = 0; l < 16; ++l) xr[e][l] = __ldg(x + idx_x(d, b, e, t, j) + kx + l * rstride);
-    build_line_tables<-1>(lt, lp.list + (size_t)who.bt * Y, n, Y, tid, NT);
+    load_line_tables<-1>(lt, lp, who.bt, n, Y, tid, NT);
+    __syncthreads();                                             // tables and mbarrier initialisation visible
     const int m = lt.meta[0], mask = lt.meta[1];
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+            if (i < d.C) tma_maps<R2, E>(mslab + (size_t)i * E * Cfg::SLAB, &maps_tm, b, i, d.C, who.kx0, bars + i);
+    }
 
 #pragma unroll 1
     for (int c = 0; c < d.C; ++c) {
-        cp_async_wait_group0();
+        const int mb = c % MB;
+        const float2* ms = mslab + (size_t)mb * E * Cfg::SLAB + tid;        // slab element (R2 l + j, col) = [l * NT + tid]
+        mbar_wait(bars + mb, (unsigned)((c / MB) & 1));
         float2 v[16];
 #pragma unroll
         for (int l = 0; l < 16; ++l) {
-            v[l] = pc_mul(mstg[l * NT + tid], xr[0][l]);
+            v[l] = pc_mul(ms[l * NT], xr[0][l]);
 #pragma unroll
-            for (int e = 1; e < E; ++e) v[l] = pc_fma(mstg[(e * 16 + l) * NT + tid], xr[e][l], v[l]);
+            for (int e = 1; e < E; ++e) v[l] = pc_fma(ms[(e * 16 + l) * NT], xr[e][l], v[l]);
         }
-        if (c + 1 < d.C) stage_maps_private<NT, R2, E>(mstg, mbase, c + 1, d.C, img, rstride, tid);   // slots already read
-        cp_async_commit();
         PDft<16, -1>::run(v);
-        float2* ex = exch + (size_t)(c & 1) * Cfg::SLAB;        // the other buffer may still be read by slower threads
+        float2* ex = exch + (size_t)(c % XB) * Cfg::SLAB;
+        if (XB == 1) __syncthreads();                            // the previous coil's bins have been consumed
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1)
             if ((mask >> k1) & 1) ex[k1 * NT + tid] = v[k1];
-        __syncthreads();
+        __syncthreads();                                         // bins visible; everyone has read the map slab
+        if (tid == 0 && c + MB < d.C)
+            tma_maps<R2, E>(mslab + (size_t)mb * E * Cfg::SLAB, &maps_tm, b, c + MB, d.C, who.kx0, bars + mb);
         float2* outp = tl_out + idx_lines(d, lp.lmax, b, c, t, 0) + kx;
-#ifdef DLSG_DEBUG_NO_GATHER
-        if (m > 1000)   // timing experiment only (wrong results): the pruned stage is skipped
-#endif
         for (int wi = j; wi < m; wi += R2) {                     // this thread's (class, column) items
             const int k1 = lt.clist[wi];
             const float2* zp = ex + k1 * NT + col;
@@ -206,29 +195,29 @@ sense_cols_fwd_lines_p_kernel(const float2* __restrict__ x, const float2* __rest
 
 // out_e[b,t,y,kx] = EPI( sum_c conj(maps[b,e,c,y,kx]) * IDFT_Y( scatter of tl[b,c,t,:,kx] to its ky lines )[y] )
 // Per coil: one thread per (class, column) forms U_j[k1] = sum_{lines of the class} conj(w)^j tl (powers by repeated
-// multiplication with w^2 on the even and odd terms, each line read once), the R2 values go to shared memory (double
-// buffered: one CTA barrier per coil); then every thread takes its 16 bins (zeros for the empty classes), IDFT16, and
-// accumulates conj(S) * out in registers.
-template <int R2, int E>
-DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(16 * R2, (E == 1 ? 3 : 2))
-sense_cols_adj_lines_p_kernel(const float2* __restrict__ tl_in, const float2* __restrict__ maps, float2* __restrict__ out,
+// multiplication with w^2 on the even and odd terms, each line read once), the R2 values go to shared memory; then
+// every thread takes its 16 bins (zeros for the empty classes), IDFT16, and accumulates conj(S) * out in registers,
+// S from the TMA-staged map slab (two buffers: the slab of coil c+2 is requested once everyone has used coil c's).
+template <int R2, int E, int XB>
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(16 * R2, 2)
+sense_cols_adj_lines_p_kernel(const float2* __restrict__ tl_in, const DLSG_GRID_CONSTANT TileMap maps_tm, float2* __restrict__ out,
                               const float2* __restrict__ xin, const float2* __restrict__ aty,
                               float step_host, const float* __restrict__ step_dev, int epi, LinePlan lp, SenseDims d) {
     using Cfg = PColCfg<R2>;
-    constexpr int NT = Cfg::NT, Y = Cfg::Y, SW = 16;
+    constexpr int NT = Cfg::NT, Y = Cfg::Y, SW = 16, MB = 2;
     DLSG_DYN_SMEM(float2, smem);
-    float2* mstg = smem;                                         // [E][16][NT] private map slots
-    float2* exch = mstg + (size_t)E * Cfg::SLAB;                 // [2][16][NT] U_j[k1] at (k1, j*16 + col)
-    float2* tbuf = exch + 2 * Cfg::SLAB;                         // [2][lmax][SW] sampled lines of a coil in sorted order
-    const LineTables lt = line_tables_at(tbuf + (size_t)2 * lp.lmax * SW, lp.lmax);
+    float2* mslab = smem;                                        // [MB][E][Y][16]
+    float2* exch = mslab + (size_t)MB * E * Cfg::SLAB;           // [XB][16][NT] U_j[k1] at (k1, j*16 + col)
+    float2* tbuf = exch + (size_t)XB * Cfg::SLAB;                // [2][lmax][SW] sampled lines of a coil in sorted order
+    mbar_t* bars = reinterpret_cast<mbar_t*>(tbuf + (size_t)2 * lp.lmax * SW);
+    const LineTables lt = line_tables_at(bars + 2, lp.lmax);
     const int tid = threadIdx.x, col = tid & 15, j = tid >> 4;
     const PColWho who = pcol_who(d);
     const int b = who.b, t = who.t, kx = who.kx0 + col;
     const int n = __ldg(lp.counts + who.bt);
     const float step = step_dev ? __ldg(step_dev) : step_host;
+    const size_t rstride = (size_t)R2 * d.X;
 
-    const size_t img = (size_t)Y * d.X, rstride = (size_t)R2 * d.X;
-    const float2* mbase = maps + idx_maps(d, b, 0, 0, j) + kx;
     auto fetch_lines = [&](int c) {                              // sorted position q <- line order[q]
         const float2* src = tl_in + idx_lines(d, lp.lmax, b, c, t, 0) + who.kx0;
         float2* dst = tbuf + (size_t)(c & 1) * lp.lmax * SW;
@@ -246,9 +235,19 @@ sense_cols_adj_lines_p_kernel(const float2* __restrict__ tl_in, const float2* __
 
     int m = 0, mask = 0;
     if (n > 0) {
-        stage_maps_private<NT, R2, E>(mstg, mbase, 0, d.C, img, rstride, tid);
-        build_line_tables<+1>(lt, lp.list + (size_t)who.bt * Y, n, Y, tid, NT);
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < MB; ++i) mbar_init(bars + i, 1);
+            mbar_fence_init();
+        }
+        load_line_tables<+1>(lt, lp, who.bt, n, Y, tid, NT);
+        __syncthreads();                                         // tables and mbarrier initialisation visible
         m = lt.meta[0]; mask = lt.meta[1];
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < MB; ++i)
+                if (i < d.C) tma_maps<R2, E>(mslab + (size_t)i * E * Cfg::SLAB, &maps_tm, b, i, d.C, who.kx0, bars + i);
+        }
         fetch_lines(0);
         cp_async_commit();
         cp_async_wait_group0();
@@ -259,9 +258,10 @@ sense_cols_adj_lines_p_kernel(const float2* __restrict__ tl_in, const float2* __
 
 #pragma unroll 1
     for (int c = 0; c < d.C && n > 0; ++c) {
-        // (1) class phase: lines of coil c (visible since the previous barrier) -> U_j[k1] in exch[c & 1]
+        // (1) class phase: lines of coil c (visible since the previous barrier) -> U_j[k1]
         const float2* tb = tbuf + (size_t)(c & 1) * lp.lmax * SW + col;
-        float2* ex = exch + (size_t)(c & 1) * Cfg::SLAB;
+        float2* ex = exch + (size_t)(c % XB) * Cfg::SLAB;
+        if (XB == 1 && c > 0) __syncthreads();                   // everyone has taken the previous coil's bins
         for (int wi = j; wi < m; wi += R2) {
             const int k1 = lt.clist[wi];
             float2 uj[R2];
@@ -290,20 +290,23 @@ sense_cols_adj_lines_p_kernel(const float2* __restrict__ tl_in, const float2* __
 #pragma unroll
             for (int jj = 0; jj < R2; ++jj) up[jj * 16] = uj[jj];
         }
-        cp_async_wait_group0();                                  // this thread's chunks of the next coil's lines and maps
-        __syncthreads();                                         // (2) bins of coil c and lines of coil c+1 visible; everyone is done with tbuf[c & 1]
+        cp_async_wait_group0();                                  // this thread's chunks of the next coil's lines
+        __syncthreads();                                         // (2) bins of coil c and lines of coil c+1 visible; tbuf[c & 1] and the slab of coil c-1 are free
         if (c + 2 < d.C) fetch_lines(c + 2);
         cp_async_commit();
+        if (tid == 0 && c >= 1 && c - 1 + MB < d.C)
+            tma_maps<R2, E>(mslab + (size_t)((c - 1) % MB) * E * Cfg::SLAB, &maps_tm, b, c - 1 + MB, d.C, who.kx0, bars + (c - 1) % MB);
         float2 u[16];
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) u[k1] = ((mask >> k1) & 1) ? ex[k1 * NT + tid] : make_float2(0.f, 0.f);
         PDft<16, +1>::run(u);
+        const int mb = c % MB;
+        const float2* ms = mslab + (size_t)mb * E * Cfg::SLAB + tid;
+        mbar_wait(bars + mb, (unsigned)((c / MB) & 1));
 #pragma unroll
         for (int e = 0; e < E; ++e)
 #pragma unroll
-            for (int l = 0; l < 16; ++l) acc[e][l] = pc_fmac(mstg[(e * 16 + l) * NT + tid], u[l], acc[e][l]);
-        if (c + 1 < d.C) stage_maps_private<NT, R2, E>(mstg, mbase, c + 1, d.C, img, rstride, tid);
-        cp_async_commit();
+            for (int l = 0; l < 16; ++l) acc[e][l] = pc_fmac(ms[(e * 16 + l) * NT], u[l], acc[e][l]);
     }
     // ---- epilogue: this thread owns y = R2 l + j of column kx
     // out = a * (acc - av) + bx * xv :  PLAIN (a, bx) = (1, 0);  DC (step, 1) with av = aty;  REG (1, step)

@@ -192,12 +192,22 @@ def test_emulated_sampled_line_path_matches_oracle(sense_emu_lib, B, E, C, T, Y,
     sampled = (wb != 0).any(axis=(1, 4))                    # [B, T, Y]
     assert np.array_equal(counts.reshape(B, T), sampled.sum(-1))
     lst = plan[B * T: B * T * (1 + Y)].reshape(B, T, Y)
-    pos = plan[B * T * (1 + Y):].reshape(B, T, Y)
+    pos = plan[B * T * (1 + Y): B * T * (1 + 2 * Y)].reshape(B, T, Y)
+    order = plan[B * T * (1 + 2 * Y): B * T * (1 + 3 * Y)].reshape(B, T, Y)
+    cls = plan[B * T * (1 + 3 * Y): B * T * (1 + 3 * Y + 36)].reshape(B, T, 36)
     for b in range(B):
         for t in range(T):
             ky = np.flatnonzero(sampled[b, t])
             assert np.array_equal(lst[b, t, : len(ky)], ky)
             assert np.array_equal(pos[b, t, ky], np.arange(len(ky))) and (pos[b, t, ~sampled[b, t]] == -1).all()
+            # class tables of the pruned column kernels: lines grouped by ky mod 16, stable
+            want_order = np.argsort(ky % 16, kind="stable")
+            assert np.array_equal(order[b, t, : len(ky)], want_order)
+            seg = cls[b, t, :17]
+            assert seg[0] == 0 and seg[16] == len(ky) and np.array_equal(np.diff(seg), np.bincount(ky % 16, minlength=16))
+            nonempty = np.flatnonzero(np.diff(seg))
+            assert cls[b, t, 33] == len(nonempty) and np.array_equal(cls[b, t, 17:17 + len(nonempty)], nonempty)
+            assert cls[b, t, 34] == sum(1 << int(k) for k in nonempty)
     lmax = max(1, int(counts.max()))
     assert lib.dlsg_sense_lines_supported(E, Y, X, lmax) == 1
 
