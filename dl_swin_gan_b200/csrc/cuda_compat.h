@@ -15,7 +15,7 @@
 #define DLSG_KERNEL __global__
 #define DLSG_DEVICE __device__ __forceinline__
 #define DLSG_DYN_SMEM(type, name)                                       \
-    extern __shared__ __align__(128) unsigned char dlsg_dyn_smem_raw[];  \
+    extern __shared__ __align__(1024) unsigned char dlsg_dyn_smem_raw[];  \
     type* name = reinterpret_cast<type*>(dlsg_dyn_smem_raw)
 #define DLSG_LAUNCH_BOUNDS(...) __launch_bounds__(__VA_ARGS__)
 
@@ -54,6 +54,9 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(dlsg::mbar_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
                  :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(dlsg::mbar_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(dlsg::mbar_t* bar, unsigned parity) {
     asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
@@ -243,25 +246,56 @@ static inline void mma_m16n8k16_f16(float* c, const unsigned* a, unsigned b0, un
 
 
 // ---- TMA + mbarrier under the emulation: the copy happens at issue time; the mbarrier word holds
-// (completed phases << 32) | pending bytes, so that waiters really wait for the issuing thread
+// (completed phases << 32) | (pending arrivals << 20) | pending bytes, so that waiters really wait
 namespace dlsg {
-struct TileMap { const float* base; long long pitch; long long rows; int box_cols, box_rows; };   // fp32 elements
+struct TileMap { const float* base; long long pitch; long long rows; int box_cols, box_rows, swizzle128; };   // fp32 elements
 typedef unsigned long long mbar_t;
 }
+namespace dlsg_emu {
+inline std::mutex& mbar_mutex() { static std::mutex m; return m; }
+inline std::vector<std::pair<const void*, unsigned>>& mbar_counts() { static std::vector<std::pair<const void*, unsigned>> v; return v; }
+inline unsigned mbar_init_count(const void* bar) {
+    for (auto& kv : mbar_counts()) if (kv.first == bar) return kv.second;
+    return 1;
+}
+// caller holds the mutex: completes the phase when no arrival and no byte is pending
+inline void mbar_settle(dlsg::mbar_t* bar, unsigned long long v) {
+    if (((v >> 20) & 0xfffull) == 0 && (v & 0xfffffull) == 0)
+        v = (((v >> 32) + 1) << 32) | ((unsigned long long)mbar_init_count(bar) << 20);
+    __atomic_store_n(bar, v, __ATOMIC_SEQ_CST);
+}
+}  // namespace dlsg_emu
 #define DLSG_GRID_CONSTANT
-static inline void mbar_init(dlsg::mbar_t* bar, unsigned) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
+static inline void mbar_init(dlsg::mbar_t* bar, unsigned count) {
+    std::lock_guard<std::mutex> g(dlsg_emu::mbar_mutex());
+    bool found = false;
+    for (auto& kv : dlsg_emu::mbar_counts()) if (kv.first == bar) { kv.second = count; found = true; }
+    if (!found) dlsg_emu::mbar_counts().push_back({bar, count});
+    __atomic_store_n(bar, (unsigned long long)count << 20, __ATOMIC_SEQ_CST);
+}
 static inline void mbar_fence_init() {}
-static inline void mbar_expect_tx(dlsg::mbar_t* bar, unsigned bytes) { __atomic_fetch_add(bar, (unsigned long long)bytes, __ATOMIC_SEQ_CST); }
+static inline void mbar_arrive(dlsg::mbar_t* bar) {
+    std::lock_guard<std::mutex> g(dlsg_emu::mbar_mutex());
+    dlsg_emu::mbar_settle(bar, __atomic_load_n(bar, __ATOMIC_SEQ_CST) - (1ull << 20));
+}
+static inline void mbar_expect_tx(dlsg::mbar_t* bar, unsigned bytes) {      // = arrive.expect_tx
+    std::lock_guard<std::mutex> g(dlsg_emu::mbar_mutex());
+    dlsg_emu::mbar_settle(bar, __atomic_load_n(bar, __ATOMIC_SEQ_CST) - (1ull << 20) + bytes);
+}
 static inline void mbar_wait(dlsg::mbar_t* bar, unsigned parity) {
     while (((__atomic_load_n(bar, __ATOMIC_SEQ_CST) >> 32) & 1ull) == (unsigned long long)parity) std::this_thread::yield();
 }
 static inline void tile_load_2d(void* smem_dst, const dlsg::TileMap* tm, int col0, int row0, dlsg::mbar_t* bar) {
     float* dst = static_cast<float*>(smem_dst);
-    for (int r = 0; r < tm->box_rows; ++r)
-        std::memcpy(dst + (size_t)r * tm->box_cols, tm->base + (size_t)(row0 + r) * tm->pitch + col0, sizeof(float) * tm->box_cols);
+    for (int r = 0; r < tm->box_rows; ++r) {
+        const float* src = tm->base + (size_t)(row0 + r) * tm->pitch + col0;
+        if (!tm->swizzle128) { std::memcpy(dst + (size_t)r * tm->box_cols, src, sizeof(float) * tm->box_cols); continue; }
+        for (int ch = 0; ch < tm->box_cols / 4; ++ch)            // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8), rows of 128 bytes
+            std::memcpy(dst + (size_t)r * 32 + 4 * (ch ^ (r & 7)), src + 4 * ch, 16);
+    }
     const unsigned long long bytes = (unsigned long long)tm->box_rows * tm->box_cols * sizeof(float);
-    const unsigned long long left = __atomic_sub_fetch(bar, bytes, __ATOMIC_SEQ_CST) & 0xffffffffull;
-    if (left == 0) __atomic_fetch_add(bar, 1ull << 32, __ATOMIC_SEQ_CST);      // all bytes of the phase have landed
+    std::lock_guard<std::mutex> g(dlsg_emu::mbar_mutex());
+    dlsg_emu::mbar_settle(bar, __atomic_load_n(bar, __ATOMIC_SEQ_CST) - bytes);
 }
 static inline void cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
 static inline void cp_async8(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 8); }

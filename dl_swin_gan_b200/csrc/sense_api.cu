@@ -388,27 +388,27 @@ inline bool pcols_disabled() {
 }
 // buffers of the map slab (mb) and of the exchange (xb) in the forward kernel: DLSG_PCOLS_CFG="mb,xb" overrides
 inline void pcols_fwd_cfg(int E, int Y, int lmax, int& mb, int& xb) {
-    mb = 2; xb = (E == 1) ? 1 : 1;
+    mb = 1; xb = 1;
     if (const char* v = std::getenv("DLSG_PCOLS_CFG")) {
         if (v[0] == '1' || v[0] == '2') mb = v[0] - '0';
         if (v[1] == ',' && (v[2] == '1' || v[2] == '2')) xb = v[2] - '0';
     }
     const size_t slab = (size_t)16 * Y * sizeof(float2);
-    const size_t tables = 16 + (size_t)lmax * (2 * sizeof(float4) + sizeof(int)) + 51 * sizeof(int);
+    const size_t tables = 16 + (size_t)lmax * (2 * sizeof(float4) + 2 * sizeof(int)) + 36 * sizeof(int);
     while ((size_t)(E * mb + xb) * slab + tables > kSmemMax && (mb > 1 || xb > 1)) { if (xb > 1) --xb; else --mb; }
 }
 inline int pcols_adj_xb(int E, int Y, int lmax) {
-    int xb = 1;
+    int xb = 2;
     if (const char* v = std::getenv("DLSG_PCOLS_ADJ_XB")) xb = (v[0] == '2') ? 2 : 1;
     const size_t slab = (size_t)16 * Y * sizeof(float2);
-    const size_t rest = 16 + (size_t)2 * lmax * 16 * sizeof(float2) + (size_t)lmax * (2 * sizeof(float4) + sizeof(int)) + 51 * sizeof(int);
+    const size_t rest = 16 + (size_t)2 * lmax * 16 * sizeof(float2) + (size_t)lmax * (2 * sizeof(float4) + 2 * sizeof(int)) + 36 * sizeof(int);
     if ((size_t)(2 * E + xb) * slab + rest > kSmemMax) xb = 1;
     return xb;
 }
 bool pcols_supported(int E, int Y, int X, int lmax) {
     if (E < 1 || E > 2 || !pradix_of(Y) || X % 16) return false;
     const size_t slab = (size_t)16 * Y * sizeof(float2);
-    const size_t tables = 16 + (size_t)lmax * (2 * sizeof(float4) + sizeof(int)) + 51 * sizeof(int);
+    const size_t tables = 16 + (size_t)lmax * (2 * sizeof(float4) + 2 * sizeof(int)) + 36 * sizeof(int);
     const size_t fwd = (size_t)(E + 1) * slab + tables;
     const size_t adj = (size_t)(2 * E + 1) * slab + (size_t)2 * lmax * 16 * sizeof(float2) + tables;
     return fwd <= kSmemMax && adj <= kSmemMax;
@@ -441,6 +441,7 @@ bool make_tile_map(TileMap* tm, const float2* base, long long rows, int X, int b
 #else
 bool make_tile_map(TileMap* tm, const float2* base, long long rows, int X, int box_rows) {
     tm->base = reinterpret_cast<const float*>(base); tm->pitch = 2LL * X; tm->rows = rows; tm->box_cols = 32; tm->box_rows = box_rows;
+    tm->swizzle128 = 0;
     return true;
 }
 #endif

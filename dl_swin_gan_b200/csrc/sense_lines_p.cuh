@@ -27,7 +27,7 @@ struct PColCfg {
     static constexpr int R1 = 16, Y = 16 * R2, SW = 16, NT = SW * R2;
     static constexpr size_t SLAB = (size_t)16 * NT;                              // complex elements of one [16][NT] block
     static constexpr int NBOX = (Y > 256) ? 2 : 1;                               // TMA boxes per slab (a box has at most 256 rows)
-    static size_t tables(int lmax) { return 16 + (size_t)lmax * (2 * sizeof(float4) + sizeof(int)) + (17 + 16 + 2 + 16) * sizeof(int); }
+    static size_t tables(int lmax) { return 16 + (size_t)lmax * (2 * sizeof(float4) + 2 * sizeof(int)) + (17 + 16 + 2 + 1) * sizeof(int); }
     static size_t smem_fwd(int E, int lmax, int mb, int xb) { return (size_t)(E * mb + xb) * SLAB * sizeof(float2) + tables(lmax); }
     static size_t smem_adj(int E, int lmax, int xb) {
         return (size_t)(E * 2 + xb) * SLAB * sizeof(float2) + (size_t)2 * lmax * SW * sizeof(float2) + tables(lmax);
@@ -64,7 +64,7 @@ DLSG_DEVICE float2 unit_root(int m, int Y) {
 //   order[q]              line index i (row of `tl`) at sorted position q
 //   wq[2q], wq[2q+1]      (c, s, -s, c) of w = exp(SIGN * 2 pi i ky / Y) and of w^2
 //   clist[0..m)           the non-empty classes, meta[0] = m, meta[1] = bit mask of the non-empty classes
-struct LineTables { float4* wq; int* order; int* seg; int* clist; int* meta; int* ccnt; };
+struct LineTables { float4* wq; int* order; int* seg; int* clist; int* meta; int* k1q; };
 DLSG_DEVICE LineTables line_tables_at(void* p, int lmax) {
     LineTables t;
     t.wq = reinterpret_cast<float4*>(p);
@@ -72,7 +72,7 @@ DLSG_DEVICE LineTables line_tables_at(void* p, int lmax) {
     t.seg = t.order + lmax;
     t.clist = t.seg + 17;
     t.meta = t.clist + 16;
-    t.ccnt = t.meta + 2;
+    t.k1q = t.meta + 2;                                      // [lmax] (ky mod 16) * NT of sorted line q
     return t;
 }
 // copies the tables of (b, t) from the plan (built once per weights tensor by sense_line_plan_kernel) into shared
@@ -85,7 +85,12 @@ DLSG_DEVICE void load_line_tables(const LineTables& lt, const LinePlan& lp, int 
         lt.wq[i] = (SIGN < 0) ? w : make_float4(w.x, w.z, w.y, w.w);       // conj: (c, s, -s, c) -> (c, -s, s, c)
     }
     const int* ord = lp.order + (size_t)bt * Y;
-    for (int i = tid; i < n; i += nt) lt.order[i] = __ldg(ord + i);
+    const int* list = lp.list + (size_t)bt * Y;
+    for (int i = tid; i < n; i += nt) {
+        const int o = __ldg(ord + i);
+        lt.order[i] = o;
+        lt.k1q[i] = (__ldg(list + o) & 15) * nt;                            // nt = 16 * R2 = row stride of the exchange
+    }
     const int* cls = lp.cls + (size_t)bt * kPlanClsInts;
     for (int i = tid; i < 35; i += nt) lt.seg[i] = __ldg(cls + i);          // seg[17], clist[16], meta[2] are contiguous
 }
@@ -110,7 +115,10 @@ DLSG_DEVICE void tma_maps(float2* slab, const TileMap* tm, int b, int c, int C, 
 // sum_j w^j Z_j for every line of the class (w = W_Y^ky; Horner's rule on the even and the odd terms).
 // MB / XB: buffers of the map slab / of the exchange (XB = 2: one CTA barrier per coil, XB = 1: two).
 template <int R2, int E, int MB, int XB>
-DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(16 * R2, ((E + 0) * MB + XB <= 3 ? 3 : 2))
+#ifndef DLSG_PCOLS_FWD_MINB
+#define DLSG_PCOLS_FWD_MINB(SLABS) ((SLABS) <= 3 ? 3 : 2)      // resident CTAs the register allocation must allow, by shared-memory slabs
+#endif
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(16 * R2, DLSG_PCOLS_FWD_MINB(E * MB + XB))
 sense_cols_fwd_lines_p_kernel(const float2* __restrict__ x, const DLSG_GRID_CONSTANT TileMap maps_tm,
                               float2* __restrict__ tl_out, LinePlan lp, SenseDims d) {
     using Cfg = PColCfg<R2>;
@@ -168,6 +176,7 @@ sense_cols_fwd_lines_p_kernel(const float2* __restrict__ x, const DLSG_GRID_CONS
         __syncthreads();                                         // bins visible; everyone has read the map slab
         if (tid == 0 && c + MB < d.C)
             tma_maps<R2, E>(mslab + (size_t)mb * E * Cfg::SLAB, &maps_tm, b, c + MB, d.C, who.kx0, bars + mb);
+#ifdef DLSG_PCOLS_GATHER_BY_CLASS
         float2* outp = tl_out + idx_lines(d, lp.lmax, b, c, t, 0) + kx;
         for (int wi = j; wi < m; wi += R2) {                     // this thread's (class, column) items
             const int k1 = lt.clist[wi];
@@ -190,6 +199,25 @@ sense_cols_fwd_lines_p_kernel(const float2* __restrict__ x, const DLSG_GRID_CONS
                 outp[(size_t)lt.order[q] * d.X] = pc_fma_w(w1, w2, ao, ae);                   // even + w * odd
             }
         }
+#else
+        // item = (sorted line q, column): n * 16 items over the NT threads; every thread takes the same number of rounds
+        // (the last one partly idle), so the warps reach the next barrier together
+        float2* outp = tl_out + idx_lines(d, lp.lmax, b, c, t, 0) + who.kx0;
+        for (int item = tid; item < n * 16; item += NT) {
+            const int q = item >> 4, cl = item & 15;
+            const float2* zp = ex + lt.k1q[q] + cl;
+            const float4 wa = lt.wq[2 * q], wb = lt.wq[2 * q + 1];
+            const float2 w1 = make_float2(wa.x, wa.y), w2 = make_float2(wa.z, wa.w);          // w
+            const float2 v1 = make_float2(wb.x, wb.y), v2 = make_float2(wb.z, wb.w);          // w^2
+            float2 ae = zp[(R2 - 2) * 16], ao = zp[(R2 - 1) * 16];
+#pragma unroll
+            for (int jj = R2 - 4; jj >= 0; jj -= 2) {
+                ae = pc_fma_w(v1, v2, ae, zp[jj * 16]);          // ae <- z[jj] + w^2 ae
+                ao = pc_fma_w(v1, v2, ao, zp[(jj + 1) * 16]);
+            }
+            outp[(size_t)lt.order[q] * d.X + cl] = pc_fma_w(w1, w2, ao, ae);                  // even + w * odd
+        }
+#endif
     }
 }
 
