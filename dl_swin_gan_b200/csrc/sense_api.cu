@@ -1,6 +1,9 @@
 // C-ABI entry points of the SENSE operator (declared in include/dlsg_b200.h):
 // argument checks, chunking of the L2-resident intermediate, kernel selection by
-// axis length, launches.  No allocation, no synchronisation, no global state.
+// axis length, launches.  No device allocation and no synchronisation on the normal paths; the only process-wide
+// state is a launch counter (statistics for bench.py) and the cached driver entry point of the TMA descriptor encoder.
+// One exception, documented in include/dlsg_b200.h: when the caller's workspace is smaller than the problem the dense
+// path pipelines chunks on a temporary side stream (created and destroyed inside the call, never during graph capture).
 #include "../../include/dlsg_b200.h"
 #include "sense_kernels.cuh"
 #include "sense_lines.cuh"
@@ -246,7 +249,11 @@ int run(Op op, const float2* in, const float2* maps, const float* w, const long 
     // Pipelined mode: when the workspace cannot hold the whole problem, split it into two slots and let the drain
     // of chunk k (second stream) overlap the fill of chunk k+1, so that a slot sized to a fraction of the 126 MB L2
     // is re-read from L2 instead of HBM and launch gaps / partial waves of one stage are covered by the other.
-    if (need_tmp && count_chunks(bchunk, tcount) > 1 && workspace_bytes / 2 >= per_bt) {
+    // (not while the caller's stream is being captured into a CUDA graph: the side stream would be destroyed inside the
+    // capture; the serial chunk walk below is used instead)
+    cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(p.stream, &capture) != cudaSuccess) { (void)cudaGetLastError(); capture = cudaStreamCaptureStatusActive; }
+    if (capture == cudaStreamCaptureStatusNone && need_tmp && count_chunks(bchunk, tcount) > 1 && workspace_bytes / 2 >= per_bt) {
         long long bch2, tc2;
         chunk_shape(workspace_bytes / 2, bch2, tc2);
         if (count_chunks(bch2, tc2) >= 3) {
@@ -269,17 +276,18 @@ int run(Op op, const float2* in, const float2* maps, const float* w, const long 
                     Problem qa = p, qb = p;
                     qa.tmp = qb.tmp = p.tmp + (size_t)slot * slot_elems;
                     qa.stream = sa; qb.stream = sb;
-                    if (used[slot]) cudaStreamWaitEvent(sa, ev2[slot], 0);   // the slot has been drained
+                    // a failed record / wait would turn into a silent race on the slot: every call is checked
+                    if (used[slot] && cudaStreamWaitEvent(sa, ev2[slot], 0) != cudaSuccess) { rc = -1; break; }   // the slot has been drained
                     rc = stage1(c, qa);
-                    cudaEventRecord(ev1[slot], sa);
-                    cudaStreamWaitEvent(sb, ev1[slot], 0);
+                    if (rc == 0 && (cudaEventRecord(ev1[slot], sa) != cudaSuccess || cudaStreamWaitEvent(sb, ev1[slot], 0) != cudaSuccess)) rc = -1;
                     if (rc == 0) rc = stage2(c, qb);
-                    cudaEventRecord(ev2[slot], sb);
-                    used[slot] = true;
+                    if (rc == 0 && cudaEventRecord(ev2[slot], sb) != cudaSuccess) rc = -1;
+                    used[slot] = (rc == 0);
                 }
             }
             for (int i = 0; i < 2; ++i)
-                if (used[i]) cudaStreamWaitEvent(sa, ev2[i], 0);             // join: later work on the caller's stream sees the results
+                if (used[i] && cudaStreamWaitEvent(sa, ev2[i], 0) != cudaSuccess) rc = -1;   // join: later work on the caller's stream sees the results
+            if (rc != 0) cudaStreamSynchronize(sb);                         // error path: nothing of the side stream may outlive this call
             for (int i = 0; i < 2; ++i) { if (ev1[i]) cudaEventDestroy(ev1[i]); if (ev2[i]) cudaEventDestroy(ev2[i]); }
             if (sb) cudaStreamDestroy(sb);                                    // deferred by the runtime until its work has drained
             return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;

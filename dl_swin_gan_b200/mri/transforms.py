@@ -12,7 +12,7 @@ Sampled lines: when the weights are a k-t sampling mask (whole ky lines of W are
 `get_mask` of undersampled data gives, dl_cs/mri/utils.py:69-79) the operator runs the Y transform first and
 keeps only the lines that carry weight (csrc/sense_lines.cuh); same results, a fraction of the HBM traffic.
 The plan is built on first use (one pass over W and one scalar read-back) and cached with the weights.
-`DLSG_SAMPLED_LINES=0` forces the dense kernels (`=force` also takes the path for E > 1, where it is the slower one).  On that path `A(y, adjoint=True)` also accepts a k-space that was
+`DLSG_SAMPLED_LINES=0` forces the dense kernels (`=force` also takes the path for E > 2, where it is the slower one).  On that path `A(y, adjoint=True)` also accepts a k-space that was
 left in *pinned host memory*: the kernels read its sampled lines straight over PCIe, so the zero-filled k-space
 (the bulk of a reconstruction's input, scripts/reconstruct.py:132-171) never needs a dense device copy.
 
@@ -51,6 +51,19 @@ def _require_cuda_c64(t: torch.Tensor, what: str) -> None:
 # low-level launcher shared by SenseModel and FFT
 # --------------------------------------------------------------------------------------
 _LINES_MAX_FRACTION = 0.5      # use the sampled-line kernels when at most this share of the ky lines carries weight
+
+# Host-resident k-space handed to the asynchronous line gather: (tensor, event recorded after the launch).  The kernel
+# reads the pinned buffer over PCIe after the call has returned, so the buffer must neither be freed nor recycled by
+# torch's pinned-memory allocator before that event has completed; entries are dropped once it has.
+_HOST_INFLIGHT = []
+
+
+def _retain_host_buffer(t: torch.Tensor, device) -> None:
+    _HOST_INFLIGHT[:] = [(h, e) for (h, e) in _HOST_INFLIGHT if not e.query()]
+    ev = torch.cuda.Event()
+    with torch.cuda.device(device):
+        ev.record(torch.cuda.current_stream())
+    _HOST_INFLIGHT.append((t, ev))
 
 
 def _sampled_lines_enabled() -> bool:
@@ -225,7 +238,9 @@ class SenseModel(nn.Module):
         else:
             self.weights = weights
         self._maps5 = None
+        self._maps_key = None
         self._w32 = None
+        self._w_key = None
         self._line_plans = {}
 
     # ---- reference interface ---------------------------------------------------------
@@ -260,13 +275,24 @@ class SenseModel(nn.Module):
         return _DcFn.apply(x, aty, step, self)
 
     # ---- preparation -------------------------------------------------------------------
+    @staticmethod
+    def _tensor_key(t):
+        """Identity of a tensor's current contents: object, storage address and in-place version (None inside inference mode)."""
+        try:
+            ver = t._version
+        except RuntimeError:               # inference tensors do not track versions
+            ver = None
+        return (id(t), t.data_ptr(), ver)
+
     def _prepared_maps(self) -> torch.Tensor:
-        if self._maps5 is None:
+        key = self._tensor_key(self.maps)
+        if self._maps5 is None or key != self._maps_key or key[2] is None:
             m = self.maps
             _require_cuda_c64(m, "SenseModel maps")
             if m.dim() != 6 or m.shape[3] != 1:
                 raise ValueError(f"maps must be [batch, emaps, coils, 1, y, x]; got {tuple(m.shape)}")
             self._maps5 = m.detach()[:, :, :, 0].contiguous()
+            self._maps_key = key
         return self._maps5
 
     def _prepared_weights(self, dims, device):
@@ -276,10 +302,13 @@ class SenseModel(nn.Module):
         if not isinstance(w, torch.Tensor):
             if float(w) == 1.0:
                 return None
-            if self._w32 is None:
+            if self._w32 is None or self._w_key != ("scalar", float(w)):
                 self._w32 = torch.full((1,), float(w), dtype=torch.float32, device=device)
+                self._w_key = ("scalar", float(w))
+                self._line_plans = {}
             return self._w32.expand(B, C, T, Y, X)
-        if self._w32 is None:
+        key = self._tensor_key(w)
+        if self._w32 is None or key != self._w_key or key[2] is None:     # `A.weights` reassigned or edited in place: re-derive
             if torch.is_complex(w):
                 raise TypeError("SenseModel weights must be real (the reference documents a float mask)")
             if not w.is_cuda:
@@ -288,6 +317,8 @@ class SenseModel(nn.Module):
             if w32.dtype != torch.float32:
                 w32 = w32.to(torch.float32)
             self._w32 = w32
+            self._w_key = key
+            self._line_plans = {}                                          # plans describe the previous weights
         w32 = self._w32
         if w32.dim() > 5:
             raise ValueError(f"weights must broadcast to [batch, coils, t, y, x]; got {tuple(w32.shape)}")
@@ -296,17 +327,15 @@ class SenseModel(nn.Module):
     def _line_plan(self, dims, wexp, ndims, any_emaps=False):
         """-> (plan, lmax) when the weights leave at most half of the ky lines sampled, else None (dense kernels).
 
-        With more than one ESPIRiT map set the sampled-line column kernels read the extra sets through the cache and
-        measure slower than the dense kernels (tools/compare_paths.py), so E > 1 stays dense unless `any_emaps`
-        (the host-resident k-space adjoint, which only exists on this path)."""
+        One and two ESPIRiT map sets (every reference configuration) run the second-generation column kernels; with more
+        the first-generation kernels read the extra sets through the cache and measure slower than the dense kernels
+        (tools/compare_paths.py), so E > 2 stays dense unless `any_emaps` (the host-resident k-space adjoint, which only
+        exists on this path)."""
         if wexp is None or ndims != 2 or not isinstance(self.weights, torch.Tensor) or not _sampled_lines_enabled():
             return None
-        if dims[1] != 1 and not any_emaps and os.environ.get("DLSG_SAMPLED_LINES") != "force":
+        if dims[1] > 2 and not any_emaps and os.environ.get("DLSG_SAMPLED_LINES") != "force":
             return None
         key = tuple(dims)
-        stamp = (self._w32.data_ptr(), self._w32._version)             # weights modified in place: rebuild the plan
-        if self._line_plans.get("stamp") != stamp:
-            self._line_plans = {"stamp": stamp}
         if key not in self._line_plans:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError(
@@ -367,7 +396,13 @@ class SenseModel(nn.Module):
             raise RuntimeError(
                 "host-resident k-space is only read in place by the sampled-line kernels (weights with empty ky lines, "
                 "2-D, 32*R axes); move the k-space to the device for this operator")
-        return _launch_lines("adj_host", data.detach().contiguous(), maps5, wexp, dims, lines)
+        if not data.is_contiguous():
+            # .contiguous() would make a pageable copy the GPU cannot read: ask for the right buffer instead
+            raise ValueError("host-resident k-space must be a contiguous pinned tensor (a strided view of a pinned tensor is not)")
+        host = data.detach()
+        out = _launch_lines("adj_host", host, maps5, wexp, dims, lines)
+        _retain_host_buffer(host, maps5.device)        # keeps the pinned buffer alive until the gather has run
+        return out
 
     def _run(self, kind: str, data: torch.Tensor, aty=None, step=None) -> torch.Tensor:
         if kind == "adj" and not data.is_cuda and data.is_pinned():

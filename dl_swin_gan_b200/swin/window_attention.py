@@ -334,8 +334,7 @@ class SwinTransformerBlock3D(nn.Module):
         window_size, shift_size = get_window_size((D, H, W), self.window_size, self.shift_size)
         shifted = any(i > 0 for i in shift_size)
         Dp, Hp, Wp = (-(-n // w) * w for n, w in zip((D, H, W), window_size))
-        fused = (isinstance(self.norm1, nn.LayerNorm) and not (torch.is_grad_enabled() and (
-            x.requires_grad or any(p.requires_grad for p in self.parameters()))))
+        fused = isinstance(self.norm1, nn.LayerNorm) and self._inference(x)
         if fused:
             _require_cuda_f32(x, "SwinTransformerBlock3D input")
             rid = _region_ids_for(mask_matrix, Dp, Hp, Wp, window_size, shift_size, x.device) if shifted else None
@@ -423,6 +422,10 @@ class SwinTransformerBlock3D(nn.Module):
         return y
 
     def _inference(self, x) -> bool:
+        """True when the fused kernels may run: no gradient is needed and no dropout would fire (a module in train()
+        mode under no_grad still applies attn_drop / proj_drop in the reference)."""
+        if self.training and (self.attn.attn_drop.p > 0 or self.attn.proj_drop.p > 0):
+            return False
         return not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())))
 
     def _qkv_f16_weight(self):
@@ -463,7 +466,7 @@ class SwinTransformerBlock3D(nn.Module):
               and (mlp.drop.p == 0 or not self.training)
               and (isinstance(self.drop_path, nn.Identity) or not self.training))
         if not (ok and x.shape[-1] == C and mlp.fc2.in_features == Hd and mlp.fc2.out_features == C
-                and C % 32 == 0 and C <= 256 and Hd % C == 0 and self.norm2.weight is not None
+                and C % 32 == 0 and C <= 256 and Hd % C == 0 and self.norm2.weight is not None and self.norm2.bias is not None
                 and max(256 * C, 33792) + 2 * C * C + 4 * Hd + 2200 <= 113 * 1024):
             return None
         _require_cuda_f32(x, "SwinTransformerBlock3D input")

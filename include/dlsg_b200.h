@@ -105,11 +105,17 @@ int dlsg_sense_dc_step_c64(const void* x, const void* aty, const void* maps, con
  * points above compute (for finite data: 0 * k contributes 0 in both), with an intermediate of
  * lmax lines per image instead of Y.  2-D only (ndims == 2), Y and X in {32..320 step 32*R} as
  * accepted by dlsg_sense_lines_supported; everything else stays on the dense entry points.
+ * For Y in {128, 160, 192, 256, 320} and E <= 2 the column passes are the second-generation kernels
+ * (packed FP32x2 butterflies, pruned radix stage, coil maps staged by TMA: csrc/sense_lines_p.cuh); the environment
+ * variable DLSG_LINES_KERNELS=v1 selects the first generation (csrc/sense_lines.cuh) for A/B runs.
  * ------------------------------------------------------------------------------------------------ */
 
 /* Bytes of the device-resident line plan for B slices of T frames with Y lines:
- * int32 counts[B*T] | list[B*T*Y] | pos[B*T*Y]   (n(b,t) = counts; list = sampled ky ascending;
- * pos[ky] = index of ky in list or -1). */
+ * int32 counts[B*T] | list[B*T*Y] | pos[B*T*Y] | order[B*T*Y] | cls[B*T*36] | float wq[B*T*Y*8]
+ *   n(b,t) = counts; list = sampled ky ascending; pos[ky] = index of ky in list or -1;
+ *   order / cls / wq = the same lines grouped by ky mod 16 with their unit roots exp(-2 pi i ky / Y) and squares:
+ *   tables of the pruned column transforms (csrc/sense_lines_p.cuh), built here once instead of in every CTA.
+ * Only counts[] is meant to be read by the caller (to obtain lmax). */
 size_t dlsg_sense_line_plan_bytes(int B, int T, int Y);
 
 /* Builds the plan from the weights (same addressing as above; one pass over W, run once per
@@ -137,7 +143,11 @@ int dlsg_sense_adjoint_lines_c64(const void* k, const void* maps, const float* w
 /* Same adjoint for a k-space that need not be in device memory: `k` is any address the device can read, in
  * particular pinned (mapped) host memory, i.e. the zero-filled k-space as the reference's loader leaves it on the
  * host (scripts/reconstruct.py:132-171).  Its sampled lines are first copied into the workspace (16-byte loads
- * straight from `k`), so only those lines cross PCIe and the dense k-space never needs a device copy. */
+ * straight from `k`), so only those lines cross PCIe and the dense k-space never needs a device copy.
+ * LIFETIME: the call only enqueues work; `k` is read when the gather kernel runs on `stream`.  The caller must keep
+ * the buffer alive and unmodified until work enqueued on `stream` after this call has completed (record an event after
+ * the call and release / recycle the buffer only when it has fired).  `k` must be a device-readable contiguous
+ * [B,C,T,Y,X] array (pinned + mapped host memory or device memory); pageable memory faults. */
 int dlsg_sense_adjoint_lines_gather_c64(const void* k, const void* maps, const float* weights, const long long* w_strides,
                                         const void* plan, int lmax, void* x_out, void* workspace, size_t workspace_bytes,
                                         int B, int E, int C, int T, int Y, int X, void* stream);

@@ -14,6 +14,7 @@ import numpy as np
 # name -> (preset, overrides of MODEL.PARAMETERS, (B, C, T, Y, X), acceleration)
 MODEL_CASES = {
     "swin_pgd_2unroll": ("config_swin", {"NUM_UNROLLS": 2}, (1, 4, 20, 64, 64), 4),
+    "swin_pgd_5unroll": ("config_swin", {}, (1, 4, 12, 48, 48), 4),          # all five unrolls; T = 12 -> depth 5 < 7: clamped window
     "resnet_pgd_example": ("example", {}, (1, 8, 20, 64, 48), 6),
     "resnet_pgd_recon": ("config_recon", {}, (2, 6, 12, 96, 64), 8),
     "resnet_hqs_example": ("example", {"MODL": {"NUM_CG_STEPS": 4, "MU": 0.1, "FIX_PENALTY": False}, "NUM_UNROLLS": 2},

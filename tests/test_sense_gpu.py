@@ -159,6 +159,35 @@ def test_sampled_line_path_is_selected_and_agrees_with_dense(dev, monkeypatch):
     assert A._line_plans[(B, E, C, T, Y, X)] is None                      # more than half of the lines sampled: dense kernels
 
 
+@pytest.mark.parametrize("E", [1, 2])
+def test_column_kernel_generations_agree(dev, monkeypatch, E):
+    """Second-generation column kernels (packed butterflies, pruned radix stage, TMA-staged maps; E <= 2) against the
+    first generation (DLSG_LINES_KERNELS=v1) and the dense kernels, reference k-t mask (VDktMaskFunc, 16 lines of 192),
+    perfusion-like 256 x 256 included (R2 = 16)."""
+    from dl_swin_gan_b200.mri import SenseModel
+    from dl_swin_gan_b200.mri.subsample import VDktMaskFunc
+    for (B, C, T, Y, X, acc) in [(2, 8, 6, 192, 160, 12), (1, 5, 3, 256, 256, 8), (1, 3, 2, 160, 128, 10), (1, 2, 2, 320, 320, 12), (1, 2, 2, 128, 128, 4)]:
+        g = torch.Generator(device=dev).manual_seed(31 + Y)
+
+        def cn(*s):
+            return torch.view_as_complex(torch.randn(*s, 2, generator=g, device=dev))
+
+        maps = cn(B, E, C, 1, Y, X) / (E * C) ** 0.5
+        x, k, aty = cn(B, E, T, Y, X), cn(B, C, T, Y, X), cn(B, E, T, Y, X)
+        f = VDktMaskFunc((acc, acc), sim_partial_kx=0.25, sim_partial_ky=0.25)
+        mask = torch.cat([f((1, 1, T, Y, X), seed=3 + b) for b in range(B)], 0).to(dev)
+        outs = {}
+        for mode in ("gen2", "v1", "dense"):
+            monkeypatch.setenv("DLSG_SAMPLED_LINES", "0" if mode == "dense" else "force")
+            monkeypatch.setenv("DLSG_LINES_KERNELS", "v1" if mode == "v1" else "")
+            A = SenseModel(maps, weights=mask)
+            outs[mode] = [A(x), A(k, adjoint=True), A.normal(x), A.dc_step(x, aty, -2.0), A.normal_reg(x, 0.3)]
+            assert (A._line_plans.get((B, E, C, T, Y, X)) is not None) == (mode != "dense")
+        for a, b, c in zip(outs["gen2"], outs["v1"], outs["dense"]):
+            assert rel_l2(to_np(a), to_np(c)) < 2e-6 and rel_l2(to_np(b), to_np(c)) < 2e-6
+    monkeypatch.delenv("DLSG_LINES_KERNELS")
+
+
 def test_adjoint_reads_pinned_host_kspace_in_place(dev, monkeypatch):
     """A(y, adjoint=True) with y in pinned host memory == the same with y copied to the device (bit for bit);
     pageable host memory, dense weights and the dense kernels refuse instead of falling back to a CPU path."""
@@ -178,6 +207,14 @@ def test_adjoint_reads_pinned_host_kspace_in_place(dev, monkeypatch):
     assert rel_l2(to_np(got2), so.sense_adjoint(k.astype(np.complex128), maps2.astype(np.complex128), mask)) < TOL
     with pytest.raises(RuntimeError):
         A(torch.from_numpy(k), adjoint=True)                   # pageable memory: no CPU fallback
+    with pytest.raises(ValueError):
+        A(hk[:, :, ::2], adjoint=True)                         # strided view of a pinned tensor: .contiguous() would be pageable
+    # the kernel reads the pinned buffer after the call returns: a temporary must stay alive until then
+    from dl_swin_gan_b200.mri import transforms as tr
+    tmp = A(torch.from_numpy(k).pin_memory(), adjoint=True)    # the pinned temporary is dropped by the caller right here
+    scratch = [torch.from_numpy(k * 0 + 7).pin_memory() for _ in range(3)]      # would recycle a freed pinned block
+    assert torch.equal(tmp, got) and len(tr._HOST_INFLIGHT) >= 1
+    del scratch
     with pytest.raises(RuntimeError):
         make_model(maps, np.ones_like(mask), dev)(hk, adjoint=True)      # every line sampled: dense kernels need a device copy
     monkeypatch.setenv("DLSG_SAMPLED_LINES", "0")
@@ -284,7 +321,7 @@ def test_autograd_vjp_is_the_adjoint(dev, E):
     want = torch.autograd.grad(ref, (x2, aty2, step2), grad_outputs=go)
     for a, b in zip(got, want):
         assert rel_l2(to_np(a), to_np(b)) < 1e-5
-    assert (A._line_plans.get((B, E, C, T, Y, X)) is not None) == (E == 1)
+    assert (A._line_plans.get((B, E, C, T, Y, X)) is not None) == (E <= 2)
 
 
 def test_fft_module_matches_reference_vectors(dev):
