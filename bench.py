@@ -1,21 +1,25 @@
 #!/usr/bin/env python
-"""Benchmark of the SENSE data-consistency hot path (BASELINE.json configs[1]).
+"""Benchmark of the SENSE data-consistency hot path and of the unrolled reconstructions around it.
 
-Workload (config.workload = "config_recon.yaml"): unrolled-network inference on a batch of 64
-synthetic cine slices per GPU — E=1 map set, 8 coils, 20 frames, 192x160, 12x k-t mask, NUM_UNROLLS=5
-(/root/reference/configs/config_recon.yaml:5-17).  One *step* is one pass of the hot path over that
-batch: ATy = A^H y, then 5 data-consistency updates x <- x + s (A^H A x - ATy)
-(dl_cs/models/unrolled.py:96-104), through the reference-facing API (SenseModel + the PGD loop mirror).
-The denoiser between the updates is not part of this path and is not run.
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME] [--scaling weak|strong]
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+Workloads (BASELINE.json `configs`):
+  config_recon (default, configs[1])  unrolled-network inference on 64 synthetic cine slices per GPU - E=1 map set, 8 coils,
+      20 frames, 192x160, 12x k-t mask from the reference's VDktMaskFunc, NUM_UNROLLS=5
+      (/root/reference/configs/config_recon.yaml:5-17).  One *step* = one pass of the hot path over the batch: ATy = A^H y, then
+      5 data-consistency updates x <- x + s (A^H A x - ATy) (dl_cs/models/unrolled.py:96-104) through the reference-facing API
+      (SenseModel + the PGD loop); the denoiser is not part of this path.
+  recon_resnet   the same data through the whole ResNet unrolled network of config_recon.yaml (denoiser included).
+  swin_recon     BASELINE.json's headline: the Swin unrolled reconstruction of config_swin.yaml (E=2, 5 unrolls, 160 features).
+  example        configs/basic/example.yaml (ResNet, E=2).      perfusion   Swin reconstruction at 32 coils, 40 frames, 256x256.
 
-Prints ONE JSON line (rank 0).  `value` = slices/s with inputs resident in HBM; `e2e` = the same through
-the same API from pinned host buffers (H2D of y/maps/mask and D2H of x inside the timed region);
-`roofline` = the dominant SENSE op (the fused DC step) in algorithmic GB/s against the measured HBM
-peak; `ops` gives forward / adjoint / normal too; `cpu_baseline` = the torch-CPU port of the
-reference path (oracle/sense_oracle_torch.py) on a bounded sample.  `--impl reference` times only
-that CPU port (the Python reference itself cannot travel to the GPU box; kind "port").
+Prints ONE JSON line (rank 0).  `value` = slices/s with inputs resident in HBM; `e2e` = the same through the same API from
+pinned host buffers (H2D of y / maps / mask and D2H of x inside the timed region); `roofline` = the dominant SENSE op (the
+fused DC step) in algorithmic GB/s against the measured HBM peak; `ops` gives forward / adjoint / normal too; `torch_eager_gpu`
+= the reference's arithmetic as plain torch ops on the same GPU; `full_recon` = whole reconstructions with the time split;
+`attention` = the Swin block's tensor-core side; `cpu_baseline` = the torch-CPU port of the reference path
+(oracle/sense_oracle_torch.py) on a bounded sample.  `--impl reference` times only that CPU port (the Python reference itself
+cannot travel to the GPU box; kind "port"), whole steps on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -32,12 +36,27 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-WORKLOAD = dict(B=64, E=1, C=8, T=20, Y=192, X=160, unrolls=5, step=-2.0, accel=12)
-METRIC = "cine slices/sec (SENSE data-consistency path of the unrolled recon)"
 UNIT = "slices/s"
+MASK_NOTE = "VDktMaskFunc((R, R), sim_partial_kx=0.25, sim_partial_ky=0.25), seed 1000 + slice index"
+# name -> (metric, preset of dl_swin_gan_b200.config or None, problem)
+WORKLOADS = {
+    "config_recon": ("cine slices/sec (SENSE data-consistency path of the unrolled recon)", None,
+                     dict(B=64, E=1, C=8, T=20, Y=192, X=160, unrolls=5, step=-2.0, accel=12)),
+    "recon_resnet": ("cine slices/sec (unrolled ResNet recon, config_recon.yaml)", "config_recon",
+                     dict(B=16, E=1, C=8, T=20, Y=192, X=160, unrolls=5, step=-2.0, accel=12)),
+    "swin_recon": ("cine slices/sec (unrolled Swin recon)", "config_swin",
+                   dict(B=4, E=2, C=8, T=20, Y=192, X=160, unrolls=5, step=-2.0, accel=12)),
+    "example": ("cine slices/sec (unrolled ResNet recon, example.yaml)", "example",
+                dict(B=16, E=2, C=8, T=20, Y=192, X=160, unrolls=5, step=-2.0, accel=12)),
+    "perfusion": ("perfusion slices/sec (unrolled Swin recon)", "config_swin",
+                  dict(B=1, E=2, C=32, T=40, Y=256, X=256, unrolls=5, step=-2.0, accel=8)),
+}
+CONFIG_FILE = {"config_recon": "config_recon.yaml", "recon_resnet": "config_recon.yaml", "swin_recon": "config_swin.yaml",
+               "example": "basic/example.yaml", "perfusion": "config_swin.yaml (perfusion-shaped data)"}
+WORKLOAD = WORKLOADS["config_recon"][2]       # tools/ import the default problem under this name
 
 
-# --------------------------------------------------------------------------- algorithmic bytes (SURVEY.md §8d)
+# --------------------------------------------------------------------------- algorithmic bytes (SURVEY.md 8d)
 def algorithmic_bytes(op: str, B, E, C, T, Y, X, mask_elems) -> int:
     P = B * T * Y * X
     maps = 8 * B * E * C * Y * X
@@ -62,8 +81,9 @@ def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+            j = json.load(f)
+        return float(j["hbm_gbs"]), float(j.get("bf16_tflops_sustained", 1413.6)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1413.6, "fallback (B200_PROFILING.md)"
 
 
 # --------------------------------------------------------------------------- clocks
@@ -132,7 +152,7 @@ def make_mask(B, T, Y, X, accel, seed):
 
 
 def device_problem(cfg, dev, seed):
-    """maps, mask, y = mask * A_full(x_true) generated on the device (seed 1000 + rank)."""
+    """maps, mask, y = mask * A_full(x_true) generated on the device (seed 1000 + first slice index)."""
     from dl_swin_gan_b200.mri import SenseModel
     B, E, C, T, Y, X = (cfg[k] for k in "BECTYX")
     g = torch.Generator(device=dev).manual_seed(seed)
@@ -148,50 +168,99 @@ def device_problem(cfg, dev, seed):
 
 
 # --------------------------------------------------------------------------- CPU port arm
-def cpu_port_rate(cfg, seconds_target=12.0):
-    """slices/s of the torch-CPU port of the reference path on a bounded sample of the workload."""
-    from oracle import sense_oracle_torch as st
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
+def cpu_problem(cfg, nb):
     E, C, T, Y, X = (cfg[k] for k in "ECTYX")
     g = torch.Generator().manual_seed(1000)
 
     def cn(*s):
         return torch.view_as_complex(torch.randn(*s, 2, generator=g)) * (0.5 ** 0.5)
 
-    nb = 1
     maps = cn(nb, E, C, 1, Y, X) / (E * C) ** 0.5
     mask = torch.from_numpy(make_mask(nb, T, Y, X, cfg["accel"], 1000))
     y = mask * cn(nb, C, T, Y, X)
-    st.dc_path(y, maps, mask, 1, cfg["step"])            # warm-up (thread pool, FFT plans)
+    return maps, mask, y
+
+
+def cpu_step_fn(workload, cfg, nb):
+    """One bounded 'step' of the reference path on the CPU: nb slices through the torch-CPU port (kind "port")."""
+    from oracle import sense_oracle_torch as st
+    maps, mask, y = cpu_problem(cfg, nb)
+    preset = WORKLOADS[workload][1]
+    if preset is None:
+        return lambda: st.dc_path(y, maps, mask, cfg["unrolls"], cfg["step"])
+    if preset == "config_swin":
+        return None                        # the Swin mirror has no CPU path (its blocks are CUDA kernels); no CPU arm for it
+    from dl_swin_gan_b200.config import load_cfg
+    from dl_swin_gan_b200.models import build_unrolled
+    torch.manual_seed(1000)
+    net = build_unrolled(load_cfg(preset)).eval()
+
+    class A:                               # the reference operator restated with torch.fft (oracle), duck-typed like SenseModel
+        def __call__(self, data, adjoint=False):
+            return st.adjoint(data, maps, mask) if adjoint else st.forward(data, maps, mask)
+
+    def step():
+        with torch.no_grad():
+            return net(y, A())
+    return step
+
+
+def cpu_port_rate(workload, cfg, seconds_target=12.0, nb=1):
+    """slices/s of the torch-CPU port of the reference path on a bounded sample of the workload."""
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    fn = cpu_step_fn(workload, cfg, nb)
+    if fn is None:
+        return None
+    fn()                                   # warm-up (thread pool, FFT plans)
     t0 = time.perf_counter()
     n = 0
     while True:
-        st.dc_path(y, maps, mask, cfg["unrolls"], cfg["step"])
+        fn()
         n += nb
         el = time.perf_counter() - t0
         if el > seconds_target or n >= 4096:
             break
-    return n / el, threads, f"{n} slice(s) of the batch through A^H y + {cfg['unrolls']} DC updates, {el:.1f} s"
+    return n / el, threads, f"{n} slice(s) of the batch through the whole step, {el:.1f} s"
+
+
+def base_config(workload, cfg):
+    """The keys both arms print (identical by construction)."""
+    return {"workload": CONFIG_FILE[workload], "name": workload,
+            **{k: cfg[k] for k in ("B", "E", "C", "T", "Y", "X", "unrolls", "step", "accel")}, "mask": MASK_NOTE}
 
 
 def run_reference_arm(args, rank):
-    cfg = dict(WORKLOAD)
+    metric, _, problem = WORKLOADS[args.workload]
+    cfg = dict(problem)
+    if args.batch:
+        cfg["B"] = args.batch
     if rank != 0:
         return
-    rates = []
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    nb = max(1, min(cfg["B"], 4 if WORKLOADS[args.workload][1] is None else 1))     # slices per timed step: a bounded sample of the batch
+    fn = cpu_step_fn(args.workload, cfg, nb)
+    if fn is None:
+        print(json.dumps({"impl": "reference", "metric": metric, "unit": UNIT, "n_gpus": args.gpus,
+                          "unavailable": "the Swin unrolled network has no CPU port here (its blocks are CUDA kernels) and the "
+                                         "Python reference cannot travel to the GPU box"}), flush=True)
+        return
     for _ in range(max(1, args.warmup)):
-        pass                                              # the port warms itself up inside cpu_port_rate
-    budget = max(2.0, min(20.0, 60.0 / max(1, args.steps)))
+        fn()
+    times = []
     for _ in range(args.steps):
-        rate, threads, sample = cpu_port_rate(cfg, seconds_target=budget)
-        rates.append(rate)
-    value = float(np.mean(rates))
+        t0 = time.perf_counter()
+        fn()
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))                   # measured: one step = nb slices through the whole path
+    value = nb / (ms * 1e-3)
+    sample = f"each step = {nb} slice(s) of the {cfg['B']}-slice batch through the whole path on {threads} threads"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cfg["B"] / value,
+        "impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "step_slices": nb,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (complex64)",
-        "data": "synthetic", "config": {"workload": "config_recon.yaml", **cfg},
+        "data": "synthetic", "config": base_config(args.workload, cfg),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -200,7 +269,7 @@ def run_reference_arm(args, rank):
 
 
 # --------------------------------------------------------------------------- window attention (second half of the hot path)
-def swin_block_timing(dev, slices=8):
+def swin_block_timing(dev, tensor_peak, slices=8):
     """forward_part1 of one Swin block (LN, shift, partition, qkv, attention, proj, reverse) for `slices` cine slices at the
     hard-coded denoiser configuration (dim 160, 8 heads, window (7,8,8), feature volume 7x48x40), shifted block."""
     from dl_swin_gan_b200.swin import window_attention as wa
@@ -218,11 +287,16 @@ def swin_block_timing(dev, slices=8):
         ms_block = time_op(lambda: blk(x, mask), 10, dev)
     windows = slices * mask.shape[0]
     useful = windows * (2 * 448 * 160 * 480 + 4 * 448 * 448 * 160 + 2 * 448 * 160 * 160)      # qkv + QK^T/PV + proj
+    tf = useful / (ms * 1e-3) / 1e12
+    tf2 = 4.0 * x.numel() * 4 * C / (ms2 * 1e-3) / 1e12
     return {"what": "SwinTransformerBlock3D.forward_part1, shifted, fp16 tensor-core operands", "slices": slices,
-            "windows": windows, "ms": ms, "us_per_slice": 1e3 * ms / slices, "useful_TFLOPs": useful / (ms * 1e-3) / 1e12,
-            "launches_per_call": launches,
-            "part2_mlp_ms": ms2, "part2_useful_TFLOPs": 4.0 * x.numel() * 4 * C / (ms2 * 1e-3) / 1e12,
-            "whole_block_ms": ms_block, "whole_block_launches": 5}
+            "windows": windows, "ms": ms, "us_per_slice": 1e3 * ms / slices, "useful_TFLOPs": tf,
+            "launches_per_call": launches, "part2_mlp_ms": ms2, "part2_useful_TFLOPs": tf2,
+            "whole_block_ms": ms_block, "whole_block_launches": 5,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak,
+                         "mlp_frac": tf2 / tensor_peak,
+                         "note": "useful FLOPs (qkv + QK^T + PV + proj at head_dim 20, 448-token windows) over the sustained bf16 cuBLAS "
+                                 "rate; per-kernel tensor-pipe counters (ncu) are under profiles/"}}
 
 
 def _lib_launches():
@@ -230,7 +304,7 @@ def _lib_launches():
     return int(_lib.load().dlsg_launch_count())
 
 
-# --------------------------------------------------------------------------- main arm
+# --------------------------------------------------------------------------- helpers
 def time_op(fn, iters, dev):
     for _ in range(2):
         fn()
@@ -244,16 +318,95 @@ def time_op(fn, iters, dev):
     return s.elapsed_time(e) / iters   # ms
 
 
+def eager_dc_path(y, maps, mask, unrolls, step):
+    """The reference's arithmetic (transforms.py:84-98, unrolled.py:96-104) as plain torch ops on the same GPU: cuFFT + ATen.
+    This is the 'PyTorch eager on the same box' comparator of SURVEY.md 8d, not part of the product."""
+    def fwd(x):
+        return mask * torch.fft.fftn((x.unsqueeze(2) * maps).sum(1), dim=(-2, -1), norm="ortho")
+
+    def adj(k):
+        return (torch.fft.ifftn(mask * k, dim=(-2, -1), norm="ortho").unsqueeze(1) * torch.conj(maps)).sum(2)
+
+    aty = adj(y)
+    x = aty
+    for _ in range(unrolls):
+        x = x + step * (adj(fwd(x)) - aty)
+    return x
+
+
+def pin_to_gpu_numa_node(local_rank: int):
+    """Run this rank's threads (and therefore the first touch of its pinned buffers) on the CPUs of its GPU's NUMA node, so that
+    8 ranks do not share one node's DRAM and PCIe root for their host buffers.  Best effort; returns what was done."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        path = f"/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/"
+        node = int(open(path + "numa_node").read().strip())
+        cpus = open(path + "local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids.update(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"numa_node": node, "local_cpus": cpus, "pinned": bool(ids)}
+    except Exception as exc:                                     # containers without sysfs / affinity rights
+        return {"numa_node": None, "pinned": False, "why": str(exc)[:80]}
+
+
+# --------------------------------------------------------------------------- whole reconstructions
+def full_recon_timing(workload, dev, rank, batch=None, iters=3, precisions=("fp32", "tf32", "bf16")):
+    """slices/s of a whole unrolled reconstruction (DC steps + denoisers) with the time split, per convolution precision."""
+    from dl_swin_gan_b200.config import load_cfg
+    from dl_swin_gan_b200.models import build_unrolled, set_conv_precision, get_conv_precision
+    from dl_swin_gan_b200.mri import SenseModel
+    metric, preset, problem = WORKLOADS[workload]
+    cfg = dict(problem)
+    if batch:
+        cfg["B"] = batch
+    torch.manual_seed(1000)
+    net = build_unrolled(load_cfg(preset)).to(dev).eval()
+    maps, mask, y = device_problem(cfg, dev, 1000 + rank * cfg["B"])
+    A = SenseModel(maps, weights=mask)
+    out = {"metric": metric, "workload": CONFIG_FILE[workload], "slices": cfg["B"], "dims": {k: cfg[k] for k in "ECTYX"},
+           "params": sum(p.numel() for p in net.parameters()), "weights": "random initialisation (no checkpoints offline)"}
+    keep = get_conv_precision()
+    with torch.no_grad():
+        aty = A(y, adjoint=True)
+        t_dc = time_op(lambda: A.dc_step(aty, aty, net.step_size), iters, dev)
+        t_adj = time_op(lambda: A(y, adjoint=True), iters, dev)
+        out["sense_ms"] = {"adjoint": t_adj, "dc_step": t_dc, "per_recon": t_adj + cfg["unrolls"] * t_dc}
+        for prec in precisions:
+            set_conv_precision(prec)
+            t_all = time_op(lambda: net(y, A), iters, dev)
+            t_den = time_op(lambda: net.cnn_update[0](aty), iters, dev)
+            out[prec] = {"ms_per_batch": t_all, "slices_per_s": cfg["B"] / (t_all * 1e-3), "denoiser_ms": t_den,
+                         "denoiser_share": cfg["unrolls"] * t_den / t_all}
+    set_conv_precision(keep)
+    out["note"] = ("conv precision fp32 = true fp32 FMAs (default: keeps the reconstruction within 1e-3 NRMSE of the fp32 reference, "
+                   "tests/test_models.py); tf32 / bf16 = cuDNN tensor cores; the denoiser convolutions are cuDNN library calls (SURVEY.md 8f-1)")
+    return out
+
+
+# --------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=WORKLOAD["B"], help="slices per GPU (default: the config's 64)")
+    ap.add_argument("--workload", default="config_recon", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: B slices per GPU; strong: the B slices of the workload split over the ranks (slice_range)")
+    ap.add_argument("--batch", type=int, default=0, help="slices per GPU (default: the workload's)")
+    ap.add_argument("--conv-precision", default="fp32", choices=["fp32", "tf32", "bf16"], help="denoiser convolutions (full-recon workloads)")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-swin", action="store_true", help="skip the window-attention side measurement")
+    ap.add_argument("--skip-full", action="store_true", help="skip the whole-reconstruction side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -271,29 +424,46 @@ def main():
     from dl_swin_gan_b200 import _lib
     from dl_swin_gan_b200.mri import SenseModel
     from dl_swin_gan_b200.unrolled import ProximalGradientDescent
-    from dl_swin_gan_b200.sharding import max_over_ranks
+    from dl_swin_gan_b200.sharding import max_over_ranks, slice_range
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = pin_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = dict(WORKLOAD)
-    cfg["B"] = args.batch
-    B, E, C, T, Y, X = (cfg[k] for k in "BECTYX")
+    metric, preset, problem = WORKLOADS[args.workload]
+    cfg = dict(problem)
+    if args.batch:
+        cfg["B"] = args.batch
+    total_slices = cfg["B"] * world if args.scaling == "weak" else cfg["B"]
+    if args.scaling == "strong":
+        b0, b1 = slice_range(rank, world, cfg["B"])              # this rank's contiguous slice range of the one batch
+        cfg_local, first_slice = dict(cfg, B=b1 - b0), b0
+    else:
+        cfg_local, first_slice = dict(cfg), rank * cfg["B"]
+    B, E, C, T, Y, X = (cfg_local[k] for k in "BECTYX")
     lib = _lib.load()
+    hbm_peak, tensor_peak, peak_src = measured_peaks()
 
-    maps, mask, y = device_problem(cfg, dev, 1000 + rank)
+    maps, mask, y = device_problem(cfg_local, dev, 1000 + first_slice)
     A = SenseModel(maps, weights=mask)
-    pgd = ProximalGradientDescent(num_unrolls=cfg["unrolls"], step_init=cfg["step"]).to(dev)
+    if preset is None:
+        net = ProximalGradientDescent(num_unrolls=cfg["unrolls"], step_init=cfg["step"]).to(dev)
+    else:
+        from dl_swin_gan_b200.config import load_cfg
+        from dl_swin_gan_b200.models import build_unrolled, set_conv_precision
+        set_conv_precision(args.conv_precision)
+        torch.manual_seed(1000)
+        net = build_unrolled(load_cfg(preset)).to(dev).eval()
 
     def step():
         with torch.no_grad():
-            return pgd(y, A)
+            return net(y, A)
 
     def barrier():
         if dist is not None:
@@ -303,14 +473,13 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    # a fresh process / box needs more than three short steps to reach steady clocks and page everything in: keep warming up
-    # (untimed) until 0.5 s have passed; config.warmup_extra_steps reports how many steps that added to the W requested
     clocks = ClockSampler(local_rank)
     # The timed steps are replays of ONE CUDA graph captured from the same public-API calls: a host-side hiccup (GC, CPU
     # throttling of the container; seen as 10-50 ms gaps in eager launches on this pool, tools/stability_probe.py) then cannot
-    # starve the GPU inside the timed region.  DLSG_BENCH_EAGER=1 times eager launches instead.
-    use_graph = os.environ.get("DLSG_BENCH_EAGER", "0") != "1"
+    # starve the GPU inside the timed region.  Eager launches are timed right after, for comparison (`eager_ms_per_step`).
+    use_graph = os.environ.get("DLSG_BENCH_EAGER", "0") != "1" and preset is None
     per_step_launches = None
+    out = step()
     if use_graph:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -327,7 +496,8 @@ def main():
         def run_step():
             nonlocal out
             out = step()
-    out = out if use_graph else step()
+    # a fresh process / box needs more than three short steps to reach steady clocks and page everything in: keep warming up
+    # (untimed) until 0.5 s have passed; `run.warmup_extra_steps` reports how many steps that added to the W requested
     extra_warmup = 0
     t_w = time.perf_counter()
     while time.perf_counter() - t_w < 0.5:
@@ -345,51 +515,66 @@ def main():
     barrier()
     launches = args.steps * per_step_launches if use_graph else int(lib.dlsg_launch_count() - n0)
     ms_per_step = max_over_ranks(s_ev.elapsed_time(e_ev), dev) / args.steps      # device-timed, max over ranks
-    value = world * B / (ms_per_step * 1e-3)
+    value = total_slices / (ms_per_step * 1e-3)
+    eager_ms = None
+    if use_graph:                                                                # the same K steps as eager launches
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for _ in range(args.steps):
+            step()
+        e2.record()
+        barrier()
+        eager_ms = max_over_ranks(s2.elapsed_time(e2), dev) / args.steps
 
     # ---- per-op timings for the roofline (CUDA events on the launching stream, batch >> L2)
-    hbm_peak, peak_src = measured_peaks()
-    x0 = out
     aty = A(y, adjoint=True)
+    x0 = out
     ops = {}
     iters = 5
+    step_size = getattr(net, "step_size", torch.tensor([cfg["step"]], device=dev))
     with torch.no_grad():
         t_ms = {
             "forward": time_op(lambda: A(x0), iters, dev),
             "adjoint": time_op(lambda: A(y, adjoint=True), iters, dev),
             "normal": time_op(lambda: A.normal(x0), iters, dev),
-            "dc_step": time_op(lambda: A.dc_step(x0, aty, pgd.step_size), iters, dev),
+            "dc_step": time_op(lambda: A.dc_step(x0, aty, step_size), iters, dev),
         }
+    plan = A._line_plans.get((B, E, C, T, Y, X))
+    path = "sampled-lines" if plan is not None else "dense"
+    tpath = os.path.join(ROOT, "profiles", "r2_dram_traffic_per_slice.json")
+    traffic_tab = None
+    if os.path.exists(tpath) and (E, C, T, Y, X) == (1, 8, 20, 192, 160):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic_tab = tj.get("ops_MB_per_slice_sampled_lines" if plan is not None else "ops_MB_per_slice")
     for name, t in t_ms.items():
         nbytes = algorithmic_bytes(name, B, E, C, T, Y, X, mask.numel())
         ops[name] = {"ms": t, "algorithmic_MB_per_slice": nbytes / B / 1e6, "GBps": nbytes / (t * 1e-3) / 1e9,
                      "frac_hbm": nbytes / (t * 1e-3) / 1e9 / hbm_peak,
                      "TFLOPs_nominal": algorithmic_flops(name, B, E, C, T, Y, X) / (t * 1e-3) / 1e12}
+        if traffic_tab and name in traffic_tab:                 # what the kernels really move (ncu), next to the algorithmic figure
+            moved = traffic_tab[name] * 1e6 * B
+            ops[name]["dram_MB_per_slice_ncu"] = traffic_tab[name]
+            ops[name]["dram_GBps_ncu"] = moved / (t * 1e-3) / 1e9
+            ops[name]["dram_frac_hbm_ncu"] = moved / (t * 1e-3) / 1e9 / hbm_peak
     # the same ops on the dense kernels (what runs when W has no empty ky lines), for comparison
-    plan = A._line_plans.get((B, E, C, T, Y, X))
-    path = "sampled-lines" if plan is not None else "dense"
     ops_dense = None
     if plan is not None:
         os.environ["DLSG_SAMPLED_LINES"] = "0"
         with torch.no_grad():
             ops_dense = {"forward_ms": time_op(lambda: A(x0), iters, dev),
                          "adjoint_ms": time_op(lambda: A(y, adjoint=True), iters, dev),
-                         "dc_step_ms": time_op(lambda: A.dc_step(x0, aty, pgd.step_size), iters, dev)}
+                         "dc_step_ms": time_op(lambda: A.dc_step(x0, aty, step_size), iters, dev)}
         os.environ["DLSG_SAMPLED_LINES"] = "1"
     dom = "dc_step"
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic_per_slice.json")
-    tkey = "ops_MB_per_slice_sampled_lines" if plan is not None else "ops_MB_per_slice"
-    if os.path.exists(tpath) and (E, C, T, Y, X) == (1, 8, 20, 192, 160):
-        with open(tpath) as f:
-            tj = json.load(f)
-        if tkey in tj:
-            traffic = tj[tkey][dom] * 1e6 * B      # ncu-measured DRAM bytes per launch chain
-    chain = ("cols_fwd_lines + rows_lines<NORMAL> + cols_adj_lines" if plan is not None
-             else "rows_fwd + cols<NORMAL> + rows_adj")
+    chain = ("cols_fwd_lines_p (TMA-staged maps, packed radix-16, pruned radix stage) + rows_lines<NORMAL> + cols_adj_lines_p"
+             if plan is not None else "rows_fwd + cols<NORMAL> + rows_adj")
     roofline = {"bound": "hbm", "kernel": f"fused DC step chain ({chain})",
                 "achieved": ops[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": ops[dom]["frac_hbm"],
-                "traffic": traffic, "traffic_source": "ncu --set full, profiles/r1_dram_traffic_per_slice.json",
+                "traffic": (traffic_tab[dom] * 1e6 * B if traffic_tab and dom in traffic_tab else None),
+                "traffic_source": "ncu --set full at batch 16 (dram__bytes_read.sum + dram__bytes_write.sum per launch, scaled to this "
+                                  "launch's slices): profiles/r2_dram_traffic_per_slice.json",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algorithmic_bytes(dom, B, E, C, T, Y, X, mask.numel()),
                 # the fused DC step is FP32-issue-bound, not HBM-bound (no k-space in or out, two 2-D transforms per coil image):
@@ -398,19 +583,32 @@ def main():
                 "fp32_peak_TFLOPs": torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 2
                                     * (clocks.max_mhz or 1965) * 1e6 / 1e12}
 
+    # ---- the reference's own arithmetic as torch eager ops on this GPU (cuFFT + ATen), same inputs, bounded batch
+    eager = None
+    if rank == 0 and preset is None:
+        nb = min(B, 16)
+        with torch.no_grad():
+            t_e = time_op(lambda: eager_dc_path(y[:nb], maps[:nb], mask[:nb], cfg["unrolls"], cfg["step"]), 3, dev)
+            ref = eager_dc_path(y[:2], maps[:2], mask[:2], cfg["unrolls"], cfg["step"])
+            err = float((out[:2] - ref).norm() / ref.norm())
+        eager = {"what": "reference arithmetic (transforms.py:84-98, unrolled.py:96-104) as torch ops on the same GPU", "slices": nb,
+                 "ms": t_e, "slices_per_s": nb / (t_e * 1e-3), "speedup_of_this_repo": (B / (ms_per_step * 1e-3)) / (nb / (t_e * 1e-3)),
+                 "rel_l2_of_this_repo_vs_eager": err}
+
     # ---- end to end from pinned host memory through the same API
     e2e = None
-    if not args.skip_e2e:
+    if not args.skip_e2e and preset is None:
         hy = torch.empty(y.shape, dtype=y.dtype, pin_memory=True).copy_(y)
         hm = torch.empty(maps.shape, dtype=maps.dtype, pin_memory=True).copy_(maps)
-        hw = torch.empty(mask.shape, dtype=mask.dtype, pin_memory=True).copy_(mask)
+        # the 0/1 mask travels as uint8 (SenseModel converts real weights of any dtype to fp32 on the device)
+        hw = torch.empty(mask.shape, dtype=torch.uint8, pin_memory=True).copy_(mask)
         hx = torch.empty((B, E, T, Y, X), dtype=torch.complex64, pin_memory=True)
         d2h = hx.numel() * 8
 
-        # The batch goes through the same public API in chunks of 16 slices on two streams, so that the H2D traffic of
-        # chunk i+1 and the D2H copy of chunk i-1 overlap the reconstruction of chunk i (slices are independent).
-        # The zero-filled k-space stays in pinned host memory: A(y, adjoint=True) reads its sampled lines over PCIe
-        # (dlsg_sense_adjoint_lines_gather_c64); maps and mask are copied.  With dense weights it is copied as before.
+        # The batch goes through the same public API in chunks on two streams, so that the H2D traffic of chunk i+1 and the
+        # D2H copy of chunk i-1 overlap the reconstruction of chunk i (slices are independent).  The zero-filled k-space stays
+        # in pinned host memory: A(y, adjoint=True) reads its sampled lines over PCIe (dlsg_sense_adjoint_lines_gather_c64);
+        # maps and mask are copied.  With dense weights it is copied as before.
         host_y = plan is not None and os.environ.get("DLSG_E2E_HOST_Y", "1") != "0"
         n_chunk = int(os.environ.get("DLSG_E2E_CHUNKS", 8))
         if n_chunk < 1 or B % n_chunk:
@@ -424,7 +622,8 @@ def main():
             y_bytes = sampled_rows * C * X * 8
         else:
             y_bytes = hy.numel() * 8
-        h2d = y_bytes + hm.numel() * 8 + hw.numel() * 4
+        h2d = y_bytes + hm.numel() * 8 + hw.numel()
+        y_rows = max(1, min(hy.shape[1] * hy.shape[2] * hy.shape[3], int(round(y_bytes / B / (X * 8)))))   # rows of X per slice
 
         def e2e_step():
             with torch.no_grad():
@@ -443,48 +642,81 @@ def main():
                         st.wait_event(ev)
                         for tns in (dm, dw, aty_i):
                             tns.record_stream(st)
-                        res = pgd(None, A_i, ATy=aty_i)
+                        res = net(None, A_i, ATy=aty_i)
                         hx[sl].copy_(res, non_blocking=True)
                 for st in streams:
                     torch.cuda.current_stream(dev).wait_stream(st)
 
+        hy_rows = hy.view(B, -1, X)                            # [B, C*T*Y, X]: contiguous rows, for the byte-equivalent copy below
+
+        def copy_only_step():                                  # the same bytes with no compute: the host-side / PCIe ceiling
+            for i in range(n_chunk):
+                sl = slice(i * cb, (i + 1) * cb)
+                with torch.cuda.stream(xfer):
+                    hw[sl].to(dev, non_blocking=True)
+                    hm[sl].to(dev, non_blocking=True)
+                    hy_rows[sl, :y_rows].to(dev, non_blocking=True)
+                with torch.cuda.stream(streams[i % n_streams]):
+                    hx[sl].copy_(out[sl], non_blocking=True)
+            for st in streams + [xfer]:
+                torch.cuda.current_stream(dev).wait_stream(st)
+
         n_e2e = max(2, min(args.steps, 5))
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            e2e_step()
-        barrier()
-        el = max_over_ranks(time.perf_counter() - t0, dev)
-        e2e = {"value": world * B * n_e2e / el, "unit": UNIT,
+
+        def timed(fn):
+            for _ in range(2):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                fn()
+            barrier()
+            return max_over_ranks(time.perf_counter() - t0, dev)
+
+        el = timed(e2e_step)
+        el_copy = timed(copy_only_step)
+        e2e = {"value": total_slices * n_e2e / el, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
+               "pcie_GBps_per_rank": (h2d + d2h) * n_e2e / el / 1e9,
+               "copy_only_ceiling_slices_per_s": total_slices * n_e2e / el_copy,
+               "copy_only_GBps_per_rank": (h2d + d2h) * n_e2e / el_copy / 1e9,
+               "fraction_of_copy_ceiling": el_copy / el,
                "pipeline": f"{n_chunk} chunks of {cb} slices: H2D + line plan + A^H y on a high-priority transfer stream, DC steps + D2H on {n_streams} streams",
                "kspace": ("left in pinned host memory, sampled ky lines read in place over PCIe" if host_y
-                          else "dense copy to the device")}
+                          else "dense copy to the device"),
+               "mask": "uint8 on the host, converted to fp32 on the device by SenseModel", "numa": numa}
+
+    full = None
+    if rank == 0 and world == 1 and not args.skip_full and preset is None:
+        full = {"recon_resnet": full_recon_timing("recon_resnet", dev, rank, batch=8),
+                "swin_recon": full_recon_timing("swin_recon", dev, rank, batch=2, iters=2)}
 
     swin = None
     if rank == 0 and not args.skip_swin:
-        swin = swin_block_timing(dev)
+        swin = swin_block_timing(dev, tensor_peak)
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        rate, threads, sample = cpu_port_rate(cfg)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        r = cpu_port_rate(args.workload, cfg)
+        if r is not None:
+            cpu = {"value": r[0], "unit": UNIT, "cores": r[1], "kind": "port", "sample": r[2]}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (complex64)", "data": "synthetic",
-            "config": {"workload": "config_recon.yaml", **cfg, "slices_per_gpu": B,
-                       "l2": "working set per step (y 2.5 GB + x/maps/mask) >> 126 MB L2, no flush needed",
-                       "workspace_MB": float(os.environ.get("DLSG_WORKSPACE_MB", 4096)),
-                       "kernel_path": path, "sampled_ky_lines_max": (plan[1] if plan is not None else Y),
-                       "launch": ("one CUDA graph of the step (captured from the public API calls), replayed K times" if use_graph
-                                  else "eager launches"),
-                       "warmup_extra_steps": extra_warmup},
-            "roofline": roofline, "ops": ops, "ops_dense_kernels": ops_dense, "swin_window_attention": swin, "cpu_baseline": cpu, "e2e": e2e,
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "eager_ms_per_step": eager_ms, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 (complex64)", "data": "synthetic",
+            "config": base_config(args.workload, cfg),
+            "run": {"slices_per_gpu": B, "total_slices": total_slices,
+                    "l2": "working set per step (y 2.5 GB + x/maps/mask) >> 126 MB L2, no flush needed",
+                    "workspace_MB": float(os.environ.get("DLSG_WORKSPACE_MB", 4096)),
+                    "kernel_path": path, "sampled_ky_lines_max": (plan[1] if plan is not None else Y),
+                    "launch": ("one CUDA graph of the step (captured from the public API calls), replayed K times" if use_graph
+                               else "eager launches"),
+                    "conv_precision": (args.conv_precision if preset is not None else None),
+                    "warmup_extra_steps": extra_warmup, "numa": numa},
+            "roofline": roofline, "ops": ops, "ops_dense_kernels": ops_dense, "torch_eager_gpu": eager, "full_recon": full,
+            "attention": (swin or {}).get("roofline"), "swin_window_attention": swin, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

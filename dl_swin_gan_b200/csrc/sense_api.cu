@@ -530,7 +530,7 @@ int run_lines(Op op, const float2* in, const float2* maps, const float* w, const
     const int* pos = list + (size_t)B * T * Y;
     const int* order = pos + (size_t)B * T * Y;
     const int* cls = order + (size_t)B * T * Y;
-    const float* wq = reinterpret_cast<const float*>(cls + (size_t)B * T * kPlanClsInts);
+    const float* wq = reinterpret_cast<const float*>(plan + line_plan_wq_offset(B, T, Y));
     for (long long b0 = 0; b0 < B; b0 += bchunk) {
         const int bc = (int)((B - b0 < bchunk) ? (B - b0) : bchunk);
         const SenseDims d{bc, E, C, T, Y, X, 0, T};
@@ -638,7 +638,7 @@ int dlsg_sense_dc_step_c64(const void* x, const void* aty, const void* maps, con
 // ---- sampled-line entry points ---------------------------------------------------------------
 size_t dlsg_sense_line_plan_bytes(int B, int T, int Y) {
     if (B <= 0 || T <= 0 || Y <= 0) return 0;
-    return sizeof(int) * (size_t)B * T * dlsg::line_plan_ints_per_bt(Y);
+    return sizeof(int) * dlsg::line_plan_ints(B, T, Y);
 }
 
 int dlsg_sense_line_plan_build(const float* weights, const long long* w_strides, int B, int C, int T, int Y, int X,
@@ -651,7 +651,7 @@ int dlsg_sense_line_plan_build(const float* weights, const long long* w_strides,
     int* pos = list + (size_t)B * T * Y;
     int* order = pos + (size_t)B * T * Y;
     int* cls = order + (size_t)B * T * Y;
-    float* wq = reinterpret_cast<float*>(cls + (size_t)B * T * dlsg::kPlanClsInts);
+    float* wq = reinterpret_cast<float*>(counts + dlsg::line_plan_wq_offset(B, T, Y));
     const int rc = dlsg::launch(dlsg::sense_line_plan_kernel, dim3((unsigned)((long long)B * T)), dim3(256), (size_t)Y * sizeof(int),
                                 static_cast<dlsg::stream_t>(stream), weights, ws, C, T, Y, X, counts, list, pos, order, cls, wq);
     return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;

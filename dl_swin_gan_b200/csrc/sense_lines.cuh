@@ -49,7 +49,9 @@ namespace dlsg {
 // (the last three serve the pruned column kernels of sense_lines_p.cuh)
 struct LinePlan { const int* counts; const int* list; const int* pos; int lmax; const int* order; const int* cls; const float* wq; };
 constexpr int kPlanClsInts = 36;
-DLSG_HD_CE size_t line_plan_ints_per_bt(int Y) { return 1 + 3 * (size_t)Y + kPlanClsInts + 8 * (size_t)Y; }
+// int32 elements in front of wq, rounded up so that wq (read as float4) is 16-byte aligned, and of the whole plan
+DLSG_HD_CE size_t line_plan_wq_offset(int B, int T, int Y) { return (((size_t)B * T * (1 + 3 * (size_t)Y + kPlanClsInts)) + 3) / 4 * 4; }
+DLSG_HD_CE size_t line_plan_ints(int B, int T, int Y) { return line_plan_wq_offset(B, T, Y) + (size_t)B * T * Y * 8; }
 
 DLSG_DEVICE size_t idx_lines(const SenseDims& d, int lmax, int b, int c, int t, int i) {
     return ((((size_t)b * d.C + c) * d.t_count + (t - d.t_begin)) * lmax + i) * (size_t)d.X;

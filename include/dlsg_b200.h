@@ -111,7 +111,7 @@ int dlsg_sense_dc_step_c64(const void* x, const void* aty, const void* maps, con
  * ------------------------------------------------------------------------------------------------ */
 
 /* Bytes of the device-resident line plan for B slices of T frames with Y lines:
- * int32 counts[B*T] | list[B*T*Y] | pos[B*T*Y] | order[B*T*Y] | cls[B*T*36] | float wq[B*T*Y*8]
+ * int32 counts[B*T] | list[B*T*Y] | pos[B*T*Y] | order[B*T*Y] | cls[B*T*36] | pad to 16 bytes | float wq[B*T*Y*8]
  *   n(b,t) = counts; list = sampled ky ascending; pos[ky] = index of ky in list or -1;
  *   order / cls / wq = the same lines grouped by ky mod 16 with their unit roots exp(-2 pi i ky / Y) and squares:
  *   tables of the pruned column transforms (csrc/sense_lines_p.cuh), built here once instead of in every CTA.

@@ -208,7 +208,7 @@ def test_adjoint_reads_pinned_host_kspace_in_place(dev, monkeypatch):
     with pytest.raises(RuntimeError):
         A(torch.from_numpy(k), adjoint=True)                   # pageable memory: no CPU fallback
     with pytest.raises(ValueError):
-        A(hk[:, :, ::2], adjoint=True)                         # strided view of a pinned tensor: .contiguous() would be pageable
+        A(torch.from_numpy(np.ascontiguousarray(k.transpose(0, 1, 2, 4, 3))).pin_memory().transpose(3, 4), adjoint=True)   # strided view of a pinned tensor: .contiguous() would be pageable
     # the kernel reads the pinned buffer after the call returns: a temporary must stay alive until then
     from dl_swin_gan_b200.mri import transforms as tr
     tmp = A(torch.from_numpy(k).pin_memory(), adjoint=True)    # the pinned temporary is dropped by the caller right here
