@@ -51,7 +51,9 @@ WORKLOADS = {
     "perfusion": ("perfusion slices/sec (unrolled Swin recon)", "config_swin",
                   dict(B=1, E=2, C=32, T=40, Y=256, X=256, unrolls=5, step=-2.0, accel=8)),
 }
-CONFIG_FILE = {"config_recon": "config_recon.yaml", "recon_resnet": "config_recon.yaml", "swin_recon": "config_swin.yaml",
+WORKLOADS["train_swin"] = ("training iterations/sec (unrolled Swin network, config_swin.yaml, DDP)", "config_swin",
+                           dict(B=1, E=2, C=8, T=20, Y=192, X=64, unrolls=5, step=-2.0, accel=12))
+CONFIG_FILE = {"train_swin": "config_swin.yaml (training, CROP_READOUT 64)", "config_recon": "config_recon.yaml", "recon_resnet": "config_recon.yaml", "swin_recon": "config_swin.yaml",
                "example": "basic/example.yaml", "perfusion": "config_swin.yaml (perfusion-shaped data)"}
 WORKLOAD = WORKLOADS["config_recon"][2]       # tools/ import the default problem under this name
 
@@ -358,7 +360,7 @@ def pin_to_gpu_numa_node(local_rank: int):
 
 
 # --------------------------------------------------------------------------- whole reconstructions
-def full_recon_timing(workload, dev, rank, batch=None, iters=3, precisions=("fp32", "tf32", "bf16")):
+def full_recon_timing(workload, dev, rank, batch=None, iters=3, precisions=("tf32x3", "tf32", "bf16", "fp32")):
     """slices/s of a whole unrolled reconstruction (DC steps + denoisers) with the time split, per convolution precision."""
     from dl_swin_gan_b200.config import load_cfg
     from dl_swin_gan_b200.models import build_unrolled, set_conv_precision, get_conv_precision
@@ -386,9 +388,73 @@ def full_recon_timing(workload, dev, rank, batch=None, iters=3, precisions=("fp3
             out[prec] = {"ms_per_batch": t_all, "slices_per_s": cfg["B"] / (t_all * 1e-3), "denoiser_ms": t_den,
                          "denoiser_share": cfg["unrolls"] * t_den / t_all}
     set_conv_precision(keep)
-    out["note"] = ("conv precision fp32 = true fp32 FMAs (default: keeps the reconstruction within 1e-3 NRMSE of the fp32 reference, "
-                   "tests/test_models.py); tf32 / bf16 = cuDNN tensor cores; the denoiser convolutions are cuDNN library calls (SURVEY.md 8f-1)")
+    out["note"] = ("conv precision tf32x3 = three TF32 tensor-core convolutions on split operands (default; fp32-accurate: the whole "
+                   "reconstruction stays within 1e-3 NRMSE of the fp32 reference, tests/test_models.py); tf32 = cuDNN default (what the "
+                   "reference itself runs on a GPU; 1.2e-3 NRMSE after 5 Swin unrolls); fp32 = cuDNN without tensor cores; the denoiser "
+                   "convolutions are cuDNN library calls (SURVEY.md 8f-1)")
     return out
+
+
+# --------------------------------------------------------------------------- training slice (BASELINE configs[2])
+def run_training_bench(args, rank, world, local_rank):
+    """config_swin.yaml training: batch 1 per GPU (DATALOADER.TRAIN_BATCH_SIZE), readout cropped to 64, Adam 1e-4, complex L1,
+    bf16 convolutions (ours; the reference trains in fp32), DDP over NCCL for N > 1.  value = iterations/s over all ranks."""
+    import __graft_entry__ as ge
+    if rank == 0 or not os.path.exists(ge.LIB):
+        ge.build()
+    from dl_swin_gan_b200.config import load_cfg
+    from dl_swin_gan_b200.sharding import max_over_ranks
+    from dl_swin_gan_b200.train import Trainer, synthetic_batch, time_allreduce
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    metric, preset, problem = WORKLOADS["train_swin"]
+    cfg = dict(problem)
+    if args.batch:
+        cfg["B"] = args.batch
+    config = load_cfg(preset)
+    torch.manual_seed(1000)
+    tr = Trainer(config, dev, conv_precision=("bf16" if args.conv_precision == "tf32x3" else args.conv_precision), ddp=world > 1)
+    batches = [synthetic_batch(config, dev, cfg["B"], seed=1000 + rank * 16 + i, coils=cfg["C"], frames=cfg["T"], ny=cfg["Y"], nx=cfg["X"])
+               for i in range(2)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    losses = []
+    for i in range(args.warmup):
+        losses.append(tr.step(batches[i % 2]))
+    barrier()
+    clocks = ClockSampler(local_rank)
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_ev.record()
+    for i in range(args.steps):
+        losses.append(tr.step(batches[i % 2]))
+    e_ev.record()
+    clocks.poll_until(e_ev)
+    barrier()
+    ms = max_over_ranks(s_ev.elapsed_time(e_ev), dev) / args.steps
+    ar_ms = time_allreduce(tr.grad_bytes(), dev) if world > 1 else None
+    if rank == 0:
+        line = {"metric": metric, "value": world * 1e3 / ms, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 convolutions (autocast), fp32 elsewhere", "data": "synthetic",
+                "config": base_config("train_swin", cfg),
+                "run": {"batch_per_gpu": cfg["B"], "optimizer": "Adam lr 1e-4", "loss": config.MODEL.RECON_LOSS.NAME,
+                        "params": sum(p.numel() for p in tr.net.parameters()), "grad_bytes": tr.grad_bytes(),
+                        "allreduce_ms_standalone": ar_ms, "ddp": world > 1,
+                        "note": "Swin blocks differentiate through their torch route (attention backward re-materialised); the SENSE "
+                                "operator and its VJP are the B200 kernels", "loss_first_last": [losses[0], losses[-1]]},
+                "gpu_launches": int(__import__("dl_swin_gan_b200")._lib.load().dlsg_launch_count()), "clocks": clocks.summary()}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------- main arm
@@ -402,7 +468,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: B slices per GPU; strong: the B slices of the workload split over the ranks (slice_range)")
     ap.add_argument("--batch", type=int, default=0, help="slices per GPU (default: the workload's)")
-    ap.add_argument("--conv-precision", default="fp32", choices=["fp32", "tf32", "bf16"], help="denoiser convolutions (full-recon workloads)")
+    ap.add_argument("--conv-precision", default="tf32x3", choices=["tf32x3", "fp32", "tf32", "bf16"], help="denoiser convolutions (full-recon workloads)")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-swin", action="store_true", help="skip the window-attention side measurement")
@@ -414,6 +480,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
 
+    if args.workload == "train_swin":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "metric": WORKLOADS["train_swin"][0], "unit": "it/s", "n_gpus": args.gpus,
+                                  "unavailable": "the reference trains through PyTorch Lightning (not installed) and cannot travel to the GPU box"}), flush=True)
+            return
+        run_training_bench(args, rank, world, local_rank)
+        return
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return
@@ -623,7 +697,6 @@ def main():
         else:
             y_bytes = hy.numel() * 8
         h2d = y_bytes + hm.numel() * 8 + hw.numel()
-        y_rows = max(1, min(hy.shape[1] * hy.shape[2] * hy.shape[3], int(round(y_bytes / B / (X * 8)))))   # rows of X per slice
 
         def e2e_step():
             with torch.no_grad():
@@ -647,7 +720,8 @@ def main():
                 for st in streams:
                     torch.cuda.current_stream(dev).wait_stream(st)
 
-        hy_rows = hy.view(B, -1, X)                            # [B, C*T*Y, X]: contiguous rows, for the byte-equivalent copy below
+        hy_flat = hy.view(-1)                                  # for the byte-equivalent contiguous copy below
+        y_elems = max(1, y_bytes // 8 // n_chunk)
 
         def copy_only_step():                                  # the same bytes with no compute: the host-side / PCIe ceiling
             for i in range(n_chunk):
@@ -655,7 +729,7 @@ def main():
                 with torch.cuda.stream(xfer):
                     hw[sl].to(dev, non_blocking=True)
                     hm[sl].to(dev, non_blocking=True)
-                    hy_rows[sl, :y_rows].to(dev, non_blocking=True)
+                    hy_flat[i * y_elems:(i + 1) * y_elems].to(dev, non_blocking=True)
                 with torch.cuda.stream(streams[i % n_streams]):
                     hx[sl].copy_(out[sl], non_blocking=True)
             for st in streams + [xfer]:

@@ -3,32 +3,41 @@
 
 These are the cuDNN part of the reconstruction (97 % of the denoiser's FLOPs): library convolutions,
 kept in PyTorch with the reference's module tree and parameter names (`layers.2.conv.weight` ...) so state dicts load.
-On the device they run channels-last-3d at the precision chosen with `set_conv_precision` (default: true fp32).
+On the device they run channels-last-3d at the precision chosen with `set_conv_precision` (default: 3xTF32, fp32-accurate).
 """
 from __future__ import annotations
 
 import torch
 from torch import nn
 
-_CONV_PRECISION = "fp32"
+_CONV_PRECISION = "tf32x3"
 
 
 def set_conv_precision(mode: str) -> None:
     """Arithmetic of the denoiser convolutions on CUDA tensors (storage stays fp32):
-    "fp32"  IEEE fp32 FMAs, cuDNN's TF32 path switched off - the default, because it is what keeps a full
-            reconstruction within the 1e-3 NRMSE bar of the fp32 reference (measured on the B200 with five unrolls of the
-            Swin network: 5.1e-4; with TF32 convolutions 1.2e-3 - which is also what the reference itself gives on a GPU
-            with PyTorch's defaults);
-    "tf32"  cuDNN's default for fp32 tensors (tensor cores, 10-bit mantissa inputs);
-    "bf16"  autocast to bfloat16 (fastest, about 1e-2)."""
+    "tf32x3"  the default: every operand is split into a TF32-representable head and the remainder, and the convolution is
+              the sum of three tensor-core (TF32) convolutions  conv(x_hi, w_hi) + conv(x_lo, w_hi) + conv(x_hi, w_lo)  with fp32
+              accumulation - fp32-level accuracy (the dropped lo*lo term is ~2^-22 relative) at a third of the TF32 rate, which on
+              the B200 is ~9x faster than cuDNN's true-fp32 3-D convolutions.  Keeps a full reconstruction within the 1e-3 NRMSE
+              bar of the fp32 reference (tests/test_models.py);
+    "fp32"    cuDNN with TF32 switched off (IEEE fp32 FMAs; slow: no tensor cores);
+    "tf32"    cuDNN's default for fp32 tensors, which is also what the reference itself runs on a GPU with PyTorch's defaults:
+              1.2e-3 NRMSE against the fp32 result after five unrolls of the Swin network (measured, tools/model_precision_probe.py);
+    "bf16"    autocast to bfloat16 (about 1e-2)."""
     global _CONV_PRECISION
-    if mode not in ("fp32", "tf32", "bf16"):
-        raise ValueError("conv precision must be 'fp32', 'tf32' or 'bf16'")
+    if mode not in ("tf32x3", "fp32", "tf32", "bf16"):
+        raise ValueError("conv precision must be 'tf32x3', 'fp32', 'tf32' or 'bf16'")
     _CONV_PRECISION = mode
 
 
 def get_conv_precision() -> str:
     return _CONV_PRECISION
+
+
+def _tf32_split(t: torch.Tensor):
+    """t = hi + lo with hi representable in TF32 (10-bit mantissa, round to nearest): the tensor cores take hi exactly."""
+    hi = ((t.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32).view_as(t)
+    return hi, t - hi
 
 
 class Normalization(nn.Module):
@@ -77,13 +86,26 @@ def conv_forward(conv: nn.Module, x: torch.Tensor) -> torch.Tensor:
     if not x.is_cuda:
         return conv(x)
     x = x.contiguous(memory_format=torch.channels_last_3d)
-    if _CONV_PRECISION == "bf16":
+    mode = _CONV_PRECISION
+    if mode == "bf16":
         with torch.autocast("cuda", dtype=torch.bfloat16):
             return conv(x).float()
+    tf32 = mode in ("tf32", "tf32x3")
     with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
-                                    deterministic=torch.backends.cudnn.deterministic,
-                                    allow_tf32=(_CONV_PRECISION == "tf32")):
-        return conv(x)
+                                    deterministic=torch.backends.cudnn.deterministic, allow_tf32=tf32):
+        if mode != "tf32x3" or x.dtype != torch.float32:
+            return conv(x)
+        if isinstance(conv, nn.ConvTranspose3d):
+            def f(a, w, b):
+                return torch.nn.functional.conv_transpose3d(a, w, b, conv.stride, conv.padding, conv.output_padding, conv.groups, conv.dilation)
+        else:
+            def f(a, w, b):
+                return torch.nn.functional.conv3d(a, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+        xh, xl = _tf32_split(x)
+        wh, wl = _tf32_split(conv.weight)
+        xh = xh.contiguous(memory_format=torch.channels_last_3d)
+        xl = xl.contiguous(memory_format=torch.channels_last_3d)
+        return f(xh, wh, conv.bias) + f(xl, wh, None) + f(xh, wl, None)
 
 
 _conv = conv_forward

@@ -13,13 +13,13 @@ g = golden(name)
 net = build(name).to(dev)
 maps, mask, y = (torch.from_numpy(a).to(dev) for a in model_problem(name))
 A = SenseModel(maps, weights=mask)
-for tf32 in (True, False):
+for tf32 in ("tf32x3", "tf32", "fp32"):
     for tc in (True, False):
         from dl_swin_gan_b200.models import set_conv_precision
-        set_conv_precision("tf32" if tf32 else "fp32")
+        set_conv_precision(tf32)
         torch.backends.cuda.matmul.allow_tf32 = False
         wa.WindowAttention3D.tc_linear = tc
         with torch.no_grad():
             recon = net(y, A)
             den = net.cnn_update[0](A(y, adjoint=True))
-        print(f"cudnn tf32={tf32} tc_linear(fp16)={tc}: denoiser {rel_l2(den.cpu().numpy(), g['denoised']):.2e} recon {rel_l2(recon.cpu().numpy(), g['recon']):.2e}")
+        print(f"conv {tf32} tc_linear(fp16)={tc}: denoiser {rel_l2(den.cpu().numpy(), g['denoised']):.2e} recon {rel_l2(recon.cpu().numpy(), g['recon']):.2e}")
