@@ -188,6 +188,41 @@ def test_column_kernel_generations_agree(dev, monkeypatch, E):
     monkeypatch.delenv("DLSG_LINES_KERNELS")
 
 
+def test_perfusion_shape_at_full_length_matches_fp64(dev):
+    """BASELINE configs[3]: 2 map sets, 32 coils, 40 frames, 256 x 256 (one slice) through the sampled-line kernels (R2 = 16,
+    E = 2) against the reference expression evaluated in complex128 with torch.fft on the same device."""
+    from dl_swin_gan_b200.mri import SenseModel
+    from dl_swin_gan_b200.mri.subsample import VDktMaskFunc
+    B, E, C, T, Y, X = 1, 2, 32, 40, 256, 256
+    g = torch.Generator(device=dev).manual_seed(77)
+
+    def cn(*s):
+        return torch.view_as_complex(torch.randn(*s, 2, generator=g, device=dev))
+
+    maps = cn(B, E, C, 1, Y, X) / (E * C) ** 0.5
+    x, aty = cn(B, E, T, Y, X), cn(B, E, T, Y, X)
+    mask = VDktMaskFunc((8, 8), sim_partial_kx=0.25, sim_partial_ky=0.25)((1, 1, T, Y, X), seed=9).to(dev)
+    A = SenseModel(maps, weights=mask)
+    k = A(x)
+    assert A._line_plans.get((B, E, C, T, Y, X)) is not None
+    m128, w = maps.to(torch.complex128), mask.to(torch.float64)
+
+    def fwd(v):
+        return w * torch.fft.fftn((v.unsqueeze(2) * m128).sum(1), dim=(-2, -1), norm="ortho")
+
+    def adj(v):
+        return (torch.fft.ifftn(w * v, dim=(-2, -1), norm="ortho").unsqueeze(1) * m128.conj()).sum(2)
+
+    def rel(a, b):
+        return float((a.to(torch.complex128) - b).norm() / b.norm())
+
+    x128 = x.to(torch.complex128)
+    k_ref = fwd(x128)
+    assert rel(k, k_ref) < TOL
+    assert rel(A(k, adjoint=True), adj(k.to(torch.complex128))) < TOL
+    assert rel(A.dc_step(x, aty, -2.0), x128 - 2.0 * (adj(k_ref) - aty.to(torch.complex128))) < TOL
+
+
 def test_adjoint_reads_pinned_host_kspace_in_place(dev, monkeypatch):
     """A(y, adjoint=True) with y in pinned host memory == the same with y copied to the device (bit for bit);
     pageable host memory, dense weights and the dense kernels refuse instead of falling back to a CPU path."""
