@@ -404,7 +404,26 @@ class SenseModel(nn.Module):
         _retain_host_buffer(host, maps5.device)        # keeps the pinned buffer alive until the gather has run
         return out
 
+    def _mark_stream_use(self, device) -> None:
+        """The operator's cached device tensors (contiguous maps, fp32 weights, line plans) may have been created on another
+        stream than the one now launching kernels that read them (e.g. operator built on a transfer stream, solver run on a
+        compute stream): tell the caching allocator, so that their memory is not recycled under the running kernels."""
+        if torch.cuda.is_current_stream_capturing():
+            return
+        st = torch.cuda.current_stream(device)
+        for t in (self._maps5, self._w32):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(st)
+        for plan in self._line_plans.values():
+            if plan is not None:
+                plan[0].record_stream(st)
+
     def _run(self, kind: str, data: torch.Tensor, aty=None, step=None) -> torch.Tensor:
+        out = self._run_impl(kind, data, aty, step)
+        self._mark_stream_use(out.device)
+        return out
+
+    def _run_impl(self, kind: str, data: torch.Tensor, aty=None, step=None) -> torch.Tensor:
         if kind == "adj" and not data.is_cuda and data.is_pinned():
             return self._run_adjoint_from_host(data)
         _require_cuda_c64(data, "SENSE input")

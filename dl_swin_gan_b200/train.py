@@ -79,6 +79,11 @@ class Trainer:
             from .mri import SenseModel
             self.operator = SenseModel
         net = (model if model is not None else build_unrolled(config)).to(device).train()
+        # `SwinTransformer3D.norm` exists in the reference's module tree but never takes part in forward (video_swin...:661,
+        # 735-756): it would never receive a gradient, which DistributedDataParallel treats as an error - freeze it
+        for name, p in net.named_parameters():
+            if name.endswith("transformer.norm.weight") or name.endswith("transformer.norm.bias"):
+                p.requires_grad_(False)
         self.net = net
         self.model = (nn.parallel.DistributedDataParallel(net, device_ids=[device.index] if device.type == "cuda" else None,
                                                           gradient_as_bucket_view=True) if ddp else net)
