@@ -3,19 +3,23 @@
 // dl_cs/models/unrolledswin.py:109) and the same intermediate `tl` [B,C,T,lmax,X], so the row pass on the sampled
 // lines (sense_rows_lines_kernel) is shared.
 //
-// Why a second generation.  The first one was issue-bound (profiles/r1q_lines_ncu_summary.csv: 12 warps/SM,
+// Why a second generation.  The first one was issue- and latency-bound (profiles/r1q_lines_ncu_summary.csv: 12 warps/SM,
 // issue-active 56 %, 1594 instructions per thread and coil for ~900 of FP32 work).  Here
 //   * every complex add / multiply / fma is one packed instruction on a register pair (FADD2 / FFMA2,
 //     fft_packed.cuh): the same FP32 pipe time in half the issue slots;
 //   * Y = 16 * R2 is split as an in-register radix-16 DFT (one thread, 16 complex registers instead of 32) and a
 //     radix-R2 stage that is only evaluated for the sampled lines ("pruned"):
-//       forward  y = R2 l + j :  Z_j[k1] = DFT16_l( img[R2 l + j] ),   tl[i] = sum_j W_Y^(j ky_i) Z_j[ky_i mod 16]
-//       adjoint                  U_j[k1] = sum_{i : ky_i mod 16 = k1} conj(W_Y^(j ky_i)) tl[i],
+//       forward  y = R2 l + j :  Z_j[k1] = DFT16_l( img[R2 l + j] ),   tl[i] = sum_j w_i^j Z_j[ky_i mod 16],  w_i = W_Y^ky_i
+//       adjoint                  U_j[k1] = sum_{i : ky_i mod 16 = k1} conj(w_i)^j tl[i],
 //                                out[R2 l + j] = IDFT16_k1( U_j )[l]
-//     so the dense part of a column transform is R2 DFT16s and the rest is n * R2 complex fmas per column;
-//   * a CTA is a 16-column slab x R2 threads per column (192 threads for Y = 192), 3-4 CTAs per SM;
-//   * each thread's coil-sensitivity values are its own: they are staged by 8-byte cp.async into thread-private
-//     shared-memory slots one coil ahead (no CTA barrier, no registers held during the flight), x stays in registers.
+//     so the dense part of a column transform is R2 DFT16s and the rest is ~n * R2 complex fmas per column; the
+//     powers of w come from Horner's rule / repeated multiplication on the even and odd terms (one coefficient
+//     pair per line, precomputed in the line plan together with the grouping of the lines by ky mod 16);
+//   * a CTA is a 16-column slab x R2 threads per column (192 threads for Y = 192), 3 CTAs per SM in the forward kernel;
+//   * the coil-map slab [Y rows][16 columns] of each coil arrives by TMA (cp.async.bulk.tensor, one copy per map set
+//     issued by one thread, completion on an mbarrier) and every thread reads its own 16 values from it; x stays in
+//     registers.  No per-thread global loads in the coil loop, nothing held in registers while a slab is in flight.
+// Measurements and the variants that were rejected: DESIGN.md section 3c.
 #pragma once
 
 #include "sense_lines.cuh"
