@@ -394,16 +394,14 @@ inline bool pcols_disabled() {
     const char* v = std::getenv("DLSG_LINES_KERNELS");
     return v && std::strcmp(v, "v1") == 0;
 }
-// buffers of the map slab (mb) and of the exchange (xb) in the forward kernel: DLSG_PCOLS_CFG="mb,xb" overrides
+// buffers of the exchange (xb) in the forward kernel; one map slab (two measured slower: 2 CTAs/SM instead of 3).
+// DLSG_PCOLS_XB=2 selects the double-buffered exchange (one CTA barrier per coil; measured equal)
 inline void pcols_fwd_cfg(int E, int Y, int lmax, int& mb, int& xb) {
     mb = 1; xb = 1;
-    if (const char* v = std::getenv("DLSG_PCOLS_CFG")) {
-        if (v[0] == '1' || v[0] == '2') mb = v[0] - '0';
-        if (v[1] == ',' && (v[2] == '1' || v[2] == '2')) xb = v[2] - '0';
-    }
+    if (const char* v = std::getenv("DLSG_PCOLS_XB")) xb = (v[0] == '2') ? 2 : 1;
     const size_t slab = (size_t)16 * Y * sizeof(float2);
     const size_t tables = 16 + (size_t)lmax * (2 * sizeof(float4) + 2 * sizeof(int)) + 36 * sizeof(int);
-    while ((size_t)(E * mb + xb) * slab + tables > kSmemMax && (mb > 1 || xb > 1)) { if (xb > 1) --xb; else --mb; }
+    if ((size_t)(E * mb + xb) * slab + tables > kSmemMax) xb = 1;
 }
 inline int pcols_adj_xb(int E, int Y, int lmax) {
     int xb = 2;
@@ -461,8 +459,6 @@ int launch_pcols_fwd_e(const float2* x, const TileMap& tm, float2* tl, const Lin
     int mb, xb;
     pcols_fwd_cfg(E, d.Y, lp.lmax, mb, xb);
     const size_t smem = Cfg::smem_fwd(E, lp.lmax, mb, xb);
-    if (mb == 2 && xb == 2) return launch(sense_cols_fwd_lines_p_kernel<R2, E, 2, 2>, dim3(grid), dim3(Cfg::NT), smem, s, x, tm, tl, lp, d);
-    if (mb == 2) return launch(sense_cols_fwd_lines_p_kernel<R2, E, 2, 1>, dim3(grid), dim3(Cfg::NT), smem, s, x, tm, tl, lp, d);
     if (xb == 2) return launch(sense_cols_fwd_lines_p_kernel<R2, E, 1, 2>, dim3(grid), dim3(Cfg::NT), smem, s, x, tm, tl, lp, d);
     return launch(sense_cols_fwd_lines_p_kernel<R2, E, 1, 1>, dim3(grid), dim3(Cfg::NT), smem, s, x, tm, tl, lp, d);
 }

@@ -3,6 +3,6 @@
 so=${1:-build_variants/libdlsg_p6.so}
 export DLSG_LIB_PATH=$PWD/$so
 python tools/quick_ops.py 2>&1 | tail -1
-for cfg in ${CFGS:-1,1 1,2 2,1}; do for axb in ${AXBS:-1 2}; do
-  echo "cfg fwd(mb,xb)=$cfg adj xb=$axb"; DLSG_PCOLS_CFG=$cfg DLSG_PCOLS_ADJ_XB=$axb tools/ncu_lines_quick.sh $so
+for xb in ${XBS:-1 2}; do for axb in ${AXBS:-1 2}; do
+  echo "cfg fwd xb=$xb adj xb=$axb"; DLSG_PCOLS_XB=$xb DLSG_PCOLS_ADJ_XB=$axb tools/ncu_lines_quick.sh $so
 done; done
