@@ -497,6 +497,35 @@ int pcols_adj(const float2* tl, const float2* maps, float2* out, const float2* x
     DLSG_PRADIX_SWITCH(pradix_of(d.Y), (launch_pcols_adj<R2>(tl, maps, out, xin, aty, step, step_dev, epi, lp, d, s)))
 }
 
+// row pass of the normal operator: second-generation kernel for X = 16 * RX (sense_lines_p.cuh), else the first generation
+template <int RX>
+int launch_prows_normal(float2* tl, const float* w, const WeightStrides& ws, float scale, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    using Cfg = PRowCfg<RX>;
+    const long long units = (long long)d.B * d.t_count;
+    const long long rounds = ((long long)d.C * lp.lmax + 1) / 2;                 // warp rounds per (b, t), upper bound
+    long long nsplit = (148LL * 5 * 4 + units - 1) / units;                       // about four waves of 5 CTAs per SM
+    const long long max_split = (rounds + Cfg::WARPS - 1) / Cfg::WARPS;
+    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit < 1) nsplit = 1;
+    return launch(sense_rows_normal_lines_p_kernel<RX>, dim3((unsigned)(units * nsplit)), dim3(32 * Cfg::WARPS), Cfg::smem(), s,
+                  tl, w, ws, scale, lp, d, (int)nsplit);
+}
+int rows_normal_lines(float2* tl, const float* w, const WeightStrides& ws, float scale, const LinePlan& lp, const SenseDims& d, stream_t s) {
+    if (!pcols_disabled()) {
+        switch (pradix_of(d.X)) {
+            DLSG_PRADIX_CASE(10, (launch_prows_normal<10>(tl, w, ws, scale, lp, d, s)))
+            DLSG_PRADIX_CASE(12, (launch_prows_normal<12>(tl, w, ws, scale, lp, d, s)))
+#ifndef DLSG_FAST_BUILD
+            DLSG_PRADIX_CASE(8, (launch_prows_normal<8>(tl, w, ws, scale, lp, d, s)))
+            DLSG_PRADIX_CASE(16, (launch_prows_normal<16>(tl, w, ws, scale, lp, d, s)))
+            DLSG_PRADIX_CASE(20, (launch_prows_normal<20>(tl, w, ws, scale, lp, d, s)))
+#endif
+            default: break;
+        }
+    }
+    return rows_lines<MODE_NORMAL>(tl, tl, w, ws, scale, lp, d, s);
+}
+
 bool lines_supported(int E, int Y, int X, int lmax) {
     if (E <= 0 || lmax <= 0 || lmax > Y) return false;
     if (!radix_of(Y) || !radix_of(X)) return false;
@@ -553,7 +582,7 @@ int run_lines(Op op, const float2* in, const float2* maps, const float* w, const
             DLSG_TRY(launch(sense_zero_unsampled_kernel, dim3((unsigned)((long long)bc * T * C)), dim3(256), 0, s, k_b, lp, d));
             DLSG_TRY((rows_lines<MODE_FWD>(tl, k_b, w_b, ws, scale, lp, d, s)));
         } else {
-            DLSG_TRY((rows_lines<MODE_NORMAL>(tl, tl, w_b, ws, scale, lp, d, s)));
+            DLSG_TRY(rows_normal_lines(tl, w_b, ws, scale, lp, d, s));
             DLSG_TRY(cols_adj_lines(tl, maps_b, out + b0 * x_slice, x_b, aty ? aty + b0 * x_slice : nullptr,
                                     step, step_dev, epi, lp, d, s));
         }

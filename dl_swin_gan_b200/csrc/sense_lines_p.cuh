@@ -367,4 +367,106 @@ sense_cols_adj_lines_p_kernel(const float2* __restrict__ tl_in, const DLSG_GRID_
     }
 }
 
+
+// ---------------------------------------------------------------------------- row pass of the normal operator, second generation
+//   tl[b,c,t,i,:] <- IDFT_X( (W*scale)^2 * DFT_X( tl[b,c,t,i,:] ) )      in place, for the sampled lines of (b, t)
+// X = 16 * RX.  A warp takes two lines at a time; both transforms share their middle stage, so a line crosses shared
+// memory twice instead of four times:
+//   lane (line, j), j < 16 :  a[l] = tl[16 l + j], l < RX          DFT_RX over l, twiddle W_X^(j k1)      -> exchange 1  [k1][j]
+//   lane (line, k1), k1 < RX: DFT16 over j  ->  k[k1 + RX k2], k2 < 16;   times (W scale)^2;   IDFT16 over k2 -> n2;
+//                             twiddle conj(W_X)^(n2 k1)                                                   -> exchange 2  [n2][k1]
+//   lane (line, n2), n2 < 16: IDFT_RX over k1 -> tl[n2 + 16 n1], n1 < RX      (the layout the line was loaded in)
+// Global accesses are 128-byte segments (16 lanes x 8 bytes per l), the exchanges are warp-private (only __syncwarp),
+// registers stay below 80 so that 6 CTAs of 4 warps share an SM.  Packed butterflies (fft_packed.cuh).
+template <int RX>
+struct PRowCfg {
+    static constexpr int X = 16 * RX, WARPS = 4;
+    static constexpr int S1 = 17, S2 = RX + 1;                       // padded strides of the two exchange layouts (conflict-free)
+    static constexpr int EX1 = RX * S1, EX2 = 16 * S2;               // complex elements per line
+    static constexpr int EXW = 2 * (EX1 + EX2);                      // per warp (two lines)
+    static size_t smem() { return ((size_t)WARPS * EXW + X) * sizeof(float2); }   // + twiddle table W_X^m, m = j k1 < X
+};
+
+template <int RX>
+DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(128, 5)
+sense_rows_normal_lines_p_kernel(float2* __restrict__ tl, const float* __restrict__ w, WeightStrides ws, float scale,
+                                 LinePlan lp, SenseDims d, int nsplit) {
+    using Cfg = PRowCfg<RX>;
+    constexpr int X = Cfg::X, S1 = Cfg::S1, S2 = Cfg::S2;
+    DLSG_DYN_SMEM(float2, smem);
+    float2* twt = smem;                                              // [X]: exp(-2 pi i m / X)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* ex1 = smem + X + (size_t)warp * Cfg::EXW;                // [2 lines][RX][S1]  (k1, j)
+    float2* ex2 = ex1 + 2 * Cfg::EX1;                                // [2 lines][16][S2]  (n2, k1)
+    for (int m = threadIdx.x; m < X; m += blockDim.x) {
+        float sn, cs;
+        sincospif((float)(2 * (2 * m > X ? m - X : m)) / (float)X, &sn, &cs);
+        twt[m] = make_float2(cs, -sn);
+    }
+    __syncthreads();
+    const int split = (int)(blockIdx.x % nsplit), unit = (int)(blockIdx.x / nsplit);
+    const int tloc = unit % d.t_count, b = unit / d.t_count, t = d.t_begin + tloc;
+    const int bt = b * d.T + t;
+    const int n = __ldg(lp.counts + bt);
+    const int rows = d.C * n;                                        // (coil, line) rows of this (b, t), line fastest
+    const int* list = lp.list + (size_t)bt * d.Y;
+    const int half = lane >> 4, j = lane & 15;                       // stages "RX": two lines x 16 lanes
+    const float s2 = scale * scale;
+
+    for (int r0 = 2 * (split * Cfg::WARPS + warp); r0 < rows; r0 += 2 * nsplit * Cfg::WARPS) {
+        const int nl = min(2, rows - r0);                            // lines of this round (uniform over the warp)
+        const int row = r0 + half;
+        const bool on = half < nl;
+        const int c = on ? row / n : 0, i = on ? row - c * n : 0;
+        float2* line = tl + idx_lines(d, lp.lmax, b, c, t, i);
+        // ---- load, DFT_RX over l, twiddle, exchange 1
+        if (on) {
+            float2 a[RX];
+#pragma unroll
+            for (int l = 0; l < RX; ++l) a[l] = line[16 * l + j];
+            PDft<RX, -1>::run(a);
+            float2* e1 = ex1 + half * Cfg::EX1 + j;
+#pragma unroll
+            for (int k1 = 0; k1 < RX; ++k1) e1[k1 * S1] = (k1 == 0) ? a[0] : pc_mul(a[k1], twt[j * k1]);
+        }
+        __syncwarp();
+        // ---- middle, items (line, k1): DFT16 over j, weights, IDFT16 over k2, twiddle, exchange 2
+        for (int item = lane; item < nl * RX; item += 32) {
+            const int hl = item / RX, k1 = item - hl * RX;
+            const int rw = r0 + hl, cc = rw / n, ii = rw - cc * n;
+            const float* wr = w + (b * ws.b + cc * ws.c + t * ws.t + __ldg(list + ii) * ws.y + k1 * ws.x);
+            float wv[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) wv[k2] = __ldg(wr + (long long)(RX * k2) * ws.x);
+            const float2* src = ex1 + hl * Cfg::EX1 + k1 * S1;
+            float2 u[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) u[jj] = src[jj];
+            PDft<16, -1>::run(u);                                    // u[k2] = X[k1 + RX k2]
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) u[k2] = p_mul(u[k2], p_bc(wv[k2] * wv[k2] * s2));
+            PDft<16, +1>::run(u);                                    // over k2 -> n2
+            float2* dst = ex2 + hl * Cfg::EX2 + k1;
+            dst[0] = u[0];
+#pragma unroll
+            for (int n2 = 1; n2 < 16; ++n2) {
+                const float2 tw = twt[n2 * k1];
+                dst[n2 * S2] = pc_mul(u[n2], make_float2(tw.x, -tw.y));     // conj(W_X)^(n2 k1)
+            }
+        }
+        __syncwarp();
+        // ---- IDFT_RX over k1, store (n2 = j: the layout the line was loaded in)
+        if (on) {
+            float2 a[RX];
+            const float2* e2 = ex2 + half * Cfg::EX2 + j * S2;
+#pragma unroll
+            for (int k1 = 0; k1 < RX; ++k1) a[k1] = e2[k1];
+            PDft<RX, +1>::run(a);
+#pragma unroll
+            for (int n1 = 0; n1 < RX; ++n1) line[j + 16 * n1] = a[n1];
+        }
+        __syncwarp();                                                // the exchanges are free for the next round
+    }
+}
+
 }  // namespace dlsg

@@ -171,6 +171,7 @@ LINE_CASES = [
     (2, 2, 2, 3, 128, 32, "coil", 1),                       # E = 2, one slice per workspace chunk
     (1, 1, 2, 3, 160, 32, "ragged", 0),                     # R2 = 10, a frame without lines
     (1, 3, 2, 1, 128, 32, "mask", 0),                       # E = 3 stays on the first-generation kernels
+    (1, 1, 3, 2, 128, 128, "coil", 0),                      # X = 16 * 8: second-generation row pass of the normal operator, odd row count
 ]
 
 
