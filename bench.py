@@ -360,7 +360,7 @@ def pin_to_gpu_numa_node(local_rank: int):
 
 
 # --------------------------------------------------------------------------- whole reconstructions
-def full_recon_timing(workload, dev, rank, batch=None, iters=3, precisions=("tf32x3", "tf32", "bf16", "fp32")):
+def full_recon_timing(workload, dev, rank, batch=None, iters=3, precisions=("tf32x3", "tf32", "bf16")):
     """slices/s of a whole unrolled reconstruction (DC steps + denoisers) with the time split, per convolution precision."""
     from dl_swin_gan_b200.config import load_cfg
     from dl_swin_gan_b200.models import build_unrolled, set_conv_precision, get_conv_precision

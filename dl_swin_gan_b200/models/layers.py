@@ -36,7 +36,10 @@ def get_conv_precision() -> str:
 
 def _tf32_split(t: torch.Tensor):
     """t = hi + lo with hi representable in TF32 (10-bit mantissa, round to nearest): the tensor cores take hi exactly."""
-    hi = ((t.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32).view_as(t)
+    # same-size dtype views keep the strides, so a channels-last tensor stays channels-last (no layout copies)
+    if not (t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last_3d)):
+        t = t.contiguous()
+    hi = ((t.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
     return hi, t - hi
 
 
