@@ -230,6 +230,8 @@ class WindowAttention3D(nn.Module):
         if self.training and self.attn_drop.p > 0:
             raise NotImplementedError("attn_drop > 0 in training is not supported by the fused attention core")
         qkv = self._linear(self.qkv, x)                     # (B_, N, 3C): the kernel reads q/k/v in place
+        if qkv.dtype != torch.float32:                      # under torch.autocast the Linear returns bf16 / fp16: the core computes in fp32
+            qkv = qkv.float()
         if _region_ids is not None:
             mode, m, dense = MASK_REGION, _region_ids, mask
         elif mask is not None:

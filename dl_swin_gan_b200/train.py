@@ -70,10 +70,13 @@ class Trainer:
     """One optimisation step = forward through the unrolled network, complex-L1 loss, backward (DDP all-reduce), Adam."""
 
     def __init__(self, config, device, conv_precision: str = "bf16", ddp: bool = False, model: Optional[nn.Module] = None,
-                 operator=None):
+                 operator=None, autocast: Optional[bool] = None):
         from .models import build_unrolled, set_conv_precision
         set_conv_precision(conv_precision)
         self.config, self.device = config, device
+        # BASELINE configs[2] trains in bf16: with bf16 convolutions the denoiser's Linear layers run under torch.autocast too
+        # (the SENSE operator is complex64 and the attention core fp32 either way; parameters and Adam states stay fp32)
+        self.autocast = (conv_precision == "bf16" and device.type == "cuda") if autocast is None else bool(autocast)
         self.operator = operator
         if operator is None:
             from .mri import SenseModel
@@ -100,7 +103,8 @@ class Trainer:
 
     def step(self, batch) -> float:
         kspace, mask, maps, init, scale, target = batch
-        pred = self.model(kspace, self.operator(maps, weights=mask), init)
+        with torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.autocast):
+            pred = self.model(kspace, self.operator(maps, weights=mask), init)
         if self.config.MODEL.RECON_LOSS.RENORMALIZE_DATA:
             s = scale.view(-1, 1, 1, 1, 1)
             pred, target = pred * s, target * s
