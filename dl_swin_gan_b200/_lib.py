@@ -56,6 +56,8 @@ SIGNATURES = {
     "dlsg_swin_qkv_stream_f32": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _i, _f, _vp]),
     "dlsg_swin_proj_scatter_residual_f32": (_i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _vp]),
     "dlsg_swin_proj_scatter_f32": (_i, [_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _vp]),
+    "dlsg_conv3d_k3_supported": (_i, [_i, _i]),
+    "dlsg_conv3d_k3_tf32x3_f32": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),
 }
 
 _lock = threading.Lock()

@@ -1,0 +1,230 @@
+// 3 x 3 x 3 convolution of the denoisers (nn.Conv3d with 'same' zero padding: dl_cs/models/swin3D.py:120-134,
+// the 160 -> 160 / 64 -> 64 layers of ConvBlock :225-273) as an implicit GEMM on the 5th-generation tensor cores,
+// channels-last, with the 3xTF32 operand split fused into the operand staging:
+//
+//     out[v, co] = bias[co] + sum_{tap, ci} x[v + tap, ci] * w[co, ci, tap]          v = (n, t, y, x) voxel
+//                = sum (x_hi * w_hi + x_lo * w_hi + x_hi * w_lo),   a = a_hi + a_lo,  a_hi = a rounded to TF32
+//
+// One persistent CTA per SM owns 256 consecutive voxels per tile = two 128-row accumulators [128 x Cout] fp32 in tensor
+// memory.  The K loop walks 27 taps x Cin/32 channel chunks through a two-stage shared-memory ring:
+//   * 8 producer warps (one thread per voxel) read the 32 input channels of the shifted voxel (one 128-byte line; zeros
+//     outside the volume), split them into the TF32 head and the remainder, and store both in the canonical no-swizzle
+//     K-major UMMA layout ([k/4][row/8][8 rows][4 floats]);
+//   * the weights arrive already split and already in that layout (prepared once per weight version on the host side)
+//     by one bulk copy per stage (cp.async.bulk, completion counted on the stage's mbarrier);
+//   * one thread issues 24 tcgen05.mma.kind::tf32 per stage (2 tiles x 4 k-steps x 3 products) and commits the stage
+//     back to the producers.
+// After the last stage the producer warps drain the accumulators (tcgen05.ld), add the bias and store channels-last rows.
+// CUDA-only: tcgen05 / TMEM have no host emulation (validated on the B200 against torch, tests/test_conv_gpu.py).
+#pragma once
+
+#include "cuda_compat.h"
+#include "tc_common.cuh"
+
+#if defined(__CUDACC__)
+namespace dlsg {
+
+constexpr int kConvProducers = 256;
+constexpr int kConvThreads = kConvProducers + 32;
+constexpr int kConvStages = 2;
+constexpr int kConvKC = 32;                        // input channels per stage
+constexpr int kConvTileRows = 256;                 // voxels per CTA tile (two UMMA M = 128 accumulators)
+constexpr int kConvLboA = 128 * 16 + 16;           // bytes between the 4-channel planes of an A block: +16 so that the 8 planes a quarter-warp stores hit 8 different bank groups
+constexpr int kConvABytes = (kConvKC / 4) * kConvLboA;   // one [128 x 32] fp32 operand block
+
+struct ConvParams {
+    const float* x;        // [NB, T, Y, X, Cin]
+    const float* wprep;    // [27][Cin/32][hi|lo][8][Cout/8][8][4]
+    const float* bias;     // [Cout] or NULL
+    float* out;            // [NB, T, Y, X, Cout]
+    int NB, T, Y, X, Cin, Cout;
+    long long NV;          // NB*T*Y*X
+    int relu_in;           // rectify the input on the fly (ConvBlock's pre-activation)
+};
+
+__host__ __device__ inline size_t conv_stage_bytes(int Cout) { return (size_t)4 * kConvABytes + (size_t)2 * Cout * kConvKC * 4; }
+inline size_t conv_smem_bytes(int Cout) { return kConvStages * conv_stage_bytes(Cout) + (size_t)Cout * 4 + 128; }
+
+__device__ __forceinline__ unsigned umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// bounded wait: a broken pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void conv_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (long long spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1ll << 28)) __trap();
+    }
+}
+__device__ __forceinline__ void conv_bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+    lo = v - hi;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvParams p) {
+    extern __shared__ __align__(1024) unsigned char conv_smem[];
+    const int Cout = p.Cout, KCH = p.Cin / kConvKC, NIT = 27 * KCH;
+    const size_t stage_bytes = conv_stage_bytes(Cout);
+    const unsigned wblock = (unsigned)Cout * kConvKC * 4;            // one of w_hi / w_lo for a stage
+    float* sBias = reinterpret_cast<float*>(conv_smem + kConvStages * stage_bytes);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sBias + Cout);   // full[2], empty[2], accfull, accempty
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 6);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned s0 = smem_u32(conv_smem), bar0 = smem_u32(bars);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kConvStages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 8u * s), "r"(kConvProducers + 1) : "memory");        // full
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 8u * (2 + s)), "r"(1) : "memory");                  // empty
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 32u), "r"(1) : "memory");                               // accfull
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 40u), "r"(kConvProducers) : "memory");                  // accempty
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = tid; i < Cout; i += kConvThreads) sBias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+
+    const long long ntiles = (p.NV + kConvTileRows - 1) / kConvTileRows;
+    const long long YX = (long long)p.Y * p.X;
+
+    if (warp < kConvProducers / 32) {
+        // =========================== producers, then epilogue ===========================
+        // loads are coalesced: 8 lanes cover the 128 bytes of one voxel's channel chunk, a warp instruction takes 4 voxels;
+        // thread (lane) owns channel quad k4 = lane & 7 of rows 4 i + (lane >> 3), i = 0..7, of its warp's 32 rows
+        const int ti = tid >> 7;
+        const int k4 = lane & 7, rsub = lane >> 3;
+        const int wrow0 = (warp & 3) * 32;                       // first row of this warp inside its 128-row block
+        unsigned g = 0, tcount = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const long long v0 = tile * kConvTileRows + ti * 128 + wrow0 + rsub;      // this thread's rows: v0 + 4 i
+            int coord[8];                                          // packed (t, y, x) of the 8 rows, -1 = beyond the volume
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long vi = v0 + 4 * i;
+                if (vi < p.NV) {
+                    const long long r1 = vi % YX;
+                    coord[i] = (int)((vi / YX) % p.T) << 20 | (int)(r1 / p.X) << 10 | (int)(r1 % p.X);
+                } else coord[i] = -1;
+            }
+            for (int tap = 0; tap < 27; ++tap) {
+                const int dt = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
+                unsigned okmask = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = coord[i];
+                    const bool ok = c >= 0 && (unsigned)((c >> 20) + dt) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + dy) < (unsigned)p.Y &&
+                                    (unsigned)((c & 1023) + dx) < (unsigned)p.X;
+                    okmask |= (ok ? 1u : 0u) << i;
+                }
+                const float* src = p.x + (size_t)(v0 + (long long)dt * YX + (long long)dy * p.X + dx) * p.Cin + 4 * k4;
+                for (int ch = 0; ch < KCH; ++ch, ++g) {
+                    const unsigned s = g & 1u, use = g >> 1;
+                    float4 a[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        a[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(4 * i) * p.Cin + ch * kConvKC))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                    conv_mbar_wait(bar0 + 8u * (2 + s), (use & 1u) ^ 1u);             // stage free (passes at once on first use)
+                    unsigned char* st = conv_smem + s * stage_bytes;
+                    if (tid == 0) {
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar0 + 8u * s), "r"(2u * wblock) : "memory");
+                        conv_bulk_load(s0 + (unsigned)(s * stage_bytes) + 4u * kConvABytes,
+                                       p.wprep + ((size_t)tap * KCH + ch) * 2 * (size_t)Cout * kConvKC, 2u * wblock, bar0 + 8u * s);
+                    }
+                    unsigned char* ahi = st + (size_t)(2 * ti) * kConvABytes + (size_t)k4 * kConvLboA;
+                    unsigned char* alo = ahi + kConvABytes;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = wrow0 + 4 * i + rsub;
+                        const unsigned off = (unsigned)(row >> 3) * 128u + (unsigned)(row & 7) * 16u;
+                        float4 x4 = a[i], h4, l4;
+                        if (p.relu_in) { x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f); }
+                        tf32_split(x4.x, h4.x, l4.x); tf32_split(x4.y, h4.y, l4.y);
+                        tf32_split(x4.z, h4.z, l4.z); tf32_split(x4.w, h4.w, l4.w);
+                        *reinterpret_cast<float4*>(ahi + off) = h4;
+                        *reinterpret_cast<float4*>(alo + off) = l4;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar0 + 8u * s) : "memory");
+                }
+            }
+            // ---- epilogue: this warp's 32 TMEM lanes of its accumulator
+            conv_mbar_wait(bar0 + 32u, tcount & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const long long v = tile * kConvTileRows + tid;                          // epilogue: thread = accumulator row (TMEM lane)
+            const bool live = v < p.NV;
+            const unsigned taddr = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(ti * 256);
+            float* orow = p.out + (size_t)v * Cout;
+            for (int c0 = 0; c0 < Cout; c0 += 32) {
+                float acc[32];
+                tmem_ld32(taddr + (unsigned)c0, acc);
+                if (live) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4*>(orow + c0 + 4 * q) =
+                            make_float4(acc[4 * q] + sBias[c0 + 4 * q], acc[4 * q + 1] + sBias[c0 + 4 * q + 1],
+                                        acc[4 * q + 2] + sBias[c0 + 4 * q + 2], acc[4 * q + 3] + sBias[c0 + 4 * q + 3]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar0 + 40u) : "memory");
+        }
+    } else if (lane == 0) {
+        // =========================== MMA issuer ===========================
+        const unsigned idesc = umma_idesc_tf32(128, Cout);
+        const unsigned lboA = (unsigned)kConvLboA, lboW = (unsigned)(Cout / 8) * 128u;
+        unsigned g = 0, tcount = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            conv_mbar_wait(bar0 + 40u, (tcount & 1u) ^ 1u);                          // accumulators drained
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            for (int it = 0; it < NIT; ++it, ++g) {
+                const unsigned s = g & 1u, use = g >> 1;
+                conv_mbar_wait(bar0 + 8u * s, use & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const unsigned sa = s0 + (unsigned)(s * stage_bytes), sw = sa + 4u * kConvABytes;
+#pragma unroll
+                for (int ti = 0; ti < 2; ++ti) {
+                    const unsigned d = tmem_base + (unsigned)(ti * 256);
+#pragma unroll
+                    for (int j = 0; j < kConvKC / 8; ++j) {
+                        const unsigned long long ahi = umma_desc(sa + (unsigned)(2 * ti) * kConvABytes + (unsigned)(2 * j) * lboA, lboA, 128u);
+                        const unsigned long long alo = umma_desc(sa + (unsigned)(2 * ti + 1) * kConvABytes + (unsigned)(2 * j) * lboA, lboA, 128u);
+                        const unsigned long long whi = umma_desc(sw + (unsigned)(2 * j) * lboW, lboW, 128u);
+                        const unsigned long long wlo = umma_desc(sw + wblock + (unsigned)(2 * j) * lboW, lboW, 128u);
+                        umma_tf32(d, alo, whi, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                        umma_tf32(d, ahi, wlo, idesc, 1u);
+                        umma_tf32(d, ahi, whi, idesc, 1u);
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar0 + 8u * (2 + s)) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar0 + 32u) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+}  // namespace dlsg
+#endif

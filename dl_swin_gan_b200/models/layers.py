@@ -11,6 +11,8 @@ import torch
 from torch import nn
 
 _CONV_PRECISION = "tf32x3"
+_TC_CONV = True          # route qualifying 3x3x3 layers to the hand-written tensor-core kernel (models/conv3d.py) in "tf32x3" mode
+_CONV_MODES = ("tf32x3", "tf32x2", "tf32r", "fp32", "tf32", "bf16")
 
 
 def set_conv_precision(mode: str) -> None:
@@ -25,8 +27,8 @@ def set_conv_precision(mode: str) -> None:
               1.2e-3 NRMSE against the fp32 result after five unrolls of the Swin network (measured, tools/model_precision_probe.py);
     "bf16"    autocast to bfloat16 (about 1e-2)."""
     global _CONV_PRECISION
-    if mode not in ("tf32x3", "fp32", "tf32", "bf16"):
-        raise ValueError("conv precision must be 'tf32x3', 'fp32', 'tf32' or 'bf16'")
+    if mode not in _CONV_MODES:
+        raise ValueError("conv precision must be one of %s" % (_CONV_MODES,))
     _CONV_PRECISION = mode
 
 
@@ -93,11 +95,15 @@ def conv_forward(conv: nn.Module, x: torch.Tensor) -> torch.Tensor:
     if mode == "bf16":
         with torch.autocast("cuda", dtype=torch.bfloat16):
             return conv(x).float()
-    tf32 = mode in ("tf32", "tf32x3")
+    tf32 = mode in ("tf32", "tf32x3", "tf32x2", "tf32r")
     with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
                                     deterministic=torch.backends.cudnn.deterministic, allow_tf32=tf32):
-        if mode != "tf32x3" or x.dtype != torch.float32:
+        if mode == "tf32" or not tf32 or x.dtype != torch.float32:
             return conv(x)
+        if mode == "tf32x3" and _TC_CONV:
+            from . import conv3d
+            if conv3d.supported(conv, x):
+                return conv3d.conv3d_k3(x, conv.weight, conv.bias)
         if isinstance(conv, nn.ConvTranspose3d):
             def f(a, w, b):
                 return torch.nn.functional.conv_transpose3d(a, w, b, conv.stride, conv.padding, conv.output_padding, conv.groups, conv.dilation)
@@ -107,7 +113,11 @@ def conv_forward(conv: nn.Module, x: torch.Tensor) -> torch.Tensor:
         xh, xl = _tf32_split(x)
         wh, wl = _tf32_split(conv.weight)
         xh = xh.contiguous(memory_format=torch.channels_last_3d)
+        if mode == "tf32r":
+            return f(xh, wh, conv.bias)
         xl = xl.contiguous(memory_format=torch.channels_last_3d)
+        if mode == "tf32x2":
+            return f(xh, wh, conv.bias) + f(xl, wh, None)
         return f(xh, wh, conv.bias) + f(xl, wh, None) + f(xh, wl, None)
 
 

@@ -1,0 +1,63 @@
+"""The tensor-core 3 x 3 x 3 convolution (csrc/conv3d_tc.cuh) against fp64 torch on the B200."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # NB, Cin, Cout, T, Y, X, bias
+    (1, 32, 32, 3, 5, 7, True),          # a single partial tile
+    (2, 64, 64, 4, 9, 16, True),         # several tiles, batch boundary inside a tile
+    (1, 160, 160, 3, 16, 24, True),      # the Swin denoiser's channel count
+    (1, 64, 32, 2, 33, 21, False),
+    (1, 96, 160, 5, 12, 40, True),
+]
+
+
+def rel(a, b):
+    return float((a.double() - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv3d_k3_matches_fp64(case):
+    from dl_swin_gan_b200.models.conv3d import conv3d_k3
+    nb, cin, cout, t, y, x, has_bias = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(cin * 1000 + cout + t)
+    inp = torch.randn(nb, cin, t, y, x, generator=g, device=dev)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g, device=dev) / (27 * cin) ** 0.5
+    b = torch.randn(cout, generator=g, device=dev) if has_bias else None
+    ref = torch.nn.functional.conv3d(inp.double(), w.double(), b.double() if has_bias else None, padding=1)
+    out = conv3d_k3(inp, w, b)
+    assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last_3d)
+    # 3xTF32 with the tensor core's fp32 accumulator: 2e-6 at K = 27*32, 1.5e-5 at K = 27*160 (measured); TF32 alone is 5e-4
+    assert rel(out, ref) < 3e-5, rel(out, ref)
+    out_r = conv3d_k3(inp, w, b, relu_in=True)
+    ref_r = torch.nn.functional.conv3d(inp.double().relu(), w.double(), b.double() if has_bias else None, padding=1)
+    assert rel(out_r, ref_r) < 3e-5
+
+
+def test_conv_forward_routes_to_the_kernel_and_matches_cudnn_path():
+    from dl_swin_gan_b200 import _lib
+    from dl_swin_gan_b200.models import layers
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    conv = torch.nn.Conv3d(64, 64, 3, padding=1).to(dev)
+    x = torch.randn(2, 64, 6, 20, 24, device=dev)
+    keep = layers.get_conv_precision()
+    try:
+        layers.set_conv_precision("tf32x3")
+        n0 = _lib.load().dlsg_launch_count()
+        with torch.no_grad():
+            y = layers.conv_forward(conv, x)
+        assert _lib.load().dlsg_launch_count() == n0 + 1
+        layers.set_conv_precision("fp32")
+        with torch.no_grad():
+            y32 = layers.conv_forward(conv, x)
+    finally:
+        layers.set_conv_precision(keep)
+    assert rel(y, y32.double()) < 2e-5
+    # training keeps the differentiable cuDNN path
+    xg = x.clone().requires_grad_(True)
+    n0 = _lib.load().dlsg_launch_count()
+    layers.conv_forward(conv, xg).sum().backward()
+    assert _lib.load().dlsg_launch_count() == n0 and xg.grad is not None

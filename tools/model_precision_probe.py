@@ -13,7 +13,7 @@ g = golden(name)
 net = build(name).to(dev)
 maps, mask, y = (torch.from_numpy(a).to(dev) for a in model_problem(name))
 A = SenseModel(maps, weights=mask)
-for tf32 in ("tf32x3", "tf32", "fp32"):
+for tf32 in os.environ.get("PROBE_MODES", "tf32x3,tf32x2,tf32r,tf32,fp32").split(","):
     for tc in (True, False):
         from dl_swin_gan_b200.models import set_conv_precision
         set_conv_precision(tf32)
