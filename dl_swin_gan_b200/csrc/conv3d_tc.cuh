@@ -72,9 +72,14 @@ __device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
     lo = v - hi;
 }
 
+// CS = 0: Cin % 32 == 0, the K loop walks (tap, 32-channel chunk).  CS = 2 / 4: the first layer of a denoiser (Cin = 2 or 4 = re / im of the
+// E map sets): K runs over k = tap * Cin + ci, padded with zero weights to a multiple of 32; a 16-byte quad of a stage is one tap (CS = 4)
+// or two taps (CS = 2) of one voxel, so a stage gathers 8 / 16 taps and the whole layer is 4 / 2 stages per tile.
+template <int CS>
 __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvParams p) {
     extern __shared__ __align__(1024) unsigned char conv_smem[];
-    const int Cout = p.Cout, KCH = p.Cin / kConvKC, NIT = 27 * KCH;
+    const int Cout = p.Cout, KCH = (CS == 0) ? p.Cin / kConvKC : 1;
+    const int NIT = (CS == 0) ? 27 * KCH : (27 * CS + kConvKC - 1) / kConvKC;
     const size_t stage_bytes = conv_stage_bytes(Cout);
     const unsigned wblock = (unsigned)Cout * kConvKC * 4;            // one of w_hi / w_lo for a stage
     float* sBias = reinterpret_cast<float*>(conv_smem + kConvStages * stage_bytes);
@@ -124,30 +129,60 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                     coord[i] = (int)((vi / YX) % p.T) << 20 | (int)(r1 / p.X) << 10 | (int)(r1 % p.X);
                 } else coord[i] = -1;
             }
-            for (int tap = 0; tap < 27; ++tap) {
+            unsigned okmask = 0;
+            const float* src = p.x;
+            // shifted voxel of row i for one tap: pointer to its Cin values, or NULL outside the volume (small-Cin modes)
+            auto tap_ptr = [&](int i, int tap) -> const float* {
+                const int c = coord[i];
                 const int dt = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
-                unsigned okmask = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = coord[i];
-                    const bool ok = c >= 0 && (unsigned)((c >> 20) + dt) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + dy) < (unsigned)p.Y &&
-                                    (unsigned)((c & 1023) + dx) < (unsigned)p.X;
-                    okmask |= (ok ? 1u : 0u) << i;
-                }
-                const float* src = p.x + (size_t)(v0 + (long long)dt * YX + (long long)dy * p.X + dx) * p.Cin + 4 * k4;
-                for (int ch = 0; ch < KCH; ++ch, ++g) {
+                const bool ok = tap < 27 && c >= 0 && (unsigned)((c >> 20) + dt) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + dy) < (unsigned)p.Y &&
+                                (unsigned)((c & 1023) + dx) < (unsigned)p.X;
+                return ok ? p.x + (size_t)(v0 + 4 * i + (long long)dt * YX + (long long)dy * p.X + dx) * CS : nullptr;
+            };
+            for (int it = 0; it < NIT; ++it, ++g) {
+                {
                     const unsigned s = g & 1u, use = g >> 1;
                     float4 a[8];
+                    if (CS == 0) {
+                        const int tap = it / KCH, ch = it - tap * KCH;
+                        if (ch == 0) {
+                            const int dt = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
+                            okmask = 0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        a[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(4 * i) * p.Cin + ch * kConvKC))
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int i = 0; i < 8; ++i) {
+                                const int c = coord[i];
+                                const bool ok = c >= 0 && (unsigned)((c >> 20) + dt) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + dy) < (unsigned)p.Y &&
+                                                (unsigned)((c & 1023) + dx) < (unsigned)p.X;
+                                okmask |= (ok ? 1u : 0u) << i;
+                            }
+                            src = p.x + (size_t)(v0 + (long long)dt * YX + (long long)dy * p.X + dx) * p.Cin + 4 * k4;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            a[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(4 * i) * p.Cin + ch * kConvKC))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else if (CS == 4) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float* q = tap_ptr(i, 8 * it + k4);
+                            a[i] = q ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float* q0 = tap_ptr(i, 2 * (8 * it + k4));
+                            const float* q1 = tap_ptr(i, 2 * (8 * it + k4) + 1);
+                            const float2 lo2 = q0 ? __ldg(reinterpret_cast<const float2*>(q0)) : make_float2(0.f, 0.f);
+                            const float2 hi2 = q1 ? __ldg(reinterpret_cast<const float2*>(q1)) : make_float2(0.f, 0.f);
+                            a[i] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+                        }
+                    }
                     conv_mbar_wait(bar0 + 8u * (2 + s), (use & 1u) ^ 1u);             // stage free (passes at once on first use)
                     unsigned char* st = conv_smem + s * stage_bytes;
                     if (tid == 0) {
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar0 + 8u * s), "r"(2u * wblock) : "memory");
                         conv_bulk_load(s0 + (unsigned)(s * stage_bytes) + 4u * kConvABytes,
-                                       p.wprep + ((size_t)tap * KCH + ch) * 2 * (size_t)Cout * kConvKC, 2u * wblock, bar0 + 8u * s);
+                                       p.wprep + (size_t)it * 2 * (size_t)Cout * kConvKC, 2u * wblock, bar0 + 8u * s);
                     }
                     unsigned char* ahi = st + (size_t)(2 * ti) * kConvABytes + (size_t)k4 * kConvLboA;
                     unsigned char* alo = ahi + kConvABytes;
@@ -225,6 +260,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(512) : "memory");
     }
 }
+
 
 }  // namespace dlsg
 #endif

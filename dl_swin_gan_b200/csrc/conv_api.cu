@@ -1,13 +1,18 @@
 // C-ABI entry point of the denoisers' 3 x 3 x 3 convolution (declared in include/dlsg_b200.h).
 #include "../../include/dlsg_b200.h"
+#include <cstdlib>
 #include "conv3d_tc.cuh"
 
 extern "C" {
 
+static int conv_kc(int Cin, int Cout) {
+    if (Cin <= 0 || Cout <= 0 || (Cin % dlsg::kConvKC != 0 && Cin != 2 && Cin != 4) || Cout % 32 != 0 || Cout > 256) return 0;
+    return dlsg::conv_smem_bytes(Cout) <= 227 * 1024 ? dlsg::kConvKC : 0;
+}
+
 int dlsg_conv3d_k3_supported(int Cin, int Cout) {
 #if defined(__CUDACC__)
-    if (Cin <= 0 || Cout <= 0 || Cin % dlsg::kConvKC != 0 || Cout % 32 != 0 || Cout > 256) return 0;
-    return dlsg::conv_smem_bytes(Cout) <= 227 * 1024 ? 1 : 0;
+    return conv_kc(Cin, Cout);
 #else
     (void)Cin; (void)Cout;
     return 0;
@@ -31,8 +36,10 @@ int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* b
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long ntiles = (p.NV + kConvTileRows - 1) / kConvTileRows;
     const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-    return launch(conv3d_k3_tf32x3_kernel, dim3(grid), dim3(kConvThreads), conv_smem_bytes(Cout), (stream_t)stream, p) == 0
-               ? DLSG_OK : DLSG_ELAUNCH;
+    const int rc = Cin == 2 ? launch(conv3d_k3_tf32x3_kernel<2>, dim3(grid), dim3(kConvThreads), conv_smem_bytes(Cout), (stream_t)stream, p)
+                 : Cin == 4 ? launch(conv3d_k3_tf32x3_kernel<4>, dim3(grid), dim3(kConvThreads), conv_smem_bytes(Cout), (stream_t)stream, p)
+                            : launch(conv3d_k3_tf32x3_kernel<0>, dim3(grid), dim3(kConvThreads), conv_smem_bytes(Cout), (stream_t)stream, p);
+    return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
 #else
     (void)x; (void)wprep; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)relu_in; (void)stream;
     return DLSG_EUNSUPPORTED;      // tcgen05 / TMEM have no host emulation

@@ -17,11 +17,23 @@ def _split(t: torch.Tensor):
     return hi, t - hi
 
 
-def prepare_weight(weight: torch.Tensor) -> torch.Tensor:
-    """weight [Cout, Cin, 3, 3, 3] -> the kernel's operand image [27][Cin/32][hi|lo][8][Cout/8][8][4] (include/dlsg_b200.h)."""
+def prepare_weight(weight: torch.Tensor, kc: int = 32) -> torch.Tensor:
+    """weight [Cout, Cin, 3, 3, 3] -> the kernel's operand image (include/dlsg_b200.h); kc = K elements per pipeline stage, as
+    `dlsg_conv3d_k3_supported(Cin, Cout)` reports it.
+      Cin % 32 == 0:  [27][Cin/kc][hi|lo][kc/4][Cout/8][8][4]                     K walks (tap, channel chunk)
+      Cin = 2 or 4:   [ceil(27 Cin / kc)][hi|lo][kc/4][Cout/8][8][4]              K index = tap * Cin + ci, zero-padded"""
     cout, cin = weight.shape[:2]
-    hi, lo = _split(weight.detach().float().contiguous())
-    hl = torch.stack([hi, lo]).reshape(2, cout // 8, 8, cin // 32, 8, 4, 27)      # [h, co/8, co%8, chunk, k4, ci%4, tap]
+    w = weight.detach().float().contiguous()
+    if cin in (2, 4):
+        k = 27 * cin
+        kpad = -(-k // kc) * kc
+        wk = torch.zeros(cout, kpad, device=w.device, dtype=torch.float32)
+        wk[:, :k] = w.reshape(cout, cin, 27).permute(0, 2, 1).reshape(cout, k)
+        hi, lo = _split(wk)
+        hl = torch.stack([hi, lo]).reshape(2, cout // 8, 8, kpad // kc, kc // 4, 4)          # [h, co/8, co%8, stage, k4, k%4]
+        return hl.permute(3, 0, 4, 1, 2, 5).contiguous()
+    hi, lo = _split(w)
+    hl = torch.stack([hi, lo]).reshape(2, cout // 8, 8, cin // kc, kc // 4, 4, 27)          # [h, co/8, co%8, chunk, k4, ci%4, tap]
     return hl.permute(6, 3, 0, 4, 1, 2, 5).contiguous()
 
 
@@ -30,7 +42,8 @@ def _cached_weight(weight: torch.Tensor) -> torch.Tensor:
     hit = _WPREP.get(key)
     if hit is not None and hit[0] == weight._version:
         return hit[1]
-    prep = prepare_weight(weight)
+    kc = _lib.load().dlsg_conv3d_k3_supported(weight.shape[1], weight.shape[0])
+    prep = prepare_weight(weight, kc)
     _WPREP[key] = (weight._version, prep)
     return prep
 

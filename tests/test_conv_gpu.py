@@ -10,6 +10,9 @@ CASES = [  # NB, Cin, Cout, T, Y, X, bias
     (1, 160, 160, 3, 16, 24, True),      # the Swin denoiser's channel count
     (1, 64, 32, 2, 33, 21, False),
     (1, 96, 160, 5, 12, 40, True),
+    (2, 4, 160, 4, 10, 24, True),        # first layer of the Swin denoiser (re / im of two map sets)
+    (1, 2, 64, 5, 17, 20, True),         # first layer of the ResNet denoiser at E = 1
+    (1, 4, 32, 2, 3, 5, False),
 ]
 
 
