@@ -32,13 +32,18 @@ constexpr int kConvTileRows = 256;                 // voxels per CTA tile (two U
 constexpr int kConvLboA = 128 * 16 + 16;           // bytes between the 4-channel planes of an A block: +16 so that the 8 planes a quarter-warp stores hit 8 different bank groups
 constexpr int kConvABytes = (kConvKC / 4) * kConvLboA;   // one [128 x 32] fp32 operand block
 
+enum : int { CONV_GATHER = 0, CONV_UNPATCH = 1 };
 struct ConvParams {
-    const float* x;        // [NB, T, Y, X, Cin]
-    const float* wprep;    // [27][Cin/32][hi|lo][8][Cout/8][8][4]
+    const float* x;        // [NB, T, Y, X, Cin]          (input volume)
+    const float* wprep;    // [taps][Cin/32][hi|lo][8][Cout/8][8][4]
     const float* bias;     // [Cout] or NULL
-    float* out;            // [NB, T, Y, X, Cout]
+    float* out;            // [NB, To, Yo, Xo, Cout]
     int NB, T, Y, X, Cin, Cout;
-    long long NV;          // NB*T*Y*X
+    int To, Yo, Xo;        // output volume
+    int ksz, stride, pad;  // CONV_GATHER: out[o] = sum over the ksz^3 taps of x[o * stride - pad + tap];  3,1,1 = 'same' 3x3x3;  P,P,0 = patch embedding
+                           // CONV_UNPATCH: out[i * ksz + tap] = W_tap x[i]  (transposed convolution with kernel = stride = ksz: patch unembedding)
+    int mode;
+    long long NV;          // GEMM rows: output voxels (CONV_GATHER) or input voxels (CONV_UNPATCH)
     int relu_in;           // rectify the input on the fly (ConvBlock's pre-activation)
 };
 
@@ -79,7 +84,9 @@ template <int CS>
 __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvParams p) {
     extern __shared__ __align__(1024) unsigned char conv_smem[];
     const int Cout = p.Cout, KCH = (CS == 0) ? p.Cin / kConvKC : 1;
-    const int NIT = (CS == 0) ? 27 * KCH : (27 * CS + kConvKC - 1) / kConvKC;
+    const int ksz = p.ksz, ntaps = ksz * ksz * ksz;
+    const bool unpatch = (CS == 0) && p.mode == CONV_UNPATCH;
+    const int NIT = (CS == 0) ? (unpatch ? KCH : ntaps * KCH) : (27 * CS + kConvKC - 1) / kConvKC;
     const size_t stage_bytes = conv_stage_bytes(Cout);
     const unsigned wblock = (unsigned)Cout * kConvKC * 4;            // one of w_hi / w_lo for a stage
     float* sBias = reinterpret_cast<float*>(conv_smem + kConvStages * stage_bytes);
@@ -107,8 +114,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const unsigned tmem_base = *tmem_slot;
 
-    const long long ntiles = (p.NV + kConvTileRows - 1) / kConvTileRows;
-    const long long YX = (long long)p.Y * p.X;
+    // CONV_UNPATCH: a tile is (256 input voxels, one of the ksz^3 output positions inside their patches); the taps of a row tile are consecutive tiles
+    const long long rtiles = (p.NV + kConvTileRows - 1) / kConvTileRows;
+    const long long ntiles = unpatch ? rtiles * ntaps : rtiles;
+    const long long YX = (long long)p.Y * p.X;                       // input plane
+    const long long YXo = (long long)p.Yo * p.Xo;                    // output plane
 
     if (warp < kConvProducers / 32) {
         // =========================== producers, then epilogue ===========================
@@ -119,25 +129,36 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
         const int wrow0 = (warp & 3) * 32;                       // first row of this warp inside its 128-row block
         unsigned g = 0, tcount = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-            const long long v0 = tile * kConvTileRows + ti * 128 + wrow0 + rsub;      // this thread's rows: v0 + 4 i
-            int coord[8];                                          // packed (t, y, x) of the 8 rows, -1 = beyond the volume
+            const long long rtile = unpatch ? tile / ntaps : tile;
+            const int cls = unpatch ? (int)(tile - rtile * ntaps) : 0;
+            const long long v0 = rtile * kConvTileRows + ti * 128 + wrow0 + rsub;     // this thread's GEMM rows: v0 + 4 i
+            // per row: packed (t, y, x) + 1 of the first tap's input voxel (-1 = row beyond the problem) and that voxel's index
+            int coord[8], ibase[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const long long vi = v0 + 4 * i;
+                coord[i] = -1; ibase[i] = 0;
                 if (vi < p.NV) {
-                    const long long r1 = vi % YX;
-                    coord[i] = (int)((vi / YX) % p.T) << 20 | (int)(r1 / p.X) << 10 | (int)(r1 % p.X);
-                } else coord[i] = -1;
+                    if (unpatch) { coord[i] = 0; ibase[i] = (int)vi; }
+                    else {
+                        const long long r1 = vi % YXo;
+                        const int n = (int)(vi / (YXo * p.To));
+                        const int t0 = (int)((vi / YXo) % p.To) * p.stride - p.pad, y0 = (int)(r1 / p.Xo) * p.stride - p.pad,
+                                  x0 = (int)(r1 % p.Xo) * p.stride - p.pad;
+                        coord[i] = (t0 + 1) << 20 | (y0 + 1) << 10 | (x0 + 1);
+                        ibase[i] = (int)((((long long)n * p.T + t0) * p.Y + y0) * p.X + x0);
+                    }
+                }
             }
             unsigned okmask = 0;
-            const float* src = p.x;
-            // shifted voxel of row i for one tap: pointer to its Cin values, or NULL outside the volume (small-Cin modes)
+            int tapoff = 0;
+            // shifted voxel of row i for one tap: pointer to its Cin values, or NULL outside the volume (small-Cin modes, 3 x 3 x 3 only)
             auto tap_ptr = [&](int i, int tap) -> const float* {
                 const int c = coord[i];
-                const int dt = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
-                const bool ok = tap < 27 && c >= 0 && (unsigned)((c >> 20) + dt) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + dy) < (unsigned)p.Y &&
-                                (unsigned)((c & 1023) + dx) < (unsigned)p.X;
-                return ok ? p.x + (size_t)(v0 + 4 * i + (long long)dt * YX + (long long)dy * p.X + dx) * CS : nullptr;
+                const int a = tap / 9, b2 = (tap / 3) % 3, c2 = tap % 3;
+                const bool ok = tap < 27 && c >= 0 && (unsigned)((c >> 20) + a - 1) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + b2 - 1) < (unsigned)p.Y &&
+                                (unsigned)((c & 1023) + c2 - 1) < (unsigned)p.X;
+                return ok ? p.x + ((long long)ibase[i] + ((long long)a * p.Y + b2) * p.X + c2) * CS : nullptr;
             };
             for (int it = 0; it < NIT; ++it, ++g) {
                 {
@@ -146,20 +167,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                     if (CS == 0) {
                         const int tap = it / KCH, ch = it - tap * KCH;
                         if (ch == 0) {
-                            const int dt = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
                             okmask = 0;
+                            if (unpatch) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int c = coord[i];
-                                const bool ok = c >= 0 && (unsigned)((c >> 20) + dt) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + dy) < (unsigned)p.Y &&
-                                                (unsigned)((c & 1023) + dx) < (unsigned)p.X;
-                                okmask |= (ok ? 1u : 0u) << i;
+                                for (int i = 0; i < 8; ++i) okmask |= (coord[i] >= 0 ? 1u : 0u) << i;
+                                tapoff = 0;
+                            } else {
+                                const int ta = tap / (ksz * ksz), tb = (tap / ksz) % ksz, tc = tap % ksz;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int c = coord[i];
+                                    const bool ok = c >= 0 && (unsigned)((c >> 20) + ta - 1) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + tb - 1) < (unsigned)p.Y &&
+                                                    (unsigned)((c & 1023) + tc - 1) < (unsigned)p.X;
+                                    okmask |= (ok ? 1u : 0u) << i;
+                                }
+                                tapoff = (ta * p.Y + tb) * p.X + tc;
                             }
-                            src = p.x + (size_t)(v0 + (long long)dt * YX + (long long)dy * p.X + dx) * p.Cin + 4 * k4;
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            a[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(4 * i) * p.Cin + ch * kConvKC))
+                            a[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.x + ((long long)ibase[i] + tapoff) * p.Cin + ch * kConvKC + 4 * k4))
                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                     } else if (CS == 4) {
 #pragma unroll
@@ -182,7 +209,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                     if (tid == 0) {
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar0 + 8u * s), "r"(2u * wblock) : "memory");
                         conv_bulk_load(s0 + (unsigned)(s * stage_bytes) + 4u * kConvABytes,
-                                       p.wprep + (size_t)it * 2 * (size_t)Cout * kConvKC, 2u * wblock, bar0 + 8u * s);
+                                       p.wprep + ((size_t)cls * KCH + it) * 2 * (size_t)Cout * kConvKC, 2u * wblock, bar0 + 8u * s);
                     }
                     unsigned char* ahi = st + (size_t)(2 * ti) * kConvABytes + (size_t)k4 * kConvLboA;
                     unsigned char* alo = ahi + kConvABytes;
@@ -204,10 +231,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
             // ---- epilogue: this warp's 32 TMEM lanes of its accumulator
             conv_mbar_wait(bar0 + 32u, tcount & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const long long v = tile * kConvTileRows + tid;                          // epilogue: thread = accumulator row (TMEM lane)
+            const long long v = rtile * kConvTileRows + tid;                         // epilogue: thread = accumulator row (TMEM lane)
             const bool live = v < p.NV;
             const unsigned taddr = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(ti * 256);
-            float* orow = p.out + (size_t)v * Cout;
+            long long vout = v;
+            if (unpatch && live) {                                                   // input voxel (n, t, y, x) -> output voxel (n, t k + a, y k + b, x k + c)
+                const long long r1 = v % YX;
+                const long long nt = v / YX;                                          // n * T + t
+                const int ta = cls / (ksz * ksz), tb = (cls / ksz) % ksz, tc = cls % ksz;
+                vout = (((nt / p.T) * p.To + (nt % p.T) * ksz + ta) * p.Yo + (r1 / p.X) * ksz + tb) * p.Xo + (r1 % p.X) * ksz + tc;
+            }
+            float* orow = p.out + (size_t)vout * Cout;
             for (int c0 = 0; c0 < Cout; c0 += 32) {
                 float acc[32];
                 tmem_ld32(taddr + (unsigned)c0, acc);

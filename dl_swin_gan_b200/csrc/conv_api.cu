@@ -19,30 +19,73 @@ int dlsg_conv3d_k3_supported(int Cin, int Cout) {
 #endif
 }
 
-int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
-                              int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream) {
 #if defined(__CUDACC__)
+static int conv_launch(dlsg::ConvParams& p, void* stream) {
     using namespace dlsg;
-    if (!x || !wprep || !out || NB <= 0 || T <= 0 || Y <= 0 || X <= 0) return DLSG_EINVAL;
-    if (!dlsg_conv3d_k3_supported(Cin, Cout) || X > 1023 || Y > 1023 || T > 2047) return DLSG_EUNSUPPORTED;
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wprep) | reinterpret_cast<uintptr_t>(out)) & 15) return DLSG_EINVAL;
-    ConvParams p{};
-    p.x = x; p.wprep = wprep; p.bias = bias; p.out = out;
-    p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin; p.Cout = Cout;
-    p.NV = (long long)NB * T * Y * X;
-    p.relu_in = relu_in ? 1 : 0;
+    if (!p.x || !p.wprep || !p.out || p.NB <= 0 || p.T <= 0 || p.Y <= 0 || p.X <= 0 || p.To <= 0 || p.Yo <= 0 || p.Xo <= 0) return DLSG_EINVAL;
+    if (!conv_kc(p.Cin, p.Cout) || p.X > 1022 || p.Y > 1022 || p.T > 2046) return DLSG_EUNSUPPORTED;
+    if ((long long)p.NB * p.T * p.Y * p.X > 0x7fffffffLL || (long long)p.NB * p.To * p.Yo * p.Xo > 0x7fffffffLL) return DLSG_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.wprep) | reinterpret_cast<uintptr_t>(p.out)) & 15) return DLSG_EINVAL;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long ntiles = (p.NV + kConvTileRows - 1) / kConvTileRows;
+    long long ntiles = (p.NV + kConvTileRows - 1) / kConvTileRows;
+    if (p.mode == CONV_UNPATCH) ntiles *= (long long)p.ksz * p.ksz * p.ksz;
     const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-    const int rc = Cin == 2 ? launch(conv3d_k3_tf32x3_kernel<2>, dim3(grid), dim3(kConvThreads), conv_smem_bytes(Cout), (stream_t)stream, p)
-                 : Cin == 4 ? launch(conv3d_k3_tf32x3_kernel<4>, dim3(grid), dim3(kConvThreads), conv_smem_bytes(Cout), (stream_t)stream, p)
-                            : launch(conv3d_k3_tf32x3_kernel<0>, dim3(grid), dim3(kConvThreads), conv_smem_bytes(Cout), (stream_t)stream, p);
+    const size_t smem = conv_smem_bytes(p.Cout);
+    const int rc = p.Cin == 2 ? launch(conv3d_k3_tf32x3_kernel<2>, dim3(grid), dim3(kConvThreads), smem, (stream_t)stream, p)
+                 : p.Cin == 4 ? launch(conv3d_k3_tf32x3_kernel<4>, dim3(grid), dim3(kConvThreads), smem, (stream_t)stream, p)
+                              : launch(conv3d_k3_tf32x3_kernel<0>, dim3(grid), dim3(kConvThreads), smem, (stream_t)stream, p);
     return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
+}
+#endif
+
+int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
+                              int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream) {
+#if defined(__CUDACC__)
+    dlsg::ConvParams p{};
+    p.x = x; p.wprep = wprep; p.bias = bias; p.out = out;
+    p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin; p.Cout = Cout;
+    p.To = T; p.Yo = Y; p.Xo = X; p.ksz = 3; p.stride = 1; p.pad = 1; p.mode = dlsg::CONV_GATHER;
+    p.NV = (long long)NB * T * Y * X;
+    p.relu_in = relu_in ? 1 : 0;
+    return conv_launch(p, stream);
 #else
     (void)x; (void)wprep; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)relu_in; (void)stream;
     return DLSG_EUNSUPPORTED;      // tcgen05 / TMEM have no host emulation
+#endif
+}
+
+int dlsg_conv3d_patch_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
+                                 int NB, int T, int Y, int X, int Cin, int Cout, int patch, void* stream) {
+#if defined(__CUDACC__)
+    if (patch < 1 || patch > 8 || Cin % dlsg::kConvKC != 0) return DLSG_EUNSUPPORTED;
+    if (T % patch || Y % patch || X % patch) return DLSG_EINVAL;
+    dlsg::ConvParams p{};
+    p.x = x; p.wprep = wprep; p.bias = bias; p.out = out;
+    p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin; p.Cout = Cout;
+    p.To = T / patch; p.Yo = Y / patch; p.Xo = X / patch; p.ksz = patch; p.stride = patch; p.pad = 0; p.mode = dlsg::CONV_GATHER;
+    p.NV = (long long)NB * p.To * p.Yo * p.Xo;
+    return conv_launch(p, stream);
+#else
+    (void)x; (void)wprep; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)patch; (void)stream;
+    return DLSG_EUNSUPPORTED;
+#endif
+}
+
+int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
+                                   int NB, int T, int Y, int X, int Cin, int Cout, int patch, void* stream) {
+#if defined(__CUDACC__)
+    if (patch < 1 || patch > 8 || Cin % dlsg::kConvKC != 0) return DLSG_EUNSUPPORTED;
+    dlsg::ConvParams p{};
+    p.x = x; p.wprep = wprep; p.bias = bias; p.out = out;
+    p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin; p.Cout = Cout;
+    p.To = T * patch; p.Yo = Y * patch; p.Xo = X * patch; p.ksz = patch; p.stride = patch; p.pad = 0; p.mode = dlsg::CONV_UNPATCH;
+    p.NV = (long long)NB * T * Y * X;
+    return conv_launch(p, stream);
+#else
+    (void)x; (void)wprep; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)patch; (void)stream;
+    return DLSG_EUNSUPPORTED;
 #endif
 }
 

@@ -1,6 +1,9 @@
-"""3 x 3 x 3 'same' convolution of the denoisers on the B200 tensor cores (csrc/conv3d_tc.cuh, `dlsg_conv3d_k3_tf32x3_f32`):
-the arithmetic of `set_conv_precision("tf32x3")` - three TF32 products on operands split into a TF32 head and the remainder -
-in ONE kernel that splits the operands while it stages them, instead of three cuDNN convolutions around elementwise passes.
+"""Denoiser convolutions on the B200 tensor cores (csrc/conv3d_tc.cuh): the arithmetic of `set_conv_precision("tf32x3")` -
+three TF32 products on operands split into a TF32 head and the remainder - in ONE kernel that splits the operands while it stages
+them, instead of three cuDNN convolutions around elementwise passes.  Three layer shapes (all the denoisers have):
+  * nn.Conv3d(kernel 3, 'same')                       `dlsg_conv3d_k3_tf32x3_f32`       (Cin % 32 == 0, or the first layer's Cin = 2 / 4)
+  * nn.Conv3d(kernel = stride = patch)                `dlsg_conv3d_patch_tf32x3_f32`    (PatchEmbed3D.proj)
+  * nn.ConvTranspose3d(kernel = stride = patch)       `dlsg_conv3d_unpatch_tf32x3_f32`  (PatchUnembed3D.proj)
 Inference only (no autograd); `layers.conv_forward` routes here when the layer and the tensor qualify.
 """
 from __future__ import annotations
@@ -9,7 +12,7 @@ import torch
 
 from .. import _lib
 
-_WPREP: dict = {}
+K3, PATCH, UNPATCH = "k3", "patch", "unpatch"
 
 
 def _split(t: torch.Tensor):
@@ -17,57 +20,115 @@ def _split(t: torch.Tensor):
     return hi, t - hi
 
 
-def prepare_weight(weight: torch.Tensor, kc: int = 32) -> torch.Tensor:
-    """weight [Cout, Cin, 3, 3, 3] -> the kernel's operand image (include/dlsg_b200.h); kc = K elements per pipeline stage, as
-    `dlsg_conv3d_k3_supported(Cin, Cout)` reports it.
-      Cin % 32 == 0:  [27][Cin/kc][hi|lo][kc/4][Cout/8][8][4]                     K walks (tap, channel chunk)
+def prepare_weight(weight: torch.Tensor, kc: int = 32, transposed: bool = False) -> torch.Tensor:
+    """weight [Cout, Cin, k, k, k] (or [Cin, Cout, k, k, k] of a transposed convolution) -> the kernel's operand image
+    (include/dlsg_b200.h); kc = K elements per pipeline stage, as `dlsg_conv3d_k3_supported(Cin, Cout)` reports it.
+      Cin % 32 == 0:  [k^3][Cin/kc][hi|lo][kc/4][Cout/8][8][4]                    K walks (tap, channel chunk)
       Cin = 2 or 4:   [ceil(27 Cin / kc)][hi|lo][kc/4][Cout/8][8][4]              K index = tap * Cin + ci, zero-padded"""
-    cout, cin = weight.shape[:2]
-    w = weight.detach().float().contiguous()
+    w = weight.detach().float()
+    if transposed:
+        w = w.transpose(0, 1)
+    w = w.contiguous()
+    cout, cin = w.shape[:2]
+    taps = w.shape[2] * w.shape[3] * w.shape[4]
     if cin in (2, 4):
-        k = 27 * cin
+        k = taps * cin
         kpad = -(-k // kc) * kc
         wk = torch.zeros(cout, kpad, device=w.device, dtype=torch.float32)
-        wk[:, :k] = w.reshape(cout, cin, 27).permute(0, 2, 1).reshape(cout, k)
+        wk[:, :k] = w.reshape(cout, cin, taps).permute(0, 2, 1).reshape(cout, k)
         hi, lo = _split(wk)
         hl = torch.stack([hi, lo]).reshape(2, cout // 8, 8, kpad // kc, kc // 4, 4)          # [h, co/8, co%8, stage, k4, k%4]
         return hl.permute(3, 0, 4, 1, 2, 5).contiguous()
     hi, lo = _split(w)
-    hl = torch.stack([hi, lo]).reshape(2, cout // 8, 8, cin // kc, kc // 4, 4, 27)          # [h, co/8, co%8, chunk, k4, ci%4, tap]
+    hl = torch.stack([hi, lo]).reshape(2, cout // 8, 8, cin // kc, kc // 4, 4, taps)        # [h, co/8, co%8, chunk, k4, ci%4, tap]
     return hl.permute(6, 3, 0, 4, 1, 2, 5).contiguous()
 
 
-def _cached_weight(weight: torch.Tensor) -> torch.Tensor:
-    key = (weight.data_ptr(), weight.device, tuple(weight.shape))
-    hit = _WPREP.get(key)
-    if hit is not None and hit[0] == weight._version:
+def _cached_weight(weight: torch.Tensor, transposed: bool) -> torch.Tensor:
+    # the image lives on the parameter object itself (a dictionary keyed by data_ptr would hand a freed model's image to the next
+    # model whose weight lands on the same address); refreshed when the parameter is written (version) or re-homed (data_ptr)
+    try:
+        ver = weight._version
+    except RuntimeError:                   # inference tensors do not track versions: rebuild every call
+        ver = None
+    tag = (ver, weight.data_ptr(), transposed)
+    hit = getattr(weight, "_dlsg_conv_image", None)
+    if hit is not None and ver is not None and hit[0] == tag:
         return hit[1]
-    kc = _lib.load().dlsg_conv3d_k3_supported(weight.shape[1], weight.shape[0])
-    prep = prepare_weight(weight, kc)
-    _WPREP[key] = (weight._version, prep)
+    cin, cout = (weight.shape[0], weight.shape[1]) if transposed else (weight.shape[1], weight.shape[0])
+    kc = _lib.load().dlsg_conv3d_k3_supported(cin, cout)
+    prep = prepare_weight(weight, kc, transposed)
+    try:
+        weight._dlsg_conv_image = (tag, prep)
+    except AttributeError:
+        pass
     return prep
 
 
+def kind(conv: torch.nn.Module, x: torch.Tensor):
+    """Which of the three kernels takes `conv(x)`, or None (then cuDNN does)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5) or conv.groups != 1 or tuple(conv.dilation) != (1, 1, 1):
+        return None
+    if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
+        return None
+    lib = _lib.load()
+    k, s, pd = tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding)
+    cubic = k[0] == k[1] == k[2]
+    if isinstance(conv, torch.nn.ConvTranspose3d):
+        if cubic and k == s and pd == (0, 0, 0) and tuple(conv.output_padding) == (0, 0, 0) and k[0] <= 8 \
+                and conv.in_channels % 32 == 0 and lib.dlsg_conv3d_k3_supported(conv.in_channels, conv.out_channels):
+            return UNPATCH
+        return None
+    if not isinstance(conv, torch.nn.Conv3d) or conv.padding_mode != "zeros":
+        return None
+    if k == (3, 3, 3) and s == (1, 1, 1) and pd == (1, 1, 1) and lib.dlsg_conv3d_k3_supported(conv.in_channels, conv.out_channels):
+        return K3
+    if cubic and k == s and pd == (0, 0, 0) and 1 < k[0] <= 8 and conv.in_channels % 32 == 0 \
+            and all(d % k[0] == 0 for d in x.shape[2:]) and lib.dlsg_conv3d_k3_supported(conv.in_channels, conv.out_channels):
+        return PATCH
+    return None
+
+
 def supported(conv: torch.nn.Module, x: torch.Tensor) -> bool:
-    return (isinstance(conv, torch.nn.Conv3d) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
-            and tuple(conv.kernel_size) == (3, 3, 3) and tuple(conv.stride) == (1, 1, 1) and tuple(conv.padding) == (1, 1, 1)
-            and tuple(conv.dilation) == (1, 1, 1) and conv.groups == 1 and conv.padding_mode == "zeros"
-            and not (torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad))
-            and bool(_lib.load().dlsg_conv3d_k3_supported(conv.in_channels, conv.out_channels)))
+    return kind(conv, x) is not None
+
+
+def _run(fn_name, x, weight, bias, out_dims, last, transposed):
+    lib = _lib.load()
+    nb, cin, t, y, xx = x.shape
+    cout = weight.shape[1] if transposed else weight.shape[0]
+    xc = x.permute(0, 2, 3, 4, 1)
+    if not xc.is_contiguous():
+        xc = xc.contiguous()
+    prep = _cached_weight(weight, transposed)
+    out = torch.empty((nb,) + tuple(out_dims) + (cout,), device=x.device, dtype=torch.float32)
+    b = bias.detach().float().contiguous() if bias is not None else None
+    st = getattr(lib, fn_name)(xc.data_ptr(), prep.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
+                               nb, t, y, xx, cin, cout, int(last), torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(st, fn_name)
+    return out.permute(0, 4, 1, 2, 3)
 
 
 def conv3d_k3(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: bool = False) -> torch.Tensor:
     """x [NB, Cin, T, Y, X] (any layout; used channels-last) -> [NB, Cout, T, Y, X] in channels_last_3d."""
-    lib = _lib.load()
-    nb, cin, t, y, xx = x.shape
-    cout = weight.shape[0]
-    xc = x.permute(0, 2, 3, 4, 1)
-    if not xc.is_contiguous():
-        xc = xc.contiguous()
-    prep = _cached_weight(weight)
-    out = torch.empty((nb, t, y, xx, cout), device=x.device, dtype=torch.float32)
-    b = bias.detach().float().contiguous() if bias is not None else None
-    st = lib.dlsg_conv3d_k3_tf32x3_f32(xc.data_ptr(), prep.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
-                                       nb, t, y, xx, cin, cout, int(relu_in), torch.cuda.current_stream(x.device).cuda_stream)
-    _lib.check(st, "dlsg_conv3d_k3_tf32x3_f32")
-    return out.permute(0, 4, 1, 2, 3)
+    return _run("dlsg_conv3d_k3_tf32x3_f32", x, weight, bias, x.shape[2:], relu_in, False)
+
+
+def conv3d_patch(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
+    """Conv3d with kernel = stride = patch: [NB, Cin, T, Y, X] -> [NB, Cout, T/p, Y/p, X/p]."""
+    p = weight.shape[2]
+    return _run("dlsg_conv3d_patch_tf32x3_f32", x, weight, bias, [d // p for d in x.shape[2:]], p, False)
+
+
+def conv3d_unpatch(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
+    """ConvTranspose3d with kernel = stride = patch (weight [Cin, Cout, p, p, p]): [NB, Cin, T, Y, X] -> [NB, Cout, T p, Y p, X p]."""
+    p = weight.shape[2]
+    return _run("dlsg_conv3d_unpatch_tf32x3_f32", x, weight, bias, [d * p for d in x.shape[2:]], p, True)
+
+
+def forward(conv: torch.nn.Module, x: torch.Tensor, which: str) -> torch.Tensor:
+    if which == K3:
+        return conv3d_k3(x, conv.weight, conv.bias)
+    if which == PATCH:
+        return conv3d_patch(x, conv.weight, conv.bias)
+    return conv3d_unpatch(x, conv.weight, conv.bias)

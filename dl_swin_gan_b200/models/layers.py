@@ -102,8 +102,9 @@ def conv_forward(conv: nn.Module, x: torch.Tensor) -> torch.Tensor:
             return conv(x)
         if mode == "tf32x3" and _TC_CONV:
             from . import conv3d
-            if conv3d.supported(conv, x):
-                return conv3d.conv3d_k3(x, conv.weight, conv.bias)
+            which = conv3d.kind(conv, x)
+            if which is not None:
+                return conv3d.forward(conv, x, which)
         if isinstance(conv, nn.ConvTranspose3d):
             def f(a, w, b):
                 return torch.nn.functional.conv_transpose3d(a, w, b, conv.stride, conv.padding, conv.output_padding, conv.groups, conv.dilation)

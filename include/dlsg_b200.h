@@ -270,17 +270,32 @@ int dlsg_sliding_window_c64(const void* data, void* out, long long outer, int T,
  * (dl_cs/models/swin3D.py:120-134, 225-273 == resnet3d.py), fp32 storage, channels-last.
  * ------------------------------------------------------------------------------------------------ */
 
-/* 1 when the tensor-core kernel takes this channel pair (Cin % 32 == 0, Cout % 32 == 0, shared memory), else 0. */
+/* K elements per pipeline stage (32) when the tensor-core kernel takes this channel pair (Cin % 32 == 0 or Cin in {2, 4}; Cout % 32 == 0;
+ * shared memory), else 0. */
 int dlsg_conv3d_k3_supported(int Cin, int Cout);
 
 /* out[n,t,y,x,:] = bias + sum over the 27 taps and Cin of x[n,t+dt,y+dy,x+dx,ci] * weight[co,ci,dt+1,dy+1,dx+1]  (cross-correlation,
  * zeros outside the volume), computed as three TF32 tensor-core products on operands split into a TF32 head and the remainder
  * (fp32-level accuracy).  x [NB,T,Y,X,Cin] and out [NB,T,Y,X,Cout] are channels-last (torch.channels_last_3d of [NB,C,T,Y,X]).
  * wprep is the weight split and laid out for the kernel, prepared once per weight version by the caller:
- *   wprep[tap][ci/32][h][(ci%32)/4][co/8][co%8][ci%4],  h = 0: TF32 head of weight[co,ci,tap], h = 1: remainder,  tap = (dt+1)*9+(dy+1)*3+(dx+1).
+ *   wprep[tap][ci/32][h][(ci%32)/4][co/8][co%8][ci%4],  h = 0: TF32 head of weight[co,ci,tap], h = 1: remainder,  tap = (dt+1)*9+(dy+1)*3+(dx+1);
+ *   for the first layer of a denoiser (Cin = 2 or 4) K runs over k = tap*Cin + ci, zero-padded to a multiple of 32:
+ *   wprep[k/32][h][(k%32)/4][co/8][co%8][k%4].
  * relu_in != 0 rectifies x on the fly (ConvBlock's pre-activation, :262-268).  bias may be NULL. */
 int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
                               int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream);
+
+/* PatchEmbed3D.proj (dl_cs/models/video_swin_transformer_mri_downsample.py:455-476): nn.Conv3d(kernel = stride = patch, no padding) on
+ * the same kernel.  x [NB,T,Y,X,Cin] (T, Y, X multiples of patch) -> out [NB,T/patch,Y/patch,X/patch,Cout]; wprep as above with
+ * patch^3 taps, tap = (dt*patch + dy)*patch + dx.  Cin % 32 == 0. */
+int dlsg_conv3d_patch_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
+                                 int NB, int T, int Y, int X, int Cin, int Cout, int patch, void* stream);
+
+/* PatchUnembed3D.proj (:503-520): nn.ConvTranspose3d(kernel = stride = patch): out[n, t*patch+dt, y*patch+dy, x*patch+dx, :] =
+ * bias + W_tap x[n,t,y,x,:].  x [NB,T,Y,X,Cin] -> out [NB,T*patch,Y*patch,X*patch,Cout]; wprep as above built from
+ * weight[ci,co,dt,dy,dx] transposed to [co,ci,...].  Cin % 32 == 0. */
+int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
+                                   int NB, int T, int Y, int X, int Cin, int Cout, int patch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,26 @@ def test_conv3d_k3_matches_fp64(case):
     assert rel(out_r, ref_r) < 3e-5
 
 
+@pytest.mark.parametrize("case", [(1, 32, 64, 2, 3, 5, 2), (2, 160, 160, 2, 6, 5, 4), (1, 64, 32, 3, 9, 7, 1)])
+def test_patch_embed_and_unembed_match_fp64(case):
+    from dl_swin_gan_b200.models.conv3d import conv3d_patch, conv3d_unpatch
+    nb, cin, cout, t, y, x, p = case                      # token grid t, y, x; patch p
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(p * 100 + cin)
+    vol = torch.randn(nb, cin, t * p, y * p, x * p, generator=g, device=dev)
+    w = torch.randn(cout, cin, p, p, p, generator=g, device=dev) / (p ** 3 * cin) ** 0.5
+    b = torch.randn(cout, generator=g, device=dev)
+    ref = torch.nn.functional.conv3d(vol.double(), w.double(), b.double(), stride=p)
+    out = conv3d_patch(vol, w, b)
+    # K = p^3 * Cin = 10 240 accumulations in the tensor core's fp32 accumulator at the Swin size: 5e-5 (measured); one TF32 pass is 5e-4
+    assert out.shape == ref.shape and rel(out, ref) < 1e-4, rel(out, ref)
+    tok = torch.randn(nb, cin, t, y, x, generator=g, device=dev)
+    wt = torch.randn(cin, cout, p, p, p, generator=g, device=dev) / cin ** 0.5
+    ref_t = torch.nn.functional.conv_transpose3d(tok.double(), wt.double(), b.double(), stride=p)
+    out_t = conv3d_unpatch(tok, wt, b)
+    assert out_t.shape == ref_t.shape and rel(out_t, ref_t) < 3e-5, rel(out_t, ref_t)
+
+
 def test_conv_forward_routes_to_the_kernel_and_matches_cudnn_path():
     from dl_swin_gan_b200 import _lib
     from dl_swin_gan_b200.models import layers
