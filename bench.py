@@ -301,6 +301,31 @@ def swin_block_timing(dev, tensor_peak, slices=8):
                                  "rate; per-kernel tensor-pipe counters (ncu) are under profiles/"}}
 
 
+def conv_kernel_timing(dev, tensor_peak_bf16):
+    """The denoiser's dominant layer (Conv3d 160 -> 160, 3x3x3, one cine slice incl. the circular time padding) on the repo's
+    tensor-core kernel against one cuDNN TF32 pass; useful = 2*27*Cin*Cout*voxels, the kernel issues three times that (3xTF32)."""
+    from dl_swin_gan_b200.models.conv3d import conv3d_k3
+    c, t, y, x = 160, 28, 192, 160
+    inp = torch.randn(1, c, t, y, x, device=dev).contiguous(memory_format=torch.channels_last_3d)
+    w = torch.randn(c, c, 3, 3, 3, device=dev) / (27 * c) ** 0.5
+    b = torch.randn(c, device=dev)
+    wc = w.contiguous(memory_format=torch.channels_last_3d)
+    flop = 2.0 * 27 * c * c * t * y * x
+    with torch.no_grad():
+        ms = time_op(lambda: conv3d_k3(inp, w, b), 5, dev)
+        keep = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = True
+        ms_c = time_op(lambda: torch.nn.functional.conv3d(inp, wc, b, padding=1), 5, dev)
+        torch.backends.cudnn.allow_tf32 = keep
+    peak = tensor_peak_bf16 / 2.0
+    return {"what": "Conv3d 160->160 3x3x3 'same', [1,160,28,192,160] channels-last, 3xTF32 in one tcgen05 kernel", "ms": ms,
+            "useful_tflops": flop / ms / 1e9, "issued_tflops": 3 * flop / ms / 1e9,
+            "cudnn_tf32_one_pass_ms": ms_c, "cudnn_three_passes_ms": 3 * ms_c,
+            "roofline": {"bound": "tensor", "achieved": 3 * flop / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": 3 * flop / ms / 1e9 / peak,
+                         "note": "issued TF32 tensor work over half the measured sustained bf16 rate (TF32 runs at half the bf16 rate; "
+                                 "MEASURED_PEAKS.json holds no TF32 figure)"}}
+
+
 def _lib_launches():
     from dl_swin_gan_b200 import _lib
     return int(_lib.load().dlsg_launch_count())
@@ -360,7 +385,7 @@ def pin_to_gpu_numa_node(local_rank: int):
 
 
 # --------------------------------------------------------------------------- whole reconstructions
-def full_recon_timing(workload, dev, rank, batch=None, iters=3, precisions=("tf32x3", "tf32", "bf16")):
+def full_recon_timing(workload, dev, rank, batch=None, iters=3, precisions=("tf32x3", "tf32x3_cudnn", "tf32", "bf16")):
     """slices/s of a whole unrolled reconstruction (DC steps + denoisers) with the time split, per convolution precision."""
     from dl_swin_gan_b200.config import load_cfg
     from dl_swin_gan_b200.models import build_unrolled, set_conv_precision, get_conv_precision
@@ -381,17 +406,22 @@ def full_recon_timing(workload, dev, rank, batch=None, iters=3, precisions=("tf3
         t_dc = time_op(lambda: A.dc_step(aty, aty, net.step_size), iters, dev)
         t_adj = time_op(lambda: A(y, adjoint=True), iters, dev)
         out["sense_ms"] = {"adjoint": t_adj, "dc_step": t_dc, "per_recon": t_adj + cfg["unrolls"] * t_dc}
+        from dl_swin_gan_b200.models import layers as _layers
         for prec in precisions:
-            set_conv_precision(prec)
+            _layers._TC_CONV = not prec.endswith("_cudnn")           # "tf32x3_cudnn": the same arithmetic as three cuDNN calls per layer
+            set_conv_precision(prec.replace("_cudnn", ""))
             t_all = time_op(lambda: net(y, A), iters, dev)
             t_den = time_op(lambda: net.cnn_update[0](aty), iters, dev)
             out[prec] = {"ms_per_batch": t_all, "slices_per_s": cfg["B"] / (t_all * 1e-3), "denoiser_ms": t_den,
                          "denoiser_share": cfg["unrolls"] * t_den / t_all}
+        _layers._TC_CONV = True
     set_conv_precision(keep)
-    out["note"] = ("conv precision tf32x3 = three TF32 tensor-core convolutions on split operands (default; fp32-accurate: the whole "
-                   "reconstruction stays within 1e-3 NRMSE of the fp32 reference, tests/test_models.py); tf32 = cuDNN default (what the "
-                   "reference itself runs on a GPU; 1.2e-3 NRMSE after 5 Swin unrolls); fp32 = cuDNN without tensor cores; the denoiser "
-                   "convolutions are cuDNN library calls (SURVEY.md 8f-1)")
+    out["note"] = ("conv precision tf32x3 (default) = 3xTF32: operands split into a TF32 head and the remainder, three tensor-core products, "
+                   "fp32-level accuracy (the whole reconstruction stays within 1e-3 NRMSE of the fp32 reference, tests/test_models.py) - run by "
+                   "the repo's own tcgen05 implicit-GEMM kernels (csrc/conv3d_tc.cuh: 3x3x3, first layer, patch embed / unembed; last layer on "
+                   "the CUDA cores, csrc/conv3d_fewout.cuh); tf32x3_cudnn = the same arithmetic as three cuDNN convolutions per layer around "
+                   "elementwise passes; tf32 = cuDNN default (what the reference itself runs on a GPU; 1.2e-3 NRMSE after 5 Swin unrolls); "
+                   "bf16 = cuDNN under autocast (1e-2)")
     return out
 
 
@@ -468,7 +498,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: B slices per GPU; strong: the B slices of the workload split over the ranks (slice_range)")
     ap.add_argument("--batch", type=int, default=0, help="slices per GPU (default: the workload's)")
-    ap.add_argument("--conv-precision", default="tf32x3", choices=["tf32x3", "fp32", "tf32", "bf16"], help="denoiser convolutions (full-recon workloads)")
+    ap.add_argument("--conv-precision", default="tf32x3", choices=["tf32x3", "tf32x3_cudnn", "fp32", "tf32", "bf16"], help="denoiser convolutions (full-recon workloads)")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-swin", action="store_true", help="skip the window-attention side measurement")
@@ -531,7 +561,9 @@ def main():
     else:
         from dl_swin_gan_b200.config import load_cfg
         from dl_swin_gan_b200.models import build_unrolled, set_conv_precision
-        set_conv_precision(args.conv_precision)
+        from dl_swin_gan_b200.models import layers as _layers
+        _layers._TC_CONV = not args.conv_precision.endswith("_cudnn")
+        set_conv_precision(args.conv_precision.replace("_cudnn", ""))
         torch.manual_seed(1000)
         net = build_unrolled(load_cfg(preset)).to(dev).eval()
 
@@ -766,8 +798,11 @@ def main():
                 "swin_recon": full_recon_timing("swin_recon", dev, rank, batch=2, iters=2)}
 
     swin = None
+    conv = None
     if rank == 0 and not args.skip_swin:
         swin = swin_block_timing(dev, tensor_peak)
+        if world == 1:
+            conv = conv_kernel_timing(dev, tensor_peak)
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -790,7 +825,7 @@ def main():
                     "conv_precision": (args.conv_precision if preset is not None else None),
                     "warmup_extra_steps": extra_warmup, "numa": numa},
             "roofline": roofline, "ops": ops, "ops_dense_kernels": ops_dense, "torch_eager_gpu": eager, "full_recon": full,
-            "attention": (swin or {}).get("roofline"), "swin_window_attention": swin, "cpu_baseline": cpu, "e2e": e2e,
+            "attention": (swin or {}).get("roofline"), "swin_window_attention": swin, "denoiser_conv": conv, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

@@ -1,0 +1,122 @@
+// Last layer of the denoisers: nn.Conv3d(Cin -> 2 or 4, kernel 3, 'same') of `final_layer` (dl_cs/models/swin3D.py:395,
+// resnet3d.py:270): the output is the re / im channels of the E map sets.  With 2 - 4 output channels there is no GEMM to
+// speak of (N = 4): plain FP32 FMAs on the CUDA cores (packed FFMA2, exact fp32 - no operand splitting needed), one pass over
+// the input.  Thread layout as the tensor-core kernel's producers: 8 lanes cover the 128 bytes of one voxel's 32-channel chunk
+// (coalesced), each thread keeps the partial sums of its channel quad for 8 voxels and all outputs; the 8 lanes of a voxel are
+// reduced with shuffles at the end.  The weights sit in shared memory as [tap][ci][co].
+#pragma once
+
+#include "cuda_compat.h"
+#include "fft_packed.cuh"
+
+#if defined(__CUDACC__)
+namespace dlsg {
+
+struct FewOutParams {
+    const float* x;        // [NB, T, Y, X, Cin]
+    const float* w;        // [27][Cin][CO]
+    const float* bias;     // [CO] or NULL
+    float* out;            // [NB, T, Y, X, CO]
+    int NB, T, Y, X, Cin;
+    long long NV;
+    int relu_in;
+};
+
+constexpr int kFewThreads = 256;
+
+template <int CO>
+__global__ void __launch_bounds__(kFewThreads, 2) conv3d_k3_fewout_kernel(FewOutParams p) {
+    extern __shared__ __align__(16) unsigned char few_smem[];
+    float* sw = reinterpret_cast<float*>(few_smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nw = 27 * p.Cin * CO;
+    for (int i = tid; i < nw / 4; i += kFewThreads) reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
+    __syncthreads();
+    const int KCH = p.Cin / 32;
+    const int k4 = lane & 7, rsub = lane >> 3;
+    const long long YX = (long long)p.Y * p.X;
+    const long long ntiles = (p.NV + kFewThreads - 1) / kFewThreads;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long v0 = tile * kFewThreads + warp * 32 + rsub;          // this thread's voxels: v0 + 4 i
+        int coord[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long vi = v0 + 4 * i;
+            if (vi < p.NV) {
+                const long long r1 = vi % YX;
+                coord[i] = (int)((vi / YX) % p.T) << 20 | (int)(r1 / p.X) << 10 | (int)(r1 % p.X);
+            } else coord[i] = -1;
+        }
+        float2 acc[8][CO / 2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < CO / 2; ++c) acc[i][c] = make_float2(0.f, 0.f);
+        for (int tap = 0; tap < 27; ++tap) {
+            const int dt = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
+            unsigned okmask = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = coord[i];
+                const bool ok = c >= 0 && (unsigned)((c >> 20) + dt) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + dy) < (unsigned)p.Y &&
+                                (unsigned)((c & 1023) + dx) < (unsigned)p.X;
+                okmask |= (ok ? 1u : 0u) << i;
+            }
+            const float* src = p.x + (size_t)(v0 + (long long)dt * YX + (long long)dy * p.X + dx) * p.Cin + 4 * k4;
+            const float* wt = sw + ((size_t)tap * p.Cin + 4 * k4) * CO;
+            for (int ch = 0; ch < KCH; ++ch) {
+                float4 a[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    a[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(4 * i) * p.Cin + ch * 32))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.relu_in) { a[i].x = fmaxf(a[i].x, 0.f); a[i].y = fmaxf(a[i].y, 0.f); a[i].z = fmaxf(a[i].z, 0.f); a[i].w = fmaxf(a[i].w, 0.f); }
+                }
+                float2 wq[4][CO / 2];                                        // weights of this thread's 4 input channels
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < CO / 2; ++c) wq[j][c] = *reinterpret_cast<const float2*>(wt + (size_t)(ch * 32 + j) * CO + 2 * c);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int c = 0; c < CO / 2; ++c) {
+                        acc[i][c] = p_fma(p_bc(a[i].x), wq[0][c], acc[i][c]);
+                        acc[i][c] = p_fma(p_bc(a[i].y), wq[1][c], acc[i][c]);
+                        acc[i][c] = p_fma(p_bc(a[i].z), wq[2][c], acc[i][c]);
+                        acc[i][c] = p_fma(p_bc(a[i].w), wq[3][c], acc[i][c]);
+                    }
+            }
+        }
+        // sum over the 8 channel-quad lanes of each voxel; lane k4 == 0 stores
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < CO / 2; ++c) {
+                float2 s = acc[i][c];
+#pragma unroll
+                for (int m = 1; m < 8; m <<= 1) {
+                    s.x += __shfl_xor_sync(0xffffffffu, s.x, m);
+                    s.y += __shfl_xor_sync(0xffffffffu, s.y, m);
+                }
+                acc[i][c] = s;
+            }
+        if (k4 == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long vi = v0 + 4 * i;
+                if (vi < p.NV) {
+#pragma unroll
+                    for (int c = 0; c < CO / 2; ++c) {
+                        float2 r = acc[i][c];
+                        if (p.bias) { r.x += __ldg(p.bias + 2 * c); r.y += __ldg(p.bias + 2 * c + 1); }
+                        *reinterpret_cast<float2*>(p.out + (size_t)vi * CO + 2 * c) = r;
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace dlsg
+#endif

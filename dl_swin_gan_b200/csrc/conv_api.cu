@@ -2,6 +2,7 @@
 #include "../../include/dlsg_b200.h"
 #include <cstdlib>
 #include "conv3d_tc.cuh"
+#include "conv3d_fewout.cuh"
 
 extern "C" {
 
@@ -85,6 +86,34 @@ int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const float* wprep, const flo
     return conv_launch(p, stream);
 #else
     (void)x; (void)wprep; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)patch; (void)stream;
+    return DLSG_EUNSUPPORTED;
+#endif
+}
+
+int dlsg_conv3d_k3_fewout_f32(const float* x, const float* w_tcc, const float* bias, float* out,
+                              int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream) {
+#if defined(__CUDACC__)
+    using namespace dlsg;
+    if (!x || !w_tcc || !out || NB <= 0 || T <= 0 || Y <= 0 || X <= 0) return DLSG_EINVAL;
+    if ((Cout != 2 && Cout != 4) || Cin <= 0 || Cin % 32 != 0 || X > 1023 || Y > 1023 || T > 2047) return DLSG_EUNSUPPORTED;
+    const size_t smem = (size_t)27 * Cin * Cout * 4;
+    if (smem > 100 * 1024) return DLSG_EUNSUPPORTED;                  // two CTAs per SM
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_tcc) | reinterpret_cast<uintptr_t>(out)) & 15) return DLSG_EINVAL;
+    FewOutParams p{};
+    p.x = x; p.w = w_tcc; p.bias = bias; p.out = out;
+    p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin;
+    p.NV = (long long)NB * T * Y * X;
+    p.relu_in = relu_in ? 1 : 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long ntiles = (p.NV + kFewThreads - 1) / kFewThreads;
+    const unsigned grid = (unsigned)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
+    const int rc = Cout == 2 ? launch(conv3d_k3_fewout_kernel<2>, dim3(grid), dim3(kFewThreads), smem, (stream_t)stream, p)
+                             : launch(conv3d_k3_fewout_kernel<4>, dim3(grid), dim3(kFewThreads), smem, (stream_t)stream, p);
+    return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
+#else
+    (void)x; (void)w_tcc; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)relu_in; (void)stream;
     return DLSG_EUNSUPPORTED;
 #endif
 }

@@ -12,7 +12,7 @@ import torch
 
 from .. import _lib
 
-K3, PATCH, UNPATCH = "k3", "patch", "unpatch"
+K3, PATCH, UNPATCH, FEWOUT = "k3", "patch", "unpatch", "fewout"
 
 
 def _split(t: torch.Tensor):
@@ -83,6 +83,9 @@ def kind(conv: torch.nn.Module, x: torch.Tensor):
         return None
     if k == (3, 3, 3) and s == (1, 1, 1) and pd == (1, 1, 1) and lib.dlsg_conv3d_k3_supported(conv.in_channels, conv.out_channels):
         return K3
+    if k == (3, 3, 3) and s == (1, 1, 1) and pd == (1, 1, 1) and conv.out_channels in (2, 4) and conv.in_channels % 32 == 0 \
+            and 27 * conv.in_channels * conv.out_channels * 4 <= 100 * 1024:
+        return FEWOUT
     if cubic and k == s and pd == (0, 0, 0) and 1 < k[0] <= 8 and conv.in_channels % 32 == 0 \
             and all(d % k[0] == 0 for d in x.shape[2:]) and lib.dlsg_conv3d_k3_supported(conv.in_channels, conv.out_channels):
         return PATCH
@@ -126,7 +129,38 @@ def conv3d_unpatch(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Te
     return _run("dlsg_conv3d_unpatch_tf32x3_f32", x, weight, bias, [d * p for d in x.shape[2:]], p, True)
 
 
+def conv3d_k3_fewout(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: bool = False) -> torch.Tensor:
+    """The last layer (Cout = 2 or 4) in exact fp32: x [NB, Cin, T, Y, X] -> [NB, Cout, T, Y, X] (channels_last_3d)."""
+    lib = _lib.load()
+    nb, cin, t, y, xx = x.shape
+    cout = weight.shape[0]
+    xc = x.permute(0, 2, 3, 4, 1)
+    if not xc.is_contiguous():
+        xc = xc.contiguous()
+    try:
+        tag = (weight._version, weight.data_ptr())
+    except RuntimeError:
+        tag = None
+    hit = getattr(weight, "_dlsg_conv_tcc", None)
+    if hit is not None and tag is not None and hit[0] == tag:
+        wt = hit[1]
+    else:
+        wt = weight.detach().float().reshape(cout, cin, 27).permute(2, 1, 0).contiguous()
+        try:
+            weight._dlsg_conv_tcc = (tag, wt)
+        except AttributeError:
+            pass
+    out = torch.empty((nb, t, y, xx, cout), device=x.device, dtype=torch.float32)
+    b = bias.detach().float().contiguous() if bias is not None else None
+    st = lib.dlsg_conv3d_k3_fewout_f32(xc.data_ptr(), wt.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
+                                       nb, t, y, xx, cin, cout, int(relu_in), torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(st, "dlsg_conv3d_k3_fewout_f32")
+    return out.permute(0, 4, 1, 2, 3)
+
+
 def forward(conv: torch.nn.Module, x: torch.Tensor, which: str) -> torch.Tensor:
+    if which == FEWOUT:
+        return conv3d_k3_fewout(x, conv.weight, conv.bias)
     if which == K3:
         return conv3d_k3(x, conv.weight, conv.bias)
     if which == PATCH:

@@ -297,6 +297,11 @@ int dlsg_conv3d_patch_tf32x3_f32(const float* x, const float* wprep, const float
 int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
                                    int NB, int T, int Y, int X, int Cin, int Cout, int patch, void* stream);
 
+/* The denoisers' last layer (final_layer, dl_cs/models/swin3D.py:395): 3 x 3 x 3 'same' convolution down to Cout = 2 or 4 channels in
+ * exact fp32 on the CUDA cores (packed FMAs).  x, out channels-last as above; w_tcc[tap][ci][co] = weight[co,ci,tap].  Cin % 32 == 0. */
+int dlsg_conv3d_k3_fewout_f32(const float* x, const float* w_tcc, const float* bias, float* out,
+                              int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,21 @@ def test_patch_embed_and_unembed_match_fp64(case):
     assert out_t.shape == ref_t.shape and rel(out_t, ref_t) < 3e-5, rel(out_t, ref_t)
 
 
+@pytest.mark.parametrize("case", [(1, 160, 4, 3, 9, 20), (2, 64, 2, 4, 7, 13), (1, 32, 4, 1, 1, 3)])
+def test_last_layer_kernel_matches_fp64(case):
+    from dl_swin_gan_b200.models.conv3d import conv3d_k3_fewout
+    nb, cin, cout, t, y, x = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(cin + cout)
+    inp = torch.randn(nb, cin, t, y, x, generator=g, device=dev)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g, device=dev) / (27 * cin) ** 0.5
+    b = torch.randn(cout, generator=g, device=dev)
+    ref = torch.nn.functional.conv3d(inp.double(), w.double(), b.double(), padding=1)
+    assert rel(conv3d_k3_fewout(inp, w, b), ref) < 2e-6                      # plain fp32 FMAs
+    ref_r = torch.nn.functional.conv3d(inp.double().relu(), w.double(), None, padding=1)
+    assert rel(conv3d_k3_fewout(inp, w, None, relu_in=True), ref_r) < 2e-6
+
+
 def test_conv_forward_routes_to_the_kernel_and_matches_cudnn_path():
     from dl_swin_gan_b200 import _lib
     from dl_swin_gan_b200.models import layers
