@@ -45,6 +45,8 @@ struct ConvParams {
     int mode;
     long long NV;          // GEMM rows: output voxels (CONV_GATHER) or input voxels (CONV_UNPATCH)
     int relu_in;           // rectify the input on the fly (ConvBlock's pre-activation)
+    const float* resid;    // optional [NB, To, Yo, Xo, Cout]: out = conv + bias + resid_scale * resid (the blocks' skip connections)
+    float resid_scale;
 };
 
 __host__ __device__ inline size_t conv_stage_bytes(int Cout) { return (size_t)4 * kConvABytes + (size_t)2 * Cout * kConvKC * 4; }
@@ -242,9 +244,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                 vout = (((nt / p.T) * p.To + (nt % p.T) * ksz + ta) * p.Yo + (r1 / p.X) * ksz + tb) * p.Xo + (r1 % p.X) * ksz + tc;
             }
             float* orow = p.out + (size_t)vout * Cout;
+            const float* rrow = p.resid ? p.resid + (size_t)vout * Cout : nullptr;
             for (int c0 = 0; c0 < Cout; c0 += 32) {
                 float acc[32];
                 tmem_ld32(taddr + (unsigned)c0, acc);
+                if (live && rrow) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + c0 + 4 * q));
+                        acc[4 * q] = fmaf(p.resid_scale, r4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(p.resid_scale, r4.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(p.resid_scale, r4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(p.resid_scale, r4.w, acc[4 * q + 3]);
+                    }
+                }
                 if (live) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)

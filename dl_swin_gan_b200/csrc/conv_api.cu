@@ -41,7 +41,7 @@ static int conv_launch(dlsg::ConvParams& p, void* stream) {
 }
 #endif
 
-int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
+int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* bias, const float* resid, float resid_scale, float* out,
                               int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream) {
 #if defined(__CUDACC__)
     dlsg::ConvParams p{};
@@ -50,9 +50,11 @@ int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* b
     p.To = T; p.Yo = Y; p.Xo = X; p.ksz = 3; p.stride = 1; p.pad = 1; p.mode = dlsg::CONV_GATHER;
     p.NV = (long long)NB * T * Y * X;
     p.relu_in = relu_in ? 1 : 0;
+    if (resid && (reinterpret_cast<uintptr_t>(resid) & 15)) return DLSG_EINVAL;
+    p.resid = resid; p.resid_scale = resid_scale;
     return conv_launch(p, stream);
 #else
-    (void)x; (void)wprep; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)relu_in; (void)stream;
+    (void)x; (void)wprep; (void)bias; (void)resid; (void)resid_scale; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)relu_in; (void)stream;
     return DLSG_EUNSUPPORTED;      // tcgen05 / TMEM have no host emulation
 #endif
 }

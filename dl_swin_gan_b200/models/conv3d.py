@@ -96,7 +96,7 @@ def supported(conv: torch.nn.Module, x: torch.Tensor) -> bool:
     return kind(conv, x) is not None
 
 
-def _run(fn_name, x, weight, bias, out_dims, last, transposed):
+def _run(fn_name, x, weight, bias, out_dims, last, transposed, residual=None, residual_scale=1.0):
     lib = _lib.load()
     nb, cin, t, y, xx = x.shape
     cout = weight.shape[1] if transposed else weight.shape[0]
@@ -106,15 +106,25 @@ def _run(fn_name, x, weight, bias, out_dims, last, transposed):
     prep = _cached_weight(weight, transposed)
     out = torch.empty((nb,) + tuple(out_dims) + (cout,), device=x.device, dtype=torch.float32)
     b = bias.detach().float().contiguous() if bias is not None else None
-    st = getattr(lib, fn_name)(xc.data_ptr(), prep.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
-                               nb, t, y, xx, cin, cout, int(last), torch.cuda.current_stream(x.device).cuda_stream)
+    args = [xc.data_ptr(), prep.data_ptr(), b.data_ptr() if b is not None else None]
+    if fn_name == "dlsg_conv3d_k3_tf32x3_f32":
+        rc = None
+        if residual is not None:
+            if tuple(residual.shape) != (nb, cout) + tuple(out_dims):
+                raise ValueError(f"residual {tuple(residual.shape)} does not match the output {(nb, cout) + tuple(out_dims)}")
+            rc = residual.permute(0, 2, 3, 4, 1)
+            if not rc.is_contiguous():
+                rc = rc.contiguous()
+        args += [rc.data_ptr() if rc is not None else None, float(residual_scale)]
+    st = getattr(lib, fn_name)(*args, out.data_ptr(), nb, t, y, xx, cin, cout, int(last), torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(st, fn_name)
     return out.permute(0, 4, 1, 2, 3)
 
 
-def conv3d_k3(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: bool = False) -> torch.Tensor:
-    """x [NB, Cin, T, Y, X] (any layout; used channels-last) -> [NB, Cout, T, Y, X] in channels_last_3d."""
-    return _run("dlsg_conv3d_k3_tf32x3_f32", x, weight, bias, x.shape[2:], relu_in, False)
+def conv3d_k3(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: bool = False, residual=None, residual_scale: float = 1.0) -> torch.Tensor:
+    """x [NB, Cin, T, Y, X] (any layout; used channels-last) -> conv(relu?(x)) + bias (+ residual_scale * residual),
+    [NB, Cout, T, Y, X] in channels_last_3d."""
+    return _run("dlsg_conv3d_k3_tf32x3_f32", x, weight, bias, x.shape[2:], relu_in, False, residual, residual_scale)
 
 
 def conv3d_patch(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
@@ -158,11 +168,16 @@ def conv3d_k3_fewout(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: 
     return out.permute(0, 4, 1, 2, 3)
 
 
-def forward(conv: torch.nn.Module, x: torch.Tensor, which: str) -> torch.Tensor:
-    if which == FEWOUT:
-        return conv3d_k3_fewout(x, conv.weight, conv.bias)
+def forward(conv: torch.nn.Module, x: torch.Tensor, which: str, relu_in: bool = False, residual=None, residual_scale: float = 1.0) -> torch.Tensor:
+    """`conv(relu?(x)) (+ residual_scale * residual)` on the kernel `kind()` chose; what a kernel cannot fuse is done around it."""
     if which == K3:
-        return conv3d_k3(x, conv.weight, conv.bias)
-    if which == PATCH:
-        return conv3d_patch(x, conv.weight, conv.bias)
-    return conv3d_unpatch(x, conv.weight, conv.bias)
+        return conv3d_k3(x, conv.weight, conv.bias, relu_in, residual, residual_scale)
+    if which == FEWOUT:
+        out = conv3d_k3_fewout(x, conv.weight, conv.bias, relu_in)
+    else:
+        if relu_in:
+            x = torch.relu(x)
+        out = conv3d_patch(x, conv.weight, conv.bias) if which == PATCH else conv3d_unpatch(x, conv.weight, conv.bias)
+    if residual is not None:
+        out = out + residual_scale * residual if residual_scale != 1.0 else out + residual
+    return out

@@ -161,8 +161,26 @@ class ConvBlock(nn.Module):
         conv = (ComplexConv3d if is_complex else Conv3d)(in_chans, out_chans, kernel_size=kernel_size)
         self.layers = nn.Sequential(Normalization(in_chans, norm_type), Activation(act_type), conv)
 
-    def forward(self, input):
-        return self.layers(input)
+    def forward(self, input, residual=None, residual_scale=1.0, input_is_temp=False):
+        """`conv(act(input))` (+ residual_scale * residual).  The extra arguments only let the B200 kernels fuse what surrounds the
+        convolution; the arithmetic is the reference's.  `input_is_temp`: nobody reads `input` after this call, so the in-place
+        ReLU of the reference (which would rectify `input` itself) may be applied inside the kernel's operand load instead."""
+        act, conv_mod = self.layers[1], self.layers[2]
+        fused = None
+        if (_TC_CONV and _CONV_PRECISION == "tf32x3" and input.is_cuda and isinstance(conv_mod, Conv3d)
+                and isinstance(self.layers[0].norm, nn.Identity) and isinstance(act.activ, (nn.Identity, nn.ReLU))):
+            from . import conv3d
+            fused = conv3d.kind(conv_mod.conv, input)
+        if fused is None:
+            out = self.layers(input)
+            if residual is not None:
+                out = out + (residual if residual_scale == 1.0 else residual_scale * residual)
+            return out
+        relu = isinstance(act.activ, nn.ReLU)
+        if relu and not input_is_temp:
+            input = act(input)                      # in place, visible to the caller, exactly as in the reference
+            relu = False
+        return conv3d.forward(conv_mod.conv, input, fused, relu_in=relu, residual=residual, residual_scale=residual_scale)
 
     def __repr__(self):
         return f"{self.name}(in_chans={self.in_chans}, out_chans={self.out_chans})"
@@ -177,7 +195,9 @@ class ResBlock(nn.Module):
                                     ConvBlock(chans, chans, kernel_size, act_type=act_type, is_complex=is_complex))
 
     def forward(self, input):
-        return self.layers(input) + input
+        # the first block rectifies `input` in place (reference quirk, see Activation), so the skip below adds relu(input)
+        h = self.layers[0](input)
+        return self.layers[1](h, residual=input, input_is_temp=True)
 
 
 def time_pad_circular(x: torch.Tensor, pad: int) -> torch.Tensor:

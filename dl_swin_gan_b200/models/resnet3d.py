@@ -40,5 +40,5 @@ class ResNet(nn.Module):
         output = self.init_layer(input)
         for res_block in self.res_blocks:
             output = res_block(output)
-        output = self.final_layer(output) + input
+        output = self.final_layer(output, residual=input, input_is_temp=len(self.res_blocks) > 0)
         return self._postprocess(output)

@@ -36,7 +36,7 @@ class ResSwinTransformer3DBlock(nn.Module):
             ConvBlock(chans, chans, kernel_size=3, act_type=act_type, is_complex=is_complex))
 
     def forward(self, input):
-        return self.layers(input) + input
+        return self.layers[1](self.layers[0](input), residual=input, input_is_temp=True)
 
 
 class DeepFeatureExtraction(nn.Module):
@@ -48,8 +48,12 @@ class DeepFeatureExtraction(nn.Module):
         self.layers = nn.Sequential(*self.resswin_blocks,
                                     ConvBlock(chans, chans, kernel_size=3, act_type=act_type, is_complex=is_complex))
 
-    def forward(self, input):
-        return self.layers(input) + input
+    def forward(self, input, skip_scale=1.0):
+        """`layers(input) + skip_scale * input`; the caller's own `x + DFE(x)` (swin3D.py:430) rides in as skip_scale = 2."""
+        x = input
+        for block in self.resswin_blocks:
+            x = block(x)
+        return self.layers[-1](x, residual=input, residual_scale=skip_scale, input_is_temp=x is not input)
 
 
 class SwinTransformer3DNet(nn.Module):
@@ -85,6 +89,6 @@ class SwinTransformer3DNet(nn.Module):
     def forward(self, x):
         x = self._preprocess(x)
         x = self.SFE(x)
-        x = x + self.DFE(x)
-        x = self.final_layer(x)
+        x = self.DFE(x, skip_scale=2.0)              # x + DFE(x) = layers(x) + 2 x
+        x = self.final_layer(x, input_is_temp=True)
         return self._postprocess(x)

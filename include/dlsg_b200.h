@@ -281,8 +281,10 @@ int dlsg_conv3d_k3_supported(int Cin, int Cout);
  *   wprep[tap][ci/32][h][(ci%32)/4][co/8][co%8][ci%4],  h = 0: TF32 head of weight[co,ci,tap], h = 1: remainder,  tap = (dt+1)*9+(dy+1)*3+(dx+1);
  *   for the first layer of a denoiser (Cin = 2 or 4) K runs over k = tap*Cin + ci, zero-padded to a multiple of 32:
  *   wprep[k/32][h][(k%32)/4][co/8][co%8][k%4].
- * relu_in != 0 rectifies x on the fly (ConvBlock's pre-activation, :262-268).  bias may be NULL. */
-int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
+ * relu_in != 0 rectifies x on the fly (ConvBlock's pre-activation, :262-268).  resid (NULL or [NB,T,Y,X,Cout]) is a skip connection added
+ * in the epilogue: out = conv + bias + resid_scale * resid (ResBlock :300, ResSwinTransformer3DBlock :340, DeepFeatureExtraction :369).
+ * bias may be NULL. */
+int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* bias, const float* resid, float resid_scale, float* out,
                               int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream);
 
 /* PatchEmbed3D.proj (dl_cs/models/video_swin_transformer_mri_downsample.py:455-476): nn.Conv3d(kernel = stride = patch, no padding) on

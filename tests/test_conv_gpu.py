@@ -34,8 +34,10 @@ def test_conv3d_k3_matches_fp64(case):
     assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last_3d)
     # 3xTF32 with the tensor core's fp32 accumulator: 2e-6 at K = 27*32, 1.5e-5 at K = 27*160 (measured); TF32 alone is 5e-4
     assert rel(out, ref) < 3e-5, rel(out, ref)
-    out_r = conv3d_k3(inp, w, b, relu_in=True)
-    ref_r = torch.nn.functional.conv3d(inp.double().relu(), w.double(), b.double() if has_bias else None, padding=1)
+    # fused pre-activation and skip connection: conv(relu(x)) + b + 2 r
+    res = torch.randn(nb, cout, t, y, x, generator=g, device=dev)
+    out_r = conv3d_k3(inp, w, b, relu_in=True, residual=res, residual_scale=2.0)
+    ref_r = torch.nn.functional.conv3d(inp.double().relu(), w.double(), b.double() if has_bias else None, padding=1) + 2.0 * res.double()
     assert rel(out_r, ref_r) < 3e-5
 
 
