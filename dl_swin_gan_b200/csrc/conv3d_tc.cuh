@@ -309,3 +309,197 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
 
 }  // namespace dlsg
 #endif
+
+// =====================================================================================================================
+// Cout = 64 (the ResNet denoiser's 64 -> 64 layers, dl_cs/models/resnet3d.py:243-317; configs/config_recon.yaml): with 64 output
+// channels the kernel above spends its time re-reading the 4 KB activation block for every N = 64 instruction (tensor pipe
+// 35 % active).  Here the operands swap roles: the MMA's A operand is the weight block [W_hi; W_lo] (2 x 64 = 128 rows) and the
+// 256 voxels of the tile are its N dimension,
+//     D[128 x 256] += [W_hi; W_lo](128 x 8) * X_hi^T(8 x 256)  and  ... * X_lo^T,
+// two N = 256 instructions per k-step: rows 0-63 collect W_hi X_hi + W_hi X_lo, rows 64-127 W_lo X_hi + W_lo X_lo, and
+// out[v, co] = D[co, v] + D[64 + co, v] + bias.  The epilogue reads the accumulator one output channel per thread and 32 voxels
+// per load, the lo half goes through shared memory to the warp that holds the hi half, and each store writes one voxel's 32
+// channels (128 bytes, coalesced).
+#if defined(__CUDACC__)
+namespace dlsg {
+
+constexpr int kC64Producers = 512;                      // 16 producer warps (4 per scheduler): the producers are latency-, not throughput-bound
+constexpr int kC64Threads = kC64Producers + 32;
+constexpr int kC64LboB = 32 * 128 + 16;                 // bytes between the 4-channel planes of the 256-row activation block (+16: bank spread)
+constexpr int kC64BBytes = (kConvKC / 4) * kC64LboB;    // one of X_hi / X_lo for a stage
+constexpr int kC64WBytes = 128 * kConvKC * 4;           // [W_hi; W_lo] for a stage
+constexpr int kC64Stage = 2 * kC64BBytes + kC64WBytes;
+inline size_t conv_c64_smem_bytes() { return (size_t)kConvStages * kC64Stage + 64 * 4 + 128; }
+
+__global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParams p) {
+    extern __shared__ __align__(1024) unsigned char conv_smem[];
+    constexpr int Cout = 64;
+    const int KCH = p.Cin / kConvKC, NIT = 27 * KCH;
+    float* sBias = reinterpret_cast<float*>(conv_smem + kConvStages * kC64Stage);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sBias + Cout);   // full[2], empty[2], accfull, accempty
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 6);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned s0 = smem_u32(conv_smem), bar0 = smem_u32(bars);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kConvStages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 8u * s), "r"(kC64Producers + 1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 8u * (2 + s)), "r"(1) : "memory");
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 32u), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 40u), "r"(kC64Producers) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = tid; i < Cout; i += kC64Threads) sBias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+    const long long ntiles = (p.NV + kConvTileRows - 1) / kConvTileRows;
+    const long long YX = (long long)p.Y * p.X;
+
+    if (warp < kC64Producers / 32) {
+        const int k4 = lane & 7, rsub = lane >> 3;
+        const int wrow0 = warp * 16;                            // first of this warp's 16 rows of the 256-row tile
+        unsigned g = 0, tcount = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const long long v0 = tile * kConvTileRows + wrow0 + rsub;
+            int coord[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long vi = v0 + 4 * i;
+                if (vi < p.NV) {
+                    const long long r1 = vi % YX;
+                    coord[i] = (int)((vi / YX) % p.T) << 20 | (int)(r1 / p.X) << 10 | (int)(r1 % p.X);
+                } else coord[i] = -1;
+            }
+            // the loads of iteration it + 1 are in flight while iteration it is split and stored (their latency exceeds a stage)
+            unsigned okmask = 0;
+            const float* src = p.x;
+            auto tap_setup = [&](int tap) {
+                const int dt = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
+                okmask = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = coord[i];
+                    const bool ok = c >= 0 && (unsigned)((c >> 20) + dt) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + dy) < (unsigned)p.Y &&
+                                    (unsigned)((c & 1023) + dx) < (unsigned)p.X;
+                    okmask |= (ok ? 1u : 0u) << i;
+                }
+                src = p.x + (size_t)(v0 + (long long)dt * YX + (long long)dy * p.X + dx) * p.Cin + 4 * k4;
+            };
+            float4 a[4], an[4];
+            auto load = [&](float4* dst, int ch) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    dst[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(4 * i) * p.Cin + ch * kConvKC))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            tap_setup(0);
+            load(a, 0);
+            int ntap = 0, nch = 0;
+            for (int it = 0; it < NIT; ++it, ++g) {
+                {
+                    const int tap = ntap, ch = nch;
+                    if (it + 1 < NIT) {
+                        if (++nch == KCH) { nch = 0; tap_setup(++ntap); }
+                        load(an, nch);
+                    }
+                    const unsigned s = g & 1u, use = g >> 1;
+                    conv_mbar_wait(bar0 + 8u * (2 + s), (use & 1u) ^ 1u);
+                    unsigned char* st = conv_smem + (size_t)s * kC64Stage;
+                    if (tid == 0) {
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar0 + 8u * s), "r"((unsigned)kC64WBytes) : "memory");
+                        conv_bulk_load(s0 + (unsigned)(s * kC64Stage) + 2u * kC64BBytes,
+                                       p.wprep + ((size_t)tap * KCH + ch) * (kC64WBytes / 4), (unsigned)kC64WBytes, bar0 + 8u * s);
+                    }
+                    unsigned char* bhi = st + (size_t)k4 * kC64LboB;
+                    unsigned char* blo = bhi + kC64BBytes;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = wrow0 + 4 * i + rsub;
+                        const unsigned off = (unsigned)(row >> 3) * 128u + (unsigned)(row & 7) * 16u;
+                        float4 x4 = a[i], h4, l4;
+                        if (p.relu_in) { x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f); }
+                        tf32_split(x4.x, h4.x, l4.x); tf32_split(x4.y, h4.y, l4.y);
+                        tf32_split(x4.z, h4.z, l4.z); tf32_split(x4.w, h4.w, l4.w);
+                        *reinterpret_cast<float4*>(bhi + off) = h4;
+                        *reinterpret_cast<float4*>(blo + off) = l4;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar0 + 8u * s) : "memory");
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = an[i];
+            }
+            // ---- epilogue.  TMEM lane = (half, co): warp quarter q = warp & 3 holds co = 32 (q & 1) + lane of half q >> 1 (0: W_hi rows, 1: W_lo rows);
+            // warps 4 g .. 4 g + 3 take voxel columns 64 g .. 64 g + 63.  The stage buffers are idle now and carry the lo halves.
+            conv_mbar_wait(bar0 + 32u, tcount & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const int q = warp & 3, half = q >> 1, cbase = 32 * (q & 1), colw = (warp >> 2) * 64;
+            const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16);
+            float* xb = reinterpret_cast<float*>(conv_smem) + (size_t)((warp >> 2) * 2 + (q & 1)) * (32 * 33);   // one exchange block per (column half, co half)
+            const float bco = sBias[cbase + lane];
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                float acc[32];
+                tmem_ld32(taddr + (unsigned)(colw + c0), acc);
+                if (half == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) xb[j * 33 + lane] = acc[j];
+                }
+                asm volatile("bar.sync 1, 512;\n" ::: "memory");
+                if (half == 0) {
+                    const long long vb = tile * kConvTileRows + colw + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const long long v = vb + j;
+                        if (v < p.NV) {
+                            float r = acc[j] + xb[j * 33 + lane] + bco;
+                            if (p.resid) r = fmaf(p.resid_scale, __ldg(p.resid + (size_t)v * Cout + cbase + lane), r);
+                            p.out[(size_t)v * Cout + cbase + lane] = r;
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 512;\n" ::: "memory");
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar0 + 40u) : "memory");
+        }
+    } else if (lane == 0) {
+        const unsigned idesc = umma_idesc_tf32(128, 256);
+        const unsigned lboB = (unsigned)kC64LboB, lboW = 16u * 128u;
+        unsigned g = 0, tcount = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            conv_mbar_wait(bar0 + 40u, (tcount & 1u) ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            for (int it = 0; it < NIT; ++it, ++g) {
+                const unsigned s = g & 1u, use = g >> 1;
+                conv_mbar_wait(bar0 + 8u * s, use & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const unsigned sb = s0 + (unsigned)(s * kC64Stage), sw = sb + 2u * kC64BBytes;
+#pragma unroll
+                for (int j = 0; j < kConvKC / 8; ++j) {
+                    const unsigned long long wd = umma_desc(sw + (unsigned)(2 * j) * lboW, lboW, 128u);
+                    const unsigned long long xhi = umma_desc(sb + (unsigned)(2 * j) * lboB, lboB, 128u);
+                    const unsigned long long xlo = umma_desc(sb + (unsigned)kC64BBytes + (unsigned)(2 * j) * lboB, lboB, 128u);
+                    umma_tf32(tmem_base, wd, xlo, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                    umma_tf32(tmem_base, wd, xhi, idesc, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar0 + 8u * (2 + s)) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar0 + 32u) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(256) : "memory");
+    }
+}
+
+}  // namespace dlsg
+#endif

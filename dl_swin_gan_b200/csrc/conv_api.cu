@@ -11,9 +11,16 @@ static int conv_kc(int Cin, int Cout) {
     return dlsg::conv_smem_bytes(Cout) <= 227 * 1024 ? dlsg::kConvKC : 0;
 }
 
+// 64 -> 64-type layers take the operand-swapped kernel (conv3d_k3_c64_kernel); its weight image stacks the heads and remainders as rows
+static bool conv_c64(int Cin, int Cout) {
+    const char* e = std::getenv("DLSG_CONV_C64");
+    return Cout == 64 && Cin % dlsg::kConvKC == 0 && !(e && e[0] == '0');
+}
+
 int dlsg_conv3d_k3_supported(int Cin, int Cout) {
 #if defined(__CUDACC__)
-    return conv_kc(Cin, Cout);
+    const int kc = conv_kc(Cin, Cout);
+    return (kc && conv_c64(Cin, Cout)) ? (kc | 0x100) : kc;
 #else
     (void)Cin; (void)Cout;
     return 0;
@@ -52,6 +59,18 @@ int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* b
     p.relu_in = relu_in ? 1 : 0;
     if (resid && (reinterpret_cast<uintptr_t>(resid) & 15)) return DLSG_EINVAL;
     p.resid = resid; p.resid_scale = resid_scale;
+    if (conv_c64(Cin, Cout)) {
+        using namespace dlsg;
+        if (!p.x || !p.wprep || !p.out || NB <= 0 || T <= 0 || Y <= 0 || X <= 0) return DLSG_EINVAL;
+        if (X > 1022 || Y > 1022 || T > 2046 || p.NV > 0x7fffffffLL) return DLSG_EUNSUPPORTED;
+        if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.wprep) | reinterpret_cast<uintptr_t>(p.out)) & 15) return DLSG_EINVAL;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long ntiles = (p.NV + kConvTileRows - 1) / kConvTileRows;
+        const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+        return launch(conv3d_k3_c64_kernel, dim3(grid), dim3(kC64Threads), conv_c64_smem_bytes(), (stream_t)stream, p) == 0 ? DLSG_OK : DLSG_ELAUNCH;
+    }
     return conv_launch(p, stream);
 #else
     (void)x; (void)wprep; (void)bias; (void)resid; (void)resid_scale; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)relu_in; (void)stream;

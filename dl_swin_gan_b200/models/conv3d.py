@@ -32,6 +32,7 @@ def prepare_weight(weight: torch.Tensor, kc: int = 32, transposed: bool = False)
     cout, cin = w.shape[:2]
     taps = w.shape[2] * w.shape[3] * w.shape[4]
     if cin in (2, 4):
+        kc &= 0xff
         k = taps * cin
         kpad = -(-k // kc) * kc
         wk = torch.zeros(cout, kpad, device=w.device, dtype=torch.float32)
@@ -39,9 +40,11 @@ def prepare_weight(weight: torch.Tensor, kc: int = 32, transposed: bool = False)
         hi, lo = _split(wk)
         hl = torch.stack([hi, lo]).reshape(2, cout // 8, 8, kpad // kc, kc // 4, 4)          # [h, co/8, co%8, stage, k4, k%4]
         return hl.permute(3, 0, 4, 1, 2, 5).contiguous()
+    stacked, kc = bool(kc & 0x100), kc & 0xff
     hi, lo = _split(w)
     hl = torch.stack([hi, lo]).reshape(2, cout // 8, 8, cin // kc, kc // 4, 4, taps)        # [h, co/8, co%8, chunk, k4, ci%4, tap]
-    return hl.permute(6, 3, 0, 4, 1, 2, 5).contiguous()
+    # stacked (Cout = 64, 3x3x3): [taps][Cin/kc][kc/4][hi|lo][Cout/8][8][4] - one operand of 2 Cout rows, heads first
+    return hl.permute(*((6, 3, 4, 0, 1, 2, 5) if stacked else (6, 3, 0, 4, 1, 2, 5))).contiguous()
 
 
 def _cached_weight(weight: torch.Tensor, transposed: bool) -> torch.Tensor:
@@ -57,6 +60,8 @@ def _cached_weight(weight: torch.Tensor, transposed: bool) -> torch.Tensor:
         return hit[1]
     cin, cout = (weight.shape[0], weight.shape[1]) if transposed else (weight.shape[1], weight.shape[0])
     kc = _lib.load().dlsg_conv3d_k3_supported(cin, cout)
+    if transposed or tuple(weight.shape[2:]) != (3, 3, 3):
+        kc &= 0xff                       # the stacked image belongs to the 3x3x3 Cout = 64 kernel only
     prep = prepare_weight(weight, kc, transposed)
     try:
         weight._dlsg_conv_image = (tag, prep)
