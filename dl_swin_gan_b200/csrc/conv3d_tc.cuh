@@ -26,11 +26,11 @@ namespace dlsg {
 
 constexpr int kConvProducers = 256;
 constexpr int kConvThreads = kConvProducers + 32;
-constexpr int kConvStages = 2;
+constexpr int kConvStages = 4;
 constexpr int kConvKC = 32;                        // input channels per stage
 constexpr int kConvTileRows = 256;                 // voxels per CTA tile (two UMMA M = 128 accumulators)
-constexpr int kConvLboA = 128 * 16 + 16;           // bytes between the 4-channel planes of an A block: +16 so that the 8 planes a quarter-warp stores hit 8 different bank groups
-constexpr int kConvABytes = (kConvKC / 4) * kConvLboA;   // one [128 x 32] fp32 operand block
+constexpr int kConvLboA = 128 * 16 + 32;           // bytes between the 8-channel planes (8 bf16 = 16 bytes per row) of an A block: +32 so that the 4 planes a half-warp stores hit different banks
+constexpr int kConvABytes = (kConvKC / 8) * kConvLboA;   // one [128 x 32] bf16 operand block
 
 enum : int { CONV_GATHER = 0, CONV_UNPATCH = 1 };
 struct ConvParams {
@@ -49,11 +49,28 @@ struct ConvParams {
     float resid_scale;
 };
 
-__host__ __device__ inline size_t conv_stage_bytes(int Cout) { return (size_t)4 * kConvABytes + (size_t)2 * Cout * kConvKC * 4; }
+__host__ __device__ inline size_t conv_stage_bytes(int Cout) { return (size_t)4 * kConvABytes + (size_t)2 * Cout * kConvKC * 2; }
 inline size_t conv_smem_bytes(int Cout) { return kConvStages * conv_stage_bytes(Cout) + (size_t)Cout * 4 + 128; }
 
 __device__ __forceinline__ unsigned umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+// kind::f16 with bf16 operands (format 1), fp32 accumulation
+__device__ __forceinline__ unsigned umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+// four floats -> bf16 heads (round to nearest) and bf16 remainders, each packed as 4 x 16 bit
+__device__ __forceinline__ void bf16_split4(float4 v, uint2& hi, uint2& lo) {
+    unsigned h01, h23;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h01) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h23) : "f"(v.w), "f"(v.z));
+    const float r0 = v.x - __uint_as_float(h01 << 16), r1 = v.y - __uint_as_float(h01 & 0xffff0000u);
+    const float r2 = v.z - __uint_as_float(h23 << 16), r3 = v.w - __uint_as_float(h23 & 0xffff0000u);
+    unsigned l01, l23;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l01) : "f"(r1), "f"(r0));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l23) : "f"(r3), "f"(r2));
+    hi = make_uint2(h01, h23);
+    lo = make_uint2(l01, l23);
 }
 __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
                                           unsigned idesc, unsigned accumulate) {
@@ -90,12 +107,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
     const bool unpatch = (CS == 0) && p.mode == CONV_UNPATCH;
     const int NIT = (CS == 0) ? (unpatch ? KCH : ntaps * KCH) : (27 * CS + kConvKC - 1) / kConvKC;
     const size_t stage_bytes = conv_stage_bytes(Cout);
-    const unsigned wblock = (unsigned)Cout * kConvKC * 4;            // one of w_hi / w_lo for a stage
+    const unsigned wblock = (unsigned)Cout * kConvKC * 2;            // one of w_hi / w_lo (bf16) for a stage
     float* sBias = reinterpret_cast<float*>(conv_smem + kConvStages * stage_bytes);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sBias + Cout);   // full[2], empty[2], accfull, accempty
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 6);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sBias + Cout);   // full[S], empty[S], accfull, accempty
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * kConvStages + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned s0 = smem_u32(conv_smem), bar0 = smem_u32(bars);
+    const unsigned bempty = bar0 + 8u * kConvStages, baccfull = bar0 + 16u * kConvStages, baccempty = baccfull + 8u;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
@@ -104,10 +122,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
     if (tid == 0) {
         for (int s = 0; s < kConvStages; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 8u * s), "r"(kConvProducers + 1) : "memory");        // full
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 8u * (2 + s)), "r"(1) : "memory");                  // empty
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bempty + 8u * s), "r"(1) : "memory");                      // empty
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 32u), "r"(1) : "memory");                               // accfull
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 40u), "r"(kConvProducers) : "memory");                  // accempty
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(baccfull), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(baccempty), "r"(kConvProducers) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     for (int i = tid; i < Cout; i += kConvThreads) sBias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
@@ -162,76 +180,93 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                                 (unsigned)((c & 1023) + c2 - 1) < (unsigned)p.X;
                 return ok ? p.x + ((long long)ibase[i] + ((long long)a * p.Y + b2) * p.X + c2) * CS : nullptr;
             };
-            for (int it = 0; it < NIT; ++it, ++g) {
-                {
-                    const unsigned s = g & 1u, use = g >> 1;
-                    float4 a[8];
-                    if (CS == 0) {
-                        const int tap = it / KCH, ch = it - tap * KCH;
-                        if (ch == 0) {
-                            okmask = 0;
-                            if (unpatch) {
+            // the global loads run one iteration ahead of the split / store (their L2 latency is longer than a stage; with 216 KB of
+            // shared memory in use there is no L1 to speak of): `fetch(it, dst)` issues iteration it's loads, its tap state is its own
+            // element offset of each row's first-tap voxel (this thread's channel quad); all address arithmetic in the loop is 32-bit
+            unsigned roff[8];
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) okmask |= (coord[i] >= 0 ? 1u : 0u) << i;
-                                tapoff = 0;
-                            } else {
-                                const int ta = tap / (ksz * ksz), tb = (tap / ksz) % ksz, tc = tap % ksz;
+            for (int i = 0; i < 8; ++i) roff[i] = (unsigned)ibase[i] * (unsigned)((CS == 0) ? p.Cin : CS) + ((CS == 0) ? 4u * k4 : 0u);
+            int ftap = 0, fch = 0;                                  // (tap, chunk) of the next fetch
+            unsigned foff = 0;                                      // tap offset * Cin + chunk * 32 of the next fetch
+            auto tap_state = [&](int tap) {
+                okmask = 0;
+                if (unpatch) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int c = coord[i];
-                                    const bool ok = c >= 0 && (unsigned)((c >> 20) + ta - 1) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + tb - 1) < (unsigned)p.Y &&
-                                                    (unsigned)((c & 1023) + tc - 1) < (unsigned)p.X;
-                                    okmask |= (ok ? 1u : 0u) << i;
-                                }
-                                tapoff = (ta * p.Y + tb) * p.X + tc;
-                            }
-                        }
+                    for (int i = 0; i < 8; ++i) okmask |= (coord[i] >= 0 ? 1u : 0u) << i;
+                    tapoff = 0;
+                } else {
+                    const int ta = tap / (ksz * ksz), tb = (tap / ksz) % ksz, tc = tap % ksz;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            a[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.x + ((long long)ibase[i] + tapoff) * p.Cin + ch * kConvKC + 4 * k4))
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                    } else if (CS == 4) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float* q = tap_ptr(i, 8 * it + k4);
-                            a[i] = q ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float* q0 = tap_ptr(i, 2 * (8 * it + k4));
-                            const float* q1 = tap_ptr(i, 2 * (8 * it + k4) + 1);
-                            const float2 lo2 = q0 ? __ldg(reinterpret_cast<const float2*>(q0)) : make_float2(0.f, 0.f);
-                            const float2 hi2 = q1 ? __ldg(reinterpret_cast<const float2*>(q1)) : make_float2(0.f, 0.f);
-                            a[i] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
-                        }
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = coord[i];
+                        const bool ok = c >= 0 && (unsigned)((c >> 20) + ta - 1) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + tb - 1) < (unsigned)p.Y &&
+                                        (unsigned)((c & 1023) + tc - 1) < (unsigned)p.X;
+                        okmask |= (ok ? 1u : 0u) << i;
                     }
-                    conv_mbar_wait(bar0 + 8u * (2 + s), (use & 1u) ^ 1u);             // stage free (passes at once on first use)
+                    tapoff = (ta * p.Y + tb) * p.X + tc;
+                }
+                foff = (unsigned)tapoff * (unsigned)p.Cin;
+            };
+            if (CS == 0) tap_state(0);
+            auto fetch = [&](int it, float4* a) {
+                if (CS == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        a[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.x + (roff[i] + foff))) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (++fch == KCH) { fch = 0; if (++ftap < ntaps) tap_state(ftap); } else foff += kConvKC;
+                } else if (CS == 4) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float* q = tap_ptr(i, 8 * it + k4);
+                        a[i] = q ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float* q0 = tap_ptr(i, 2 * (8 * it + k4));
+                        const float* q1 = tap_ptr(i, 2 * (8 * it + k4) + 1);
+                        const float2 lo2 = q0 ? __ldg(reinterpret_cast<const float2*>(q0)) : make_float2(0.f, 0.f);
+                        const float2 hi2 = q1 ? __ldg(reinterpret_cast<const float2*>(q1)) : make_float2(0.f, 0.f);
+                        a[i] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+                    }
+                }
+            };
+            float4 a[8], an[8];
+            fetch(0, a);
+            for (int it = 0; it < NIT; ++it, ++g) {
+                if (it + 1 < NIT) fetch(it + 1, an);
+                {
+                    const unsigned s = g % kConvStages, use = g / kConvStages;
+                    conv_mbar_wait(bempty + 8u * s, (use & 1u) ^ 1u);                 // stage free (passes at once on first use)
                     unsigned char* st = conv_smem + s * stage_bytes;
                     if (tid == 0) {
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar0 + 8u * s), "r"(2u * wblock) : "memory");
                         conv_bulk_load(s0 + (unsigned)(s * stage_bytes) + 4u * kConvABytes,
-                                       p.wprep + ((size_t)cls * KCH + it) * 2 * (size_t)Cout * kConvKC, 2u * wblock, bar0 + 8u * s);
+                                       reinterpret_cast<const unsigned char*>(p.wprep) + ((size_t)cls * KCH + it) * 2 * (size_t)wblock, 2u * wblock, bar0 + 8u * s);
                     }
-                    unsigned char* ahi = st + (size_t)(2 * ti) * kConvABytes + (size_t)k4 * kConvLboA;
+                    // this thread's 4 channels are half of a 16-byte core-matrix row: plane k4 / 2, bytes 8 (k4 % 2) ..
+                    unsigned char* ahi = st + (size_t)(2 * ti) * kConvABytes + (size_t)(k4 >> 1) * kConvLboA + (k4 & 1) * 8;
                     unsigned char* alo = ahi + kConvABytes;
+                    // row = wrow0 + rsub + 4 i with rsub < 4: row i sits (i / 2) * 128 + (i % 2) * 64 bytes after row 0
+                    const unsigned off0 = (unsigned)((wrow0 + rsub) >> 3) * 128u + (unsigned)(rsub & 7) * 16u;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int row = wrow0 + 4 * i + rsub;
-                        const unsigned off = (unsigned)(row >> 3) * 128u + (unsigned)(row & 7) * 16u;
-                        float4 x4 = a[i], h4, l4;
+                        const unsigned off = off0 + (unsigned)(i >> 1) * 128u + (unsigned)(i & 1) * 64u;
+                        float4 x4 = a[i];
                         if (p.relu_in) { x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f); }
-                        tf32_split(x4.x, h4.x, l4.x); tf32_split(x4.y, h4.y, l4.y);
-                        tf32_split(x4.z, h4.z, l4.z); tf32_split(x4.w, h4.w, l4.w);
-                        *reinterpret_cast<float4*>(ahi + off) = h4;
-                        *reinterpret_cast<float4*>(alo + off) = l4;
+                        uint2 h2, l2;
+                        bf16_split4(x4, h2, l2);
+                        *reinterpret_cast<uint2*>(ahi + off) = h2;
+                        *reinterpret_cast<uint2*>(alo + off) = l2;
                     }
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar0 + 8u * s) : "memory");
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = an[i];
             }
             // ---- epilogue: this warp's 32 TMEM lanes of its accumulator
-            conv_mbar_wait(bar0 + 32u, tcount & 1u);
+            conv_mbar_wait(baccfull, tcount & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const long long v = rtile * kConvTileRows + tid;                         // epilogue: thread = accumulator row (TMEM lane)
             const bool live = v < p.NV;
@@ -265,18 +300,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar0 + 40u) : "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(baccempty) : "memory");
         }
     } else if (lane == 0) {
         // =========================== MMA issuer ===========================
-        const unsigned idesc = umma_idesc_tf32(128, Cout);
+        const unsigned idesc = umma_idesc_bf16(128, Cout);
         const unsigned lboA = (unsigned)kConvLboA, lboW = (unsigned)(Cout / 8) * 128u;
         unsigned g = 0, tcount = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-            conv_mbar_wait(bar0 + 40u, (tcount & 1u) ^ 1u);                          // accumulators drained
+            conv_mbar_wait(baccempty, (tcount & 1u) ^ 1u);                           // accumulators drained
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             for (int it = 0; it < NIT; ++it, ++g) {
-                const unsigned s = g & 1u, use = g >> 1;
+                const unsigned s = g % kConvStages, use = g / kConvStages;
                 conv_mbar_wait(bar0 + 8u * s, use & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const unsigned sa = s0 + (unsigned)(s * stage_bytes), sw = sa + 4u * kConvABytes;
@@ -284,19 +319,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                 for (int ti = 0; ti < 2; ++ti) {
                     const unsigned d = tmem_base + (unsigned)(ti * 256);
 #pragma unroll
-                    for (int j = 0; j < kConvKC / 8; ++j) {
+                    for (int j = 0; j < kConvKC / 16; ++j) {                          // K = 16 per instruction = two 8-channel planes
                         const unsigned long long ahi = umma_desc(sa + (unsigned)(2 * ti) * kConvABytes + (unsigned)(2 * j) * lboA, lboA, 128u);
                         const unsigned long long alo = umma_desc(sa + (unsigned)(2 * ti + 1) * kConvABytes + (unsigned)(2 * j) * lboA, lboA, 128u);
                         const unsigned long long whi = umma_desc(sw + (unsigned)(2 * j) * lboW, lboW, 128u);
                         const unsigned long long wlo = umma_desc(sw + wblock + (unsigned)(2 * j) * lboW, lboW, 128u);
-                        umma_tf32(d, alo, whi, idesc, (it > 0 || j > 0) ? 1u : 0u);
-                        umma_tf32(d, ahi, wlo, idesc, 1u);
-                        umma_tf32(d, ahi, whi, idesc, 1u);
+                        umma_f16(d, alo, whi, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                        umma_f16(d, ahi, wlo, idesc, 1u);
+                        umma_f16(d, ahi, whi, idesc, 1u);
                     }
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar0 + 8u * (2 + s)) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bempty + 8u * s) : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar0 + 32u) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(baccfull) : "memory");
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -325,9 +360,9 @@ namespace dlsg {
 
 constexpr int kC64Producers = 512;                      // 16 producer warps (4 per scheduler): the producers are latency-, not throughput-bound
 constexpr int kC64Threads = kC64Producers + 32;
-constexpr int kC64LboB = 32 * 128 + 16;                 // bytes between the 4-channel planes of the 256-row activation block (+16: bank spread)
-constexpr int kC64BBytes = (kConvKC / 4) * kC64LboB;    // one of X_hi / X_lo for a stage
-constexpr int kC64WBytes = 128 * kConvKC * 4;           // [W_hi; W_lo] for a stage
+constexpr int kC64LboB = 32 * 128 + 32;                 // bytes between the 8-channel planes of the 256-row activation block (+32: bank spread)
+constexpr int kC64BBytes = (kConvKC / 8) * kC64LboB;    // one of X_hi / X_lo (bf16) for a stage
+constexpr int kC64WBytes = 128 * kConvKC * 2;           // [W_hi; W_lo] (bf16) for a stage
 constexpr int kC64Stage = 2 * kC64BBytes + kC64WBytes;
 inline size_t conv_c64_smem_bytes() { return (size_t)kConvStages * kC64Stage + 64 * 4 + 128; }
 
@@ -336,10 +371,11 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
     constexpr int Cout = 64;
     const int KCH = p.Cin / kConvKC, NIT = 27 * KCH;
     float* sBias = reinterpret_cast<float*>(conv_smem + kConvStages * kC64Stage);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sBias + Cout);   // full[2], empty[2], accfull, accempty
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 6);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sBias + Cout);   // full[S], empty[S], accfull, accempty
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * kConvStages + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned s0 = smem_u32(conv_smem), bar0 = smem_u32(bars);
+    const unsigned bempty = bar0 + 8u * kConvStages, baccfull = bar0 + 16u * kConvStages, baccempty = baccfull + 8u;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(256) : "memory");
@@ -348,10 +384,10 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
     if (tid == 0) {
         for (int s = 0; s < kConvStages; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 8u * s), "r"(kC64Producers + 1) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 8u * (2 + s)), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bempty + 8u * s), "r"(1) : "memory");
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 32u), "r"(1) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar0 + 40u), "r"(kC64Producers) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(baccfull), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(baccempty), "r"(kC64Producers) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     for (int i = tid; i < Cout; i += kC64Threads) sBias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
@@ -409,26 +445,26 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
                         if (++nch == KCH) { nch = 0; tap_setup(++ntap); }
                         load(an, nch);
                     }
-                    const unsigned s = g & 1u, use = g >> 1;
-                    conv_mbar_wait(bar0 + 8u * (2 + s), (use & 1u) ^ 1u);
+                    const unsigned s = g % kConvStages, use = g / kConvStages;
+                    conv_mbar_wait(bempty + 8u * s, (use & 1u) ^ 1u);
                     unsigned char* st = conv_smem + (size_t)s * kC64Stage;
                     if (tid == 0) {
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar0 + 8u * s), "r"((unsigned)kC64WBytes) : "memory");
                         conv_bulk_load(s0 + (unsigned)(s * kC64Stage) + 2u * kC64BBytes,
-                                       p.wprep + ((size_t)tap * KCH + ch) * (kC64WBytes / 4), (unsigned)kC64WBytes, bar0 + 8u * s);
+                                       reinterpret_cast<const unsigned char*>(p.wprep) + ((size_t)tap * KCH + ch) * kC64WBytes, (unsigned)kC64WBytes, bar0 + 8u * s);
                     }
-                    unsigned char* bhi = st + (size_t)k4 * kC64LboB;
+                    unsigned char* bhi = st + (size_t)(k4 >> 1) * kC64LboB + (k4 & 1) * 8;
                     unsigned char* blo = bhi + kC64BBytes;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int row = wrow0 + 4 * i + rsub;
                         const unsigned off = (unsigned)(row >> 3) * 128u + (unsigned)(row & 7) * 16u;
-                        float4 x4 = a[i], h4, l4;
+                        float4 x4 = a[i];
                         if (p.relu_in) { x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f); }
-                        tf32_split(x4.x, h4.x, l4.x); tf32_split(x4.y, h4.y, l4.y);
-                        tf32_split(x4.z, h4.z, l4.z); tf32_split(x4.w, h4.w, l4.w);
-                        *reinterpret_cast<float4*>(bhi + off) = h4;
-                        *reinterpret_cast<float4*>(blo + off) = l4;
+                        uint2 h2, l2;
+                        bf16_split4(x4, h2, l2);
+                        *reinterpret_cast<uint2*>(bhi + off) = h2;
+                        *reinterpret_cast<uint2*>(blo + off) = l2;
                     }
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar0 + 8u * s) : "memory");
@@ -438,7 +474,7 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
             }
             // ---- epilogue.  TMEM lane = (half, co): warp quarter q = warp & 3 holds co = 32 (q & 1) + lane of half q >> 1 (0: W_hi rows, 1: W_lo rows);
             // warps 4 g .. 4 g + 3 take voxel columns 64 g .. 64 g + 63.  The stage buffers are idle now and carry the lo halves.
-            conv_mbar_wait(bar0 + 32u, tcount & 1u);
+            conv_mbar_wait(baccfull, tcount & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const int q = warp & 3, half = q >> 1, cbase = 32 * (q & 1), colw = (warp >> 2) * 64;
             const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16);
@@ -467,31 +503,31 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
                 asm volatile("bar.sync 1, 512;\n" ::: "memory");
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar0 + 40u) : "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(baccempty) : "memory");
         }
     } else if (lane == 0) {
-        const unsigned idesc = umma_idesc_tf32(128, 256);
+        const unsigned idesc = umma_idesc_bf16(128, 256);
         const unsigned lboB = (unsigned)kC64LboB, lboW = 16u * 128u;
         unsigned g = 0, tcount = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-            conv_mbar_wait(bar0 + 40u, (tcount & 1u) ^ 1u);
+            conv_mbar_wait(baccempty, (tcount & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             for (int it = 0; it < NIT; ++it, ++g) {
-                const unsigned s = g & 1u, use = g >> 1;
+                const unsigned s = g % kConvStages, use = g / kConvStages;
                 conv_mbar_wait(bar0 + 8u * s, use & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const unsigned sb = s0 + (unsigned)(s * kC64Stage), sw = sb + 2u * kC64BBytes;
 #pragma unroll
-                for (int j = 0; j < kConvKC / 8; ++j) {
+                for (int j = 0; j < kConvKC / 16; ++j) {
                     const unsigned long long wd = umma_desc(sw + (unsigned)(2 * j) * lboW, lboW, 128u);
                     const unsigned long long xhi = umma_desc(sb + (unsigned)(2 * j) * lboB, lboB, 128u);
                     const unsigned long long xlo = umma_desc(sb + (unsigned)kC64BBytes + (unsigned)(2 * j) * lboB, lboB, 128u);
-                    umma_tf32(tmem_base, wd, xlo, idesc, (it > 0 || j > 0) ? 1u : 0u);
-                    umma_tf32(tmem_base, wd, xhi, idesc, 1u);
+                    umma_f16(tmem_base, wd, xlo, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                    umma_f16(tmem_base, wd, xhi, idesc, 1u);
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar0 + 8u * (2 + s)) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bempty + 8u * s) : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar0 + 32u) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(baccfull) : "memory");
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");

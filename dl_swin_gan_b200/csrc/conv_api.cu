@@ -32,7 +32,8 @@ static int conv_launch(dlsg::ConvParams& p, void* stream) {
     using namespace dlsg;
     if (!p.x || !p.wprep || !p.out || p.NB <= 0 || p.T <= 0 || p.Y <= 0 || p.X <= 0 || p.To <= 0 || p.Yo <= 0 || p.Xo <= 0) return DLSG_EINVAL;
     if (!conv_kc(p.Cin, p.Cout) || p.X > 1022 || p.Y > 1022 || p.T > 2046) return DLSG_EUNSUPPORTED;
-    if ((long long)p.NB * p.T * p.Y * p.X > 0x7fffffffLL || (long long)p.NB * p.To * p.Yo * p.Xo > 0x7fffffffLL) return DLSG_EUNSUPPORTED;
+    // the kernel's address arithmetic is 32-bit in elements
+    if ((long long)p.NB * p.T * p.Y * p.X * p.Cin > 0x7fffffffLL || (long long)p.NB * p.To * p.Yo * p.Xo > 0x7fffffffLL) return DLSG_EUNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.wprep) | reinterpret_cast<uintptr_t>(p.out)) & 15) return DLSG_EINVAL;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -16,34 +16,35 @@ K3, PATCH, UNPATCH, FEWOUT = "k3", "patch", "unpatch", "fewout"
 
 
 def _split(t: torch.Tensor):
-    hi = ((t.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
-    return hi, t - hi
+    """t = hi + lo + O(2^-18 t): bf16 head (round to nearest) and bf16 remainder."""
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi, lo
 
 
 def prepare_weight(weight: torch.Tensor, kc: int = 32, transposed: bool = False) -> torch.Tensor:
-    """weight [Cout, Cin, k, k, k] (or [Cin, Cout, k, k, k] of a transposed convolution) -> the kernel's operand image
-    (include/dlsg_b200.h); kc = K elements per pipeline stage, as `dlsg_conv3d_k3_supported(Cin, Cout)` reports it.
-      Cin % 32 == 0:  [k^3][Cin/kc][hi|lo][kc/4][Cout/8][8][4]                    K walks (tap, channel chunk)
-      Cin = 2 or 4:   [ceil(27 Cin / kc)][hi|lo][kc/4][Cout/8][8][4]              K index = tap * Cin + ci, zero-padded"""
+    """weight [Cout, Cin, k, k, k] (or [Cin, Cout, k, k, k] of a transposed convolution) -> the kernel's bf16 operand image
+    (include/dlsg_b200.h); kc = K elements per pipeline stage, as `dlsg_conv3d_k3_supported(Cin, Cout)` reports it (bit 0x100: stacked).
+      Cin % 32 == 0:  [k^3][Cin/kc][hi|lo][kc/8][Cout/8][8][8]                    K walks (tap, channel chunk)
+      stacked:        [k^3][Cin/kc][kc/8][hi|lo][Cout/8][8][8]                    one operand of 2 Cout rows, heads first (Cout = 64, 3x3x3)
+      Cin = 2 or 4:   [ceil(27 Cin / kc)][hi|lo][kc/8][Cout/8][8][8]              K index = tap * Cin + ci, zero-padded"""
     w = weight.detach().float()
     if transposed:
         w = w.transpose(0, 1)
     w = w.contiguous()
     cout, cin = w.shape[:2]
     taps = w.shape[2] * w.shape[3] * w.shape[4]
+    stacked, kc = bool(kc & 0x100), kc & 0xff
     if cin in (2, 4):
-        kc &= 0xff
         k = taps * cin
         kpad = -(-k // kc) * kc
         wk = torch.zeros(cout, kpad, device=w.device, dtype=torch.float32)
         wk[:, :k] = w.reshape(cout, cin, taps).permute(0, 2, 1).reshape(cout, k)
         hi, lo = _split(wk)
-        hl = torch.stack([hi, lo]).reshape(2, cout // 8, 8, kpad // kc, kc // 4, 4)          # [h, co/8, co%8, stage, k4, k%4]
+        hl = torch.stack([hi, lo]).reshape(2, cout // 8, 8, kpad // kc, kc // 8, 8)          # [h, co/8, co%8, stage, k8, k%8]
         return hl.permute(3, 0, 4, 1, 2, 5).contiguous()
-    stacked, kc = bool(kc & 0x100), kc & 0xff
     hi, lo = _split(w)
-    hl = torch.stack([hi, lo]).reshape(2, cout // 8, 8, cin // kc, kc // 4, 4, taps)        # [h, co/8, co%8, chunk, k4, ci%4, tap]
-    # stacked (Cout = 64, 3x3x3): [taps][Cin/kc][kc/4][hi|lo][Cout/8][8][4] - one operand of 2 Cout rows, heads first
+    hl = torch.stack([hi, lo]).reshape(2, cout // 8, 8, cin // kc, kc // 8, 8, taps)        # [h, co/8, co%8, chunk, k8, ci%8, tap]
     return hl.permute(*((6, 3, 4, 0, 1, 2, 5) if stacked else (6, 3, 0, 4, 1, 2, 5))).contiguous()
 
 
