@@ -81,10 +81,10 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long ad
 // bounded wait: a broken pipeline traps instead of hanging the GPU
 __device__ __forceinline__ void conv_mbar_wait(unsigned bar, unsigned parity) {
     unsigned done = 0;
-    for (long long spin = 0; !done; ++spin) {
+    for (unsigned spin = 0; !done; ++spin) {             // try_wait suspends for a while by itself; 2^26 rounds is seconds
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1ll << 28)) __trap();
+        if (spin > (1u << 26)) __trap();
     }
 }
 __device__ __forceinline__ void conv_bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
@@ -99,7 +99,7 @@ __device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
 // CS = 0: Cin % 32 == 0, the K loop walks (tap, 32-channel chunk).  CS = 2 / 4: the first layer of a denoiser (Cin = 2 or 4 = re / im of the
 // E map sets): K runs over k = tap * Cin + ci, padded with zero weights to a multiple of 32; a 16-byte quad of a stage is one tap (CS = 4)
 // or two taps (CS = 2) of one voxel, so a stage gathers 8 / 16 taps and the whole layer is 4 / 2 stages per tile.
-template <int CS>
+template <int CS, bool RELU>
 __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvParams p) {
     extern __shared__ __align__(1024) unsigned char conv_smem[];
     const int Cout = p.Cout, KCH = (CS == 0) ? p.Cin / kConvKC : 1;
@@ -231,11 +231,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                     }
                 }
             };
-            float4 a[8], an[8];
-            fetch(0, a);
-            for (int it = 0; it < NIT; ++it, ++g) {
-                if (it + 1 < NIT) fetch(it + 1, an);
-                {
+            float4 a0[8], a1[8];
+            auto stage = [&](int it, const float4* a) {
                     const unsigned s = g % kConvStages, use = g / kConvStages;
                     conv_mbar_wait(bempty + 8u * s, (use & 1u) ^ 1u);                 // stage free (passes at once on first use)
                     unsigned char* st = conv_smem + s * stage_bytes;
@@ -253,7 +250,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                     for (int i = 0; i < 8; ++i) {
                         const unsigned off = off0 + (unsigned)(i >> 1) * 128u + (unsigned)(i & 1) * 64u;
                         float4 x4 = a[i];
-                        if (p.relu_in) { x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f); }
+                        if (RELU) { x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f); }
                         uint2 h2, l2;
                         bf16_split4(x4, h2, l2);
                         *reinterpret_cast<uint2*>(ahi + off) = h2;
@@ -261,9 +258,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                     }
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar0 + 8u * s) : "memory");
+            };
+            fetch(0, a0);
+            for (int it = 0; it < NIT; it += 2) {                    // two iterations per round: the register sets alternate without copies
+                if (it + 1 < NIT) fetch(it + 1, a1);
+                stage(it, a0);
+                ++g;
+                if (it + 1 < NIT) {
+                    if (it + 2 < NIT) fetch(it + 2, a0);
+                    stage(it + 1, a1);
+                    ++g;
                 }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = an[i];
             }
             // ---- epilogue: this warp's 32 TMEM lanes of its accumulator
             conv_mbar_wait(baccfull, tcount & 1u);

@@ -42,9 +42,15 @@ static int conv_launch(dlsg::ConvParams& p, void* stream) {
     if (p.mode == CONV_UNPATCH) ntiles *= (long long)p.ksz * p.ksz * p.ksz;
     const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
     const size_t smem = conv_smem_bytes(p.Cout);
-    const int rc = p.Cin == 2 ? launch(conv3d_k3_tf32x3_kernel<2>, dim3(grid), dim3(kConvThreads), smem, (stream_t)stream, p)
-                 : p.Cin == 4 ? launch(conv3d_k3_tf32x3_kernel<4>, dim3(grid), dim3(kConvThreads), smem, (stream_t)stream, p)
-                              : launch(conv3d_k3_tf32x3_kernel<0>, dim3(grid), dim3(kConvThreads), smem, (stream_t)stream, p);
+    int rc;
+    if (p.relu_in)
+        rc = p.Cin == 2 ? launch(conv3d_k3_tf32x3_kernel<2, true>, dim3(grid), dim3(kConvThreads), smem, (stream_t)stream, p)
+           : p.Cin == 4 ? launch(conv3d_k3_tf32x3_kernel<4, true>, dim3(grid), dim3(kConvThreads), smem, (stream_t)stream, p)
+                        : launch(conv3d_k3_tf32x3_kernel<0, true>, dim3(grid), dim3(kConvThreads), smem, (stream_t)stream, p);
+    else
+        rc = p.Cin == 2 ? launch(conv3d_k3_tf32x3_kernel<2, false>, dim3(grid), dim3(kConvThreads), smem, (stream_t)stream, p)
+           : p.Cin == 4 ? launch(conv3d_k3_tf32x3_kernel<4, false>, dim3(grid), dim3(kConvThreads), smem, (stream_t)stream, p)
+                        : launch(conv3d_k3_tf32x3_kernel<0, false>, dim3(grid), dim3(kConvThreads), smem, (stream_t)stream, p);
     return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
 }
 #endif
