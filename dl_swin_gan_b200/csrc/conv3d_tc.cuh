@@ -24,8 +24,9 @@
 #if defined(__CUDACC__)
 namespace dlsg {
 
-constexpr int kConvProducers = 256;
+constexpr int kConvProducers = 512;                // 16 producer warps: two threads per voxel row pair ... four rows per thread and stage
 constexpr int kConvThreads = kConvProducers + 32;
+constexpr int kConvRows = 4;                       // rows per producer thread and stage
 constexpr int kConvStages = 4;
 constexpr int kConvKC = 32;                        // input channels per stage
 constexpr int kConvTileRows = 256;                 // voxels per CTA tile (two UMMA M = 128 accumulators)
@@ -144,18 +145,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
         // =========================== producers, then epilogue ===========================
         // loads are coalesced: 8 lanes cover the 128 bytes of one voxel's channel chunk, a warp instruction takes 4 voxels;
         // thread (lane) owns channel quad k4 = lane & 7 of rows 4 i + (lane >> 3), i = 0..7, of its warp's 32 rows
-        const int ti = tid >> 7;
+        const int ti = warp >> 3;                                // which of the two 128-row blocks this warp fills
         const int k4 = lane & 7, rsub = lane >> 3;
-        const int wrow0 = (warp & 3) * 32;                       // first row of this warp inside its 128-row block
+        const int wrow0 = (warp & 7) * 16;                       // first of this warp's 16 rows inside its 128-row block
         unsigned g = 0, tcount = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
             const long long rtile = unpatch ? tile / ntaps : tile;
             const int cls = unpatch ? (int)(tile - rtile * ntaps) : 0;
             const long long v0 = rtile * kConvTileRows + ti * 128 + wrow0 + rsub;     // this thread's GEMM rows: v0 + 4 i
             // per row: packed (t, y, x) + 1 of the first tap's input voxel (-1 = row beyond the problem) and that voxel's index
-            int coord[8], ibase[8];
+            int coord[kConvRows], ibase[kConvRows];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < kConvRows; ++i) {
                 const long long vi = v0 + 4 * i;
                 coord[i] = -1; ibase[i] = 0;
                 if (vi < p.NV) {
@@ -183,21 +184,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
             // the global loads run one iteration ahead of the split / store (their L2 latency is longer than a stage; with 216 KB of
             // shared memory in use there is no L1 to speak of): `fetch(it, dst)` issues iteration it's loads, its tap state is its own
             // element offset of each row's first-tap voxel (this thread's channel quad); all address arithmetic in the loop is 32-bit
-            unsigned roff[8];
+            unsigned roff[kConvRows];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) roff[i] = (unsigned)ibase[i] * (unsigned)((CS == 0) ? p.Cin : CS) + ((CS == 0) ? 4u * k4 : 0u);
+            for (int i = 0; i < kConvRows; ++i) roff[i] = (unsigned)ibase[i] * (unsigned)((CS == 0) ? p.Cin : CS) + ((CS == 0) ? 4u * k4 : 0u);
             int ftap = 0, fch = 0;                                  // (tap, chunk) of the next fetch
             unsigned foff = 0;                                      // tap offset * Cin + chunk * 32 of the next fetch
             auto tap_state = [&](int tap) {
                 okmask = 0;
                 if (unpatch) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) okmask |= (coord[i] >= 0 ? 1u : 0u) << i;
+                    for (int i = 0; i < kConvRows; ++i) okmask |= (coord[i] >= 0 ? 1u : 0u) << i;
                     tapoff = 0;
                 } else {
                     const int ta = tap / (ksz * ksz), tb = (tap / ksz) % ksz, tc = tap % ksz;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < kConvRows; ++i) {
                         const int c = coord[i];
                         const bool ok = c >= 0 && (unsigned)((c >> 20) + ta - 1) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + tb - 1) < (unsigned)p.Y &&
                                         (unsigned)((c & 1023) + tc - 1) < (unsigned)p.X;
@@ -211,18 +212,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
             auto fetch = [&](int it, float4* a) {
                 if (CS == 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < kConvRows; ++i)
                         a[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.x + (roff[i] + foff))) : make_float4(0.f, 0.f, 0.f, 0.f);
                     if (++fch == KCH) { fch = 0; if (++ftap < ntaps) tap_state(ftap); } else foff += kConvKC;
                 } else if (CS == 4) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < kConvRows; ++i) {
                         const float* q = tap_ptr(i, 8 * it + k4);
                         a[i] = q ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < kConvRows; ++i) {
                         const float* q0 = tap_ptr(i, 2 * (8 * it + k4));
                         const float* q1 = tap_ptr(i, 2 * (8 * it + k4) + 1);
                         const float2 lo2 = q0 ? __ldg(reinterpret_cast<const float2*>(q0)) : make_float2(0.f, 0.f);
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                     }
                 }
             };
-            float4 a0[8], a1[8];
+            float4 a0[kConvRows], a1[kConvRows];
             auto stage = [&](int it, const float4* a) {
                     const unsigned s = g % kConvStages, use = g / kConvStages;
                     conv_mbar_wait(bempty + 8u * s, (use & 1u) ^ 1u);                 // stage free (passes at once on first use)
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                     // row = wrow0 + rsub + 4 i with rsub < 4: row i sits (i / 2) * 128 + (i % 2) * 64 bytes after row 0
                     const unsigned off0 = (unsigned)((wrow0 + rsub) >> 3) * 128u + (unsigned)(rsub & 7) * 16u;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < kConvRows; ++i) {
                         const unsigned off = off0 + (unsigned)(i >> 1) * 128u + (unsigned)(i & 1) * 64u;
                         float4 x4 = a[i];
                         if (RELU) { x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f); }
@@ -273,9 +274,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
             // ---- epilogue: this warp's 32 TMEM lanes of its accumulator
             conv_mbar_wait(baccfull, tcount & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const long long v = rtile * kConvTileRows + tid;                         // epilogue: thread = accumulator row (TMEM lane)
+            // epilogue: thread = accumulator row (TMEM lane 32 (warp % 4) + lane) of block eti; warps w and w + 8 share rows and split the columns
+            const int eti = (warp >> 2) & 1, ehalf = warp >> 3;
+            const long long v = rtile * kConvTileRows + eti * 128 + (warp & 3) * 32 + lane;
             const bool live = v < p.NV;
-            const unsigned taddr = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(ti * 256);
+            const unsigned taddr = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(eti * 256);
             long long vout = v;
             if (unpatch && live) {                                                   // input voxel (n, t, y, x) -> output voxel (n, t k + a, y k + b, x k + c)
                 const long long r1 = v % YX;
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
             }
             float* orow = p.out + (size_t)vout * Cout;
             const float* rrow = p.resid ? p.resid + (size_t)vout * Cout : nullptr;
-            for (int c0 = 0; c0 < Cout; c0 += 32) {
+            for (int c0 = 32 * ehalf; c0 < Cout; c0 += 64) {
                 float acc[32];
                 tmem_ld32(taddr + (unsigned)c0, acc);
                 if (live && rrow) {
