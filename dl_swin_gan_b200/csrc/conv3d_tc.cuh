@@ -374,6 +374,7 @@ constexpr int kC64WBytes = 128 * kConvKC * 2;           // [W_hi; W_lo] (bf16) f
 constexpr int kC64Stage = 2 * kC64BBytes + kC64WBytes;
 inline size_t conv_c64_smem_bytes() { return (size_t)kConvStages * kC64Stage + 64 * 4 + 128; }
 
+template <bool RELU>
 __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParams p) {
     extern __shared__ __align__(1024) unsigned char conv_smem[];
     constexpr int Cout = 64;
@@ -421,10 +422,12 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
                     coord[i] = (int)((vi / YX) % p.T) << 20 | (int)(r1 / p.X) << 10 | (int)(r1 % p.X);
                 } else coord[i] = -1;
             }
-            // the loads of iteration it + 1 are in flight while iteration it is split and stored (their latency exceeds a stage)
-            unsigned okmask = 0;
-            const float* src = p.x;
-            auto tap_setup = [&](int tap) {
+            // the loads run one iteration ahead of the split / store; 32-bit element offsets, (tap, chunk) advanced incrementally
+            unsigned okmask = 0, foff = 0;
+            unsigned roff[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) roff[i] = (unsigned)(v0 + 4 * i) * (unsigned)p.Cin + 4u * k4;
+            auto tap_state = [&](int tap) {
                 const int dt = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
                 okmask = 0;
 #pragma unroll
@@ -434,51 +437,52 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
                                     (unsigned)((c & 1023) + dx) < (unsigned)p.X;
                     okmask |= (ok ? 1u : 0u) << i;
                 }
-                src = p.x + (size_t)(v0 + (long long)dt * YX + (long long)dy * p.X + dx) * p.Cin + 4 * k4;
+                foff = (unsigned)((dt * p.Y + dy) * p.X + dx) * (unsigned)p.Cin;
             };
-            float4 a[4], an[4];
-            auto load = [&](float4* dst, int ch) {
+            int ftap = 0, fch = 0;
+            auto fetch = [&](float4* dst) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    dst[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(4 * i) * p.Cin + ch * kConvKC))
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dst[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.x + (roff[i] + foff))) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (++fch == KCH) { fch = 0; if (++ftap < 27) tap_state(ftap); } else foff += kConvKC;
             };
-            tap_setup(0);
-            load(a, 0);
-            int ntap = 0, nch = 0;
-            for (int it = 0; it < NIT; ++it, ++g) {
-                {
-                    const int tap = ntap, ch = nch;
-                    if (it + 1 < NIT) {
-                        if (++nch == KCH) { nch = 0; tap_setup(++ntap); }
-                        load(an, nch);
-                    }
-                    const unsigned s = g % kConvStages, use = g / kConvStages;
-                    conv_mbar_wait(bempty + 8u * s, (use & 1u) ^ 1u);
-                    unsigned char* st = conv_smem + (size_t)s * kC64Stage;
-                    if (tid == 0) {
-                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar0 + 8u * s), "r"((unsigned)kC64WBytes) : "memory");
-                        conv_bulk_load(s0 + (unsigned)(s * kC64Stage) + 2u * kC64BBytes,
-                                       reinterpret_cast<const unsigned char*>(p.wprep) + ((size_t)tap * KCH + ch) * kC64WBytes, (unsigned)kC64WBytes, bar0 + 8u * s);
-                    }
-                    unsigned char* bhi = st + (size_t)(k4 >> 1) * kC64LboB + (k4 & 1) * 8;
-                    unsigned char* blo = bhi + kC64BBytes;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int row = wrow0 + 4 * i + rsub;
-                        const unsigned off = (unsigned)(row >> 3) * 128u + (unsigned)(row & 7) * 16u;
-                        float4 x4 = a[i];
-                        if (p.relu_in) { x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f); }
-                        uint2 h2, l2;
-                        bf16_split4(x4, h2, l2);
-                        *reinterpret_cast<uint2*>(bhi + off) = h2;
-                        *reinterpret_cast<uint2*>(blo + off) = l2;
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar0 + 8u * s) : "memory");
+            const unsigned off0 = (unsigned)((wrow0 + rsub) >> 3) * 128u + (unsigned)(rsub & 7) * 16u;
+            auto stage = [&](int it, const float4* a) {
+                const unsigned s = g % kConvStages, use = g / kConvStages;
+                conv_mbar_wait(bempty + 8u * s, (use & 1u) ^ 1u);
+                unsigned char* st = conv_smem + (size_t)s * kC64Stage;
+                if (tid == 0) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar0 + 8u * s), "r"((unsigned)kC64WBytes) : "memory");
+                    conv_bulk_load(s0 + (unsigned)(s * kC64Stage) + 2u * kC64BBytes,
+                                   reinterpret_cast<const unsigned char*>(p.wprep) + (size_t)it * kC64WBytes, (unsigned)kC64WBytes, bar0 + 8u * s);
                 }
+                unsigned char* bhi = st + (size_t)(k4 >> 1) * kC64LboB + (k4 & 1) * 8;
+                unsigned char* blo = bhi + kC64BBytes;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = an[i];
+                for (int i = 0; i < 4; ++i) {
+                    const unsigned off = off0 + (unsigned)(i >> 1) * 128u + (unsigned)(i & 1) * 64u;
+                    float4 x4 = a[i];
+                    if (RELU) { x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f); }
+                    uint2 h2, l2;
+                    bf16_split4(x4, h2, l2);
+                    *reinterpret_cast<uint2*>(bhi + off) = h2;
+                    *reinterpret_cast<uint2*>(blo + off) = l2;
+                }
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar0 + 8u * s) : "memory");
+            };
+            float4 a0[4], a1[4];
+            tap_state(0);
+            fetch(a0);
+            for (int it = 0; it < NIT; it += 2) {
+                if (it + 1 < NIT) fetch(a1);
+                stage(it, a0);
+                ++g;
+                if (it + 1 < NIT) {
+                    if (it + 2 < NIT) fetch(a0);
+                    stage(it + 1, a1);
+                    ++g;
+                }
             }
             // ---- epilogue.  TMEM lane = (half, co): warp quarter q = warp & 3 holds co = 32 (q & 1) + lane of half q >> 1 (0: W_hi rows, 1: W_lo rows);
             // warps 4 g .. 4 g + 3 take voxel columns 64 g .. 64 g + 63.  The stage buffers are idle now and carry the lo halves.

@@ -76,7 +76,10 @@ int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* b
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long ntiles = (p.NV + kConvTileRows - 1) / kConvTileRows;
         const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-        return launch(conv3d_k3_c64_kernel, dim3(grid), dim3(kC64Threads), conv_c64_smem_bytes(), (stream_t)stream, p) == 0 ? DLSG_OK : DLSG_ELAUNCH;
+        if ((long long)p.NV * Cin > 0x7fffffffLL) return DLSG_EUNSUPPORTED;       // 32-bit element offsets
+        const int rc = p.relu_in ? launch(conv3d_k3_c64_kernel<true>, dim3(grid), dim3(kC64Threads), conv_c64_smem_bytes(), (stream_t)stream, p)
+                                 : launch(conv3d_k3_c64_kernel<false>, dim3(grid), dim3(kC64Threads), conv_c64_smem_bytes(), (stream_t)stream, p);
+        return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
     }
     return conv_launch(p, stream);
 #else
