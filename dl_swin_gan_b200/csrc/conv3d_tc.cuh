@@ -502,14 +502,17 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
                 asm volatile("bar.sync 1, 512;\n" ::: "memory");
                 if (half == 0) {
                     const long long vb = tile * kConvTileRows + colw + c0;
+                    if (p.resid) {                                            // all 32 skip-connection loads in flight together
+                        float rs[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) rs[j] = (vb + j < p.NV) ? __ldg(p.resid + (size_t)(vb + j) * Cout + cbase + lane) : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = fmaf(p.resid_scale, rs[j], acc[j]);
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const long long v = vb + j;
-                        if (v < p.NV) {
-                            float r = acc[j] + xb[j * 33 + lane] + bco;
-                            if (p.resid) r = fmaf(p.resid_scale, __ldg(p.resid + (size_t)v * Cout + cbase + lane), r);
-                            p.out[(size_t)v * Cout + cbase + lane] = r;
-                        }
+                        if (v < p.NV) p.out[(size_t)v * Cout + cbase + lane] = acc[j] + xb[j * 33 + lane] + bco;
                     }
                 }
                 asm volatile("bar.sync 1, 512;\n" ::: "memory");
