@@ -30,7 +30,10 @@ __global__ void __launch_bounds__(kFewThreads, 2) conv3d_k3_fewout_kernel(FewOut
     float* sw = reinterpret_cast<float*>(few_smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nw = 27 * p.Cin * CO;
+    int* sTapOff = reinterpret_cast<int*>(sw + nw);                          // voxel offset of each tap
+    unsigned char* sOk = reinterpret_cast<unsigned char*>(sTapOff + 28);      // [27][kFewThreads]
     for (int i = tid; i < nw / 4; i += kFewThreads) reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
+    if (tid < 27) sTapOff[tid] = ((tid / 9 - 1) * p.Y + ((tid / 3) % 3 - 1)) * p.X + (tid % 3 - 1);
     __syncthreads();
     const int KCH = p.Cin / 32;
     const int k4 = lane & 7, rsub = lane >> 3;
@@ -52,23 +55,32 @@ __global__ void __launch_bounds__(kFewThreads, 2) conv3d_k3_fewout_kernel(FewOut
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int c = 0; c < CO / 2; ++c) acc[i][c] = make_float2(0.f, 0.f);
+        // in-volume flags of this thread's 8 rows for each tap, kept in shared memory (one byte per tap and thread)
         for (int tap = 0; tap < 27; ++tap) {
             const int dt = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
-            unsigned okmask = 0;
+            unsigned m = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int c = coord[i];
                 const bool ok = c >= 0 && (unsigned)((c >> 20) + dt) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + dy) < (unsigned)p.Y &&
                                 (unsigned)((c & 1023) + dx) < (unsigned)p.X;
-                okmask |= (ok ? 1u : 0u) << i;
+                m |= (ok ? 1u : 0u) << i;
             }
-            const float* src = p.x + (size_t)(v0 + (long long)dt * YX + (long long)dy * p.X + dx) * p.Cin + 4 * k4;
-            const float* wt = sw + ((size_t)tap * p.Cin + 4 * k4) * CO;
-            for (int ch = 0; ch < KCH; ++ch) {
+            sOk[tap * kFewThreads + tid] = (unsigned char)m;
+        }
+        // channel chunk outermost, taps inside: the three dx taps of a (dt, dy) pair read the same lines one voxel apart, so two of the
+        // three come from L1 (with the taps outermost each of the 27 passes over the input came from L2: ~10 TB/s, L2-bound)
+        const unsigned rbase = (unsigned)v0 * (unsigned)p.Cin + 4u * k4;
+        for (int ch = 0; ch < KCH; ++ch) {
+#pragma unroll 1
+            for (int tap = 0; tap < 27; ++tap) {
+                const unsigned okmask = sOk[tap * kFewThreads + tid];
+                const unsigned soff = rbase + (unsigned)(sTapOff[tap] * p.Cin + ch * 32);      // 32-bit on purpose: a row's offset wraps back into range
+                const float* wt = sw + ((size_t)tap * p.Cin + ch * 32 + 4 * k4) * CO;
                 float4 a[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    a[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(4 * i) * p.Cin + ch * 32))
+                    a[i] = ((okmask >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.x + (soff + (unsigned)(4 * i) * (unsigned)p.Cin)))
                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                     if (p.relu_in) { a[i].x = fmaxf(a[i].x, 0.f); a[i].y = fmaxf(a[i].y, 0.f); a[i].z = fmaxf(a[i].z, 0.f); a[i].w = fmaxf(a[i].w, 0.f); }
                 }
@@ -76,7 +88,7 @@ __global__ void __launch_bounds__(kFewThreads, 2) conv3d_k3_fewout_kernel(FewOut
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int c = 0; c < CO / 2; ++c) wq[j][c] = *reinterpret_cast<const float2*>(wt + (size_t)(ch * 32 + j) * CO + 2 * c);
+                    for (int c = 0; c < CO / 2; ++c) wq[j][c] = *reinterpret_cast<const float2*>(wt + (size_t)j * CO + 2 * c);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll

@@ -127,8 +127,8 @@ int dlsg_conv3d_k3_fewout_f32(const float* x, const float* w_tcc, const float* b
     using namespace dlsg;
     if (!x || !w_tcc || !out || NB <= 0 || T <= 0 || Y <= 0 || X <= 0) return DLSG_EINVAL;
     if ((Cout != 2 && Cout != 4) || Cin <= 0 || Cin % 32 != 0 || X > 1023 || Y > 1023 || T > 2047) return DLSG_EUNSUPPORTED;
-    const size_t smem = (size_t)27 * Cin * Cout * 4;
-    if (smem > 100 * 1024) return DLSG_EUNSUPPORTED;                  // two CTAs per SM
+    const size_t smem = (size_t)27 * Cin * Cout * 4 + 28 * 4 + 27 * dlsg::kFewThreads;
+    if (smem > 110 * 1024 || (long long)NB * T * Y * X * Cin > 0x7fffffffLL) return DLSG_EUNSUPPORTED;   // two CTAs per SM; 32-bit element offsets
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_tcc) | reinterpret_cast<uintptr_t>(out)) & 15) return DLSG_EINVAL;
     FewOutParams p{};
     p.x = x; p.w = w_tcc; p.bias = bias; p.out = out;
