@@ -303,7 +303,8 @@ def swin_block_timing(dev, tensor_peak, slices=8):
 
 def conv_kernel_timing(dev, tensor_peak_bf16):
     """The denoiser's dominant layer (Conv3d 160 -> 160, 3x3x3, one cine slice incl. the circular time padding) on the repo's
-    tensor-core kernel against one cuDNN TF32 pass; useful = 2*27*Cin*Cout*voxels, the kernel issues three times that (3xTF32)."""
+    tensor-core kernel against one cuDNN TF32 pass; useful = 2*27*Cin*Cout*voxels, the kernel issues three times that (three bf16
+    products on split operands)."""
     from dl_swin_gan_b200.models.conv3d import conv3d_k3
     c, t, y, x = 160, 28, 192, 160
     inp = torch.randn(1, c, t, y, x, device=dev).contiguous(memory_format=torch.channels_last_3d)
@@ -317,18 +318,16 @@ def conv_kernel_timing(dev, tensor_peak_bf16):
         torch.backends.cudnn.allow_tf32 = True
         ms_c = time_op(lambda: torch.nn.functional.conv3d(inp, wc, b, padding=1), 5, dev)
         torch.backends.cudnn.allow_tf32 = keep
-    burst = tensor_peak_bf16
+    peak = tensor_peak_bf16
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            burst = float(json.load(f).get("bf16_tflops", tensor_peak_bf16))
-    peak = burst / 2.0                   # the kernel is timed alone (five launches): the burst figure applies
-    return {"what": "Conv3d 160->160 3x3x3 'same', [1,160,28,192,160] channels-last, 3xTF32 in one tcgen05 kernel", "ms": ms,
+            peak = float(json.load(f).get("bf16_tflops", tensor_peak_bf16))     # timed alone (five launches): the burst figure applies
+    return {"what": "Conv3d 160->160 3x3x3 'same', [1,160,28,192,160] channels-last, split operands (bf16 head + bf16 remainder, 3 products) in one tcgen05 kernel", "ms": ms,
             "useful_tflops": flop / ms / 1e9, "issued_tflops": 3 * flop / ms / 1e9,
             "cudnn_tf32_one_pass_ms": ms_c, "cudnn_three_passes_ms": 3 * ms_c,
             "roofline": {"bound": "tensor", "achieved": 3 * flop / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": 3 * flop / ms / 1e9 / peak,
-                         "note": "issued TF32 tensor work over half the measured burst bf16 rate (TF32 runs at half the bf16 rate; "
-                                 "MEASURED_PEAKS.json holds no TF32 figure; kernel timed alone)"}}
+                         "note": "issued bf16 tensor work (3 x useful) over the measured burst bf16 rate (kernel timed alone)"}}
 
 
 def _lib_launches():
@@ -421,11 +420,11 @@ def full_recon_timing(workload, dev, rank, batch=None, iters=3, precisions=("tf3
                          "denoiser_share": cfg["unrolls"] * t_den / t_all}
         _layers._TC_CONV = True
     set_conv_precision(keep)
-    out["note"] = ("conv precision tf32x3 (default) = 3xTF32: operands split into a TF32 head and the remainder, three tensor-core products, "
-                   "fp32-level accuracy (the whole reconstruction stays within 1e-3 NRMSE of the fp32 reference, tests/test_models.py) - run by "
-                   "the repo's own tcgen05 implicit-GEMM kernels (csrc/conv3d_tc.cuh: 3x3x3, first layer, patch embed / unembed; last layer on "
-                   "the CUDA cores, csrc/conv3d_fewout.cuh); tf32x3_cudnn = the same arithmetic as three cuDNN convolutions per layer around "
-                   "elementwise passes; tf32 = cuDNN default (what the reference itself runs on a GPU; 1.2e-3 NRMSE after 5 Swin unrolls); "
+    out["note"] = ("conv precision tf32x3 (default) = three split products: operands split into a short-mantissa head and the remainder, three "
+                   "tensor-core products, ~1e-5 per layer (the whole reconstruction stays within 1e-3 NRMSE of the fp32 reference, "
+                   "tests/test_models.py) - run by the repo's own tcgen05 implicit-GEMM kernels (csrc/conv3d_tc.cuh: bf16 pieces; 3x3x3, first "
+                   "layer, patch embed / unembed, ReLU and skip connections fused; last layer on the CUDA cores, csrc/conv3d_fewout.cuh); "
+                   "tf32x3_cudnn = the same scheme as three cuDNN TF32 convolutions per layer around elementwise passes; tf32 = cuDNN default (what the reference itself runs on a GPU; 1.2e-3 NRMSE after 5 Swin unrolls); "
                    "bf16 = cuDNN under autocast (1e-2)")
     return out
 

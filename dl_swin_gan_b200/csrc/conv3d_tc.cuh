@@ -1,21 +1,29 @@
-// 3 x 3 x 3 convolution of the denoisers (nn.Conv3d with 'same' zero padding: dl_cs/models/swin3D.py:120-134,
-// the 160 -> 160 / 64 -> 64 layers of ConvBlock :225-273) as an implicit GEMM on the 5th-generation tensor cores,
-// channels-last, with the 3xTF32 operand split fused into the operand staging:
+// Convolutions of the denoisers (nn.Conv3d with 'same' zero padding: dl_cs/models/swin3D.py:120-134, the 160 -> 160 / 64 -> 64
+// layers of ConvBlock :225-273; PatchEmbed3D / PatchUnembed3D of video_swin_transformer_mri_downsample.py:455-520) as implicit
+// GEMMs on the 5th-generation tensor cores, channels-last, with the operand split fused into the operand staging:
 //
 //     out[v, co] = bias[co] + sum_{tap, ci} x[v + tap, ci] * w[co, ci, tap]          v = (n, t, y, x) voxel
-//                = sum (x_hi * w_hi + x_lo * w_hi + x_hi * w_lo),   a = a_hi + a_lo,  a_hi = a rounded to TF32
+//                = sum (x_hi * w_hi + x_lo * w_hi + x_hi * w_lo),   a = a_hi + a_lo + O(2^-18 a),  a_hi = bf16(a),  a_lo = bf16(a - a_hi)
+//
+// i.e. the "3x" scheme of models.set_conv_precision("tf32x3") on 16-bit pieces: 16 mantissa bits per operand, fp32 accumulation,
+// 1e-5 relative on a layer's output - the level the tensor core's own accumulator leaves at K = 27 * 160 - where one TF32 pass
+// gives 5e-4.  bf16 pieces instead of TF32 ones because the kernel is bound by shared-memory wavefronts (operand reads of the
+// MMAs + the producers' stores share one 128 B/clk pipe; ncu, profiles/r2r_conv_*): 2-byte operands halve both and run at twice
+// the MMA rate (first version, TF32 pieces: 4.33 ms for the 160 -> 160 layer of one cine slice; this one: 2.87 ms).
 //
 // One persistent CTA per SM owns 256 consecutive voxels per tile = two 128-row accumulators [128 x Cout] fp32 in tensor
-// memory.  The K loop walks 27 taps x Cin/32 channel chunks through a two-stage shared-memory ring:
-//   * 8 producer warps (one thread per voxel) read the 32 input channels of the shifted voxel (one 128-byte line; zeros
-//     outside the volume), split them into the TF32 head and the remainder, and store both in the canonical no-swizzle
-//     K-major UMMA layout ([k/4][row/8][8 rows][4 floats]);
+// memory.  The K loop walks taps x Cin/32 channel chunks through a four-stage shared-memory ring:
+//   * 16 producer warps read the 32 input channels of the shifted voxels (8 lanes per 128-byte line, coalesced; zeros outside the
+//     volume; loads issued one iteration ahead), split them into the bf16 head and remainder, and store both in the canonical
+//     no-swizzle K-major UMMA layout ([k/8][row/8][8 rows][8 bf16], planes padded by 32 bytes against bank conflicts);
 //   * the weights arrive already split and already in that layout (prepared once per weight version on the host side)
 //     by one bulk copy per stage (cp.async.bulk, completion counted on the stage's mbarrier);
-//   * one thread issues 24 tcgen05.mma.kind::tf32 per stage (2 tiles x 4 k-steps x 3 products) and commits the stage
-//     back to the producers.
-// After the last stage the producer warps drain the accumulators (tcgen05.ld), add the bias and store channels-last rows.
-// CUDA-only: tcgen05 / TMEM have no host emulation (validated on the B200 against torch, tests/test_conv_gpu.py).
+//   * one thread issues 12 tcgen05.mma.kind::f16 (bf16 operands) per stage (2 tiles x 2 k-steps x 3 products) and commits the
+//     stage back to the producers.
+// After the last stage the producer warps drain the accumulators (tcgen05.ld), add the bias and the optional skip connection and
+// store channels-last rows.  The same kernel serves the first layer (Cin = 2 / 4, K gathered over taps), the patch embedding
+// (kernel = stride) and the transposed patch unembedding; Cout = 64 has an operand-swapped variant (below).
+// CUDA-only: tcgen05 / TMEM have no host emulation (validated on the B200 against fp64 torch, tests/test_conv_gpu.py).
 #pragma once
 
 #include "cuda_compat.h"
@@ -36,7 +44,7 @@ constexpr int kConvABytes = (kConvKC / 8) * kConvLboA;   // one [128 x 32] bf16 
 enum : int { CONV_GATHER = 0, CONV_UNPATCH = 1 };
 struct ConvParams {
     const float* x;        // [NB, T, Y, X, Cin]          (input volume)
-    const float* wprep;    // [taps][Cin/32][hi|lo][8][Cout/8][8][4]
+    const float* wprep;    // bf16 image [taps][Cin/32][hi|lo][4][Cout/8][8][8] (include/dlsg_b200.h)
     const float* bias;     // [Cout] or NULL
     float* out;            // [NB, To, Yo, Xo, Cout]
     int NB, T, Y, X, Cin, Cout;
@@ -355,11 +363,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
 
 // =====================================================================================================================
 // Cout = 64 (the ResNet denoiser's 64 -> 64 layers, dl_cs/models/resnet3d.py:243-317; configs/config_recon.yaml): with 64 output
-// channels the kernel above spends its time re-reading the 4 KB activation block for every N = 64 instruction (tensor pipe
+// channels the kernel above spends its time re-reading the activation block for every N = 64 instruction (tensor pipe
 // 35 % active).  Here the operands swap roles: the MMA's A operand is the weight block [W_hi; W_lo] (2 x 64 = 128 rows) and the
 // 256 voxels of the tile are its N dimension,
 //     D[128 x 256] += [W_hi; W_lo](128 x 8) * X_hi^T(8 x 256)  and  ... * X_lo^T,
-// two N = 256 instructions per k-step: rows 0-63 collect W_hi X_hi + W_hi X_lo, rows 64-127 W_lo X_hi + W_lo X_lo, and
+// two N = 256 instructions per k-step (all four products): rows 0-63 collect W_hi X_hi + W_hi X_lo, rows 64-127 W_lo X_hi + W_lo X_lo, and
 // out[v, co] = D[co, v] + D[64 + co, v] + bias.  The epilogue reads the accumulator one output channel per thread and 32 voxels
 // per load, the lo half goes through shared memory to the warp that holds the hi half, and each store writes one voxel's 32
 // channels (128 bytes, coalesced).

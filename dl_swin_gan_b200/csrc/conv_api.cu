@@ -55,11 +55,11 @@ static int conv_launch(dlsg::ConvParams& p, void* stream) {
 }
 #endif
 
-int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* bias, const float* resid, float resid_scale, float* out,
+int dlsg_conv3d_k3_tf32x3_f32(const float* x, const void* wprep, const float* bias, const float* resid, float resid_scale, float* out,
                               int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream) {
 #if defined(__CUDACC__)
     dlsg::ConvParams p{};
-    p.x = x; p.wprep = wprep; p.bias = bias; p.out = out;
+    p.x = x; p.wprep = static_cast<const float*>(wprep); p.bias = bias; p.out = out;
     p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin; p.Cout = Cout;
     p.To = T; p.Yo = Y; p.Xo = X; p.ksz = 3; p.stride = 1; p.pad = 1; p.mode = dlsg::CONV_GATHER;
     p.NV = (long long)NB * T * Y * X;
@@ -88,13 +88,13 @@ int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* b
 #endif
 }
 
-int dlsg_conv3d_patch_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
+int dlsg_conv3d_patch_tf32x3_f32(const float* x, const void* wprep, const float* bias, float* out,
                                  int NB, int T, int Y, int X, int Cin, int Cout, int patch, void* stream) {
 #if defined(__CUDACC__)
     if (patch < 1 || patch > 8 || Cin % dlsg::kConvKC != 0) return DLSG_EUNSUPPORTED;
     if (T % patch || Y % patch || X % patch) return DLSG_EINVAL;
     dlsg::ConvParams p{};
-    p.x = x; p.wprep = wprep; p.bias = bias; p.out = out;
+    p.x = x; p.wprep = static_cast<const float*>(wprep); p.bias = bias; p.out = out;
     p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin; p.Cout = Cout;
     p.To = T / patch; p.Yo = Y / patch; p.Xo = X / patch; p.ksz = patch; p.stride = patch; p.pad = 0; p.mode = dlsg::CONV_GATHER;
     p.NV = (long long)NB * p.To * p.Yo * p.Xo;
@@ -105,12 +105,12 @@ int dlsg_conv3d_patch_tf32x3_f32(const float* x, const float* wprep, const float
 #endif
 }
 
-int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
+int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const void* wprep, const float* bias, float* out,
                                    int NB, int T, int Y, int X, int Cin, int Cout, int patch, void* stream) {
 #if defined(__CUDACC__)
     if (patch < 1 || patch > 8 || Cin % dlsg::kConvKC != 0) return DLSG_EUNSUPPORTED;
     dlsg::ConvParams p{};
-    p.x = x; p.wprep = wprep; p.bias = bias; p.out = out;
+    p.x = x; p.wprep = static_cast<const float*>(wprep); p.bias = bias; p.out = out;
     p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin; p.Cout = Cout;
     p.To = T * patch; p.Yo = Y * patch; p.Xo = X * patch; p.ksz = patch; p.stride = patch; p.pad = 0; p.mode = dlsg::CONV_UNPATCH;
     p.NV = (long long)NB * T * Y * X;

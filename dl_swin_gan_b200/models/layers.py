@@ -17,14 +17,19 @@ _CONV_MODES = ("tf32x3", "tf32x2", "tf32r", "fp32", "tf32", "bf16")
 
 def set_conv_precision(mode: str) -> None:
     """Arithmetic of the denoiser convolutions on CUDA tensors (storage stays fp32):
-    "tf32x3"  the default: every operand is split into a TF32-representable head and the remainder, and the convolution is
-              the sum of three tensor-core (TF32) convolutions  conv(x_hi, w_hi) + conv(x_lo, w_hi) + conv(x_hi, w_lo)  with fp32
-              accumulation - fp32-level accuracy (the dropped lo*lo term is ~2^-22 relative) at a third of the TF32 rate, which on
-              the B200 is ~9x faster than cuDNN's true-fp32 3-D convolutions.  Keeps a full reconstruction within the 1e-3 NRMSE
-              bar of the fp32 reference (tests/test_models.py);
+    "tf32x3"  the default, "three split products": every operand is split into a short-mantissa head and the remainder and the
+              convolution is  conv(x_hi, w_hi) + conv(x_lo, w_hi) + conv(x_hi, w_lo)  with fp32 accumulation.  At inference the layers
+              the denoisers have (3x3x3 'same', first / last layer, patch embed / unembed) run on the repo's own tensor-core kernels
+              (models/conv3d.py, csrc/conv3d_tc.cuh: bf16 head + bf16 remainder, 16 mantissa bits, ~1e-5 per layer, ONE pass over the
+              activations with the split, the pre-activation ReLU and the skip connection fused); anything else, and training, takes
+              three cuDNN TF32 convolutions on TF32 head / remainder (~1e-6, three passes + elementwise kernels).  Keeps a full
+              reconstruction within the 1e-3 NRMSE bar of the fp32 reference (tests/test_models.py: 5.1e-4 for five Swin unrolls, of
+              which the fp16 attention linears are the larger part);
+    "tf32x2" / "tf32r"   two split products / one product on operands rounded to TF32: measured 1.07e-3 / 1.26e-3 on the five-unroll
+              Swin fixture, i.e. outside the bar - kept for the precision probe (tools/model_precision_probe.py);
     "fp32"    cuDNN with TF32 switched off (IEEE fp32 FMAs; slow: no tensor cores);
     "tf32"    cuDNN's default for fp32 tensors, which is also what the reference itself runs on a GPU with PyTorch's defaults:
-              1.2e-3 NRMSE against the fp32 result after five unrolls of the Swin network (measured, tools/model_precision_probe.py);
+              1.2e-3 NRMSE against the fp32 result after five unrolls of the Swin network;
     "bf16"    autocast to bfloat16 (about 1e-2)."""
     global _CONV_PRECISION
     if mode not in _CONV_MODES:

@@ -266,37 +266,43 @@ int dlsg_sliding_window_c64(const void* data, void* out, long long outer, int T,
                             int keep_all_frames, float mask_eps, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Denoiser convolutions: nn.Conv3d(kernel 3, stride 1, 'same' zero padding) of ConvBlock
- * (dl_cs/models/swin3D.py:120-134, 225-273 == resnet3d.py), fp32 storage, channels-last.
+ * Denoiser convolutions: the layers of ConvBlock / PatchEmbed3D / PatchUnembed3D
+ * (dl_cs/models/swin3D.py:120-134, 225-273 == resnet3d.py; video_swin_transformer_mri_downsample.py:455-520), fp32 storage,
+ * channels-last, as implicit GEMMs on the tcgen05 tensor cores with split operands: every fp32 operand is a bf16 head (round to
+ * nearest) plus a bf16 remainder, and a product is the three (Cout = 64: four) tensor-core products hi*hi + lo*hi + hi*lo with fp32
+ * accumulation - 16 mantissa bits per operand, 1e-5 relative on a layer's output (one TF32 pass: 5e-4).  The entry points keep the
+ * "tf32x3" of the precision mode they implement (models.set_conv_precision) in their names.
  * ------------------------------------------------------------------------------------------------ */
 
 /* K elements per pipeline stage (32) when the tensor-core kernel takes this channel pair (Cin % 32 == 0 or Cin in {2, 4}; Cout % 32 == 0;
- * shared memory), else 0. */
+ * shared memory), else 0.  Bit 0x100 is set when the 3x3x3 layer runs on the operand-swapped kernel (Cout = 64), whose weight image
+ * stacks heads and remainders as rows (see below). */
 int dlsg_conv3d_k3_supported(int Cin, int Cout);
 
 /* out[n,t,y,x,:] = bias + sum over the 27 taps and Cin of x[n,t+dt,y+dy,x+dx,ci] * weight[co,ci,dt+1,dy+1,dx+1]  (cross-correlation,
- * zeros outside the volume), computed as three TF32 tensor-core products on operands split into a TF32 head and the remainder
- * (fp32-level accuracy).  x [NB,T,Y,X,Cin] and out [NB,T,Y,X,Cout] are channels-last (torch.channels_last_3d of [NB,C,T,Y,X]).
- * wprep is the weight split and laid out for the kernel, prepared once per weight version by the caller:
- *   wprep[tap][ci/32][h][(ci%32)/4][co/8][co%8][ci%4],  h = 0: TF32 head of weight[co,ci,tap], h = 1: remainder,  tap = (dt+1)*9+(dy+1)*3+(dx+1);
- *   for the first layer of a denoiser (Cin = 2 or 4) K runs over k = tap*Cin + ci, zero-padded to a multiple of 32:
- *   wprep[k/32][h][(k%32)/4][co/8][co%8][k%4].
+ * zeros outside the volume).  x [NB,T,Y,X,Cin] and out [NB,T,Y,X,Cout] are channels-last (torch.channels_last_3d of [NB,C,T,Y,X]).
+ * wprep is the bf16 weight image the kernel stages with one bulk copy per pipeline stage, prepared once per weight version by the caller
+ * (h = 0: bf16 head of weight[co,ci,tap], h = 1: bf16 of the remainder; tap = (dt+1)*9+(dy+1)*3+(dx+1)):
+ *   Cin % 32 == 0:            wprep[tap][ci/32][h][(ci%32)/8][co/8][co%8][ci%8]
+ *   stacked (code & 0x100):   wprep[tap][ci/32][(ci%32)/8][h][co/8][co%8][ci%8]
+ *   Cin = 2 or 4 (first layer of a denoiser), K index k = tap*Cin + ci zero-padded to a multiple of 32:
+ *                             wprep[k/32][h][(k%32)/8][co/8][co%8][k%8]
  * relu_in != 0 rectifies x on the fly (ConvBlock's pre-activation, :262-268).  resid (NULL or [NB,T,Y,X,Cout]) is a skip connection added
  * in the epilogue: out = conv + bias + resid_scale * resid (ResBlock :300, ResSwinTransformer3DBlock :340, DeepFeatureExtraction :369).
- * bias may be NULL. */
-int dlsg_conv3d_k3_tf32x3_f32(const float* x, const float* wprep, const float* bias, const float* resid, float resid_scale, float* out,
+ * bias may be NULL.  NB*T*Y*X*Cin < 2^31. */
+int dlsg_conv3d_k3_tf32x3_f32(const float* x, const void* wprep, const float* bias, const float* resid, float resid_scale, float* out,
                               int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream);
 
 /* PatchEmbed3D.proj (dl_cs/models/video_swin_transformer_mri_downsample.py:455-476): nn.Conv3d(kernel = stride = patch, no padding) on
- * the same kernel.  x [NB,T,Y,X,Cin] (T, Y, X multiples of patch) -> out [NB,T/patch,Y/patch,X/patch,Cout]; wprep as above with
+ * the same kernel.  x [NB,T,Y,X,Cin] (T, Y, X multiples of patch) -> out [NB,T/patch,Y/patch,X/patch,Cout]; wprep as above (first form) with
  * patch^3 taps, tap = (dt*patch + dy)*patch + dx.  Cin % 32 == 0. */
-int dlsg_conv3d_patch_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
+int dlsg_conv3d_patch_tf32x3_f32(const float* x, const void* wprep, const float* bias, float* out,
                                  int NB, int T, int Y, int X, int Cin, int Cout, int patch, void* stream);
 
 /* PatchUnembed3D.proj (:503-520): nn.ConvTranspose3d(kernel = stride = patch): out[n, t*patch+dt, y*patch+dy, x*patch+dx, :] =
  * bias + W_tap x[n,t,y,x,:].  x [NB,T,Y,X,Cin] -> out [NB,T*patch,Y*patch,X*patch,Cout]; wprep as above built from
  * weight[ci,co,dt,dy,dx] transposed to [co,ci,...].  Cin % 32 == 0. */
-int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const float* wprep, const float* bias, float* out,
+int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const void* wprep, const float* bias, float* out,
                                    int NB, int T, int Y, int X, int Cin, int Cout, int patch, void* stream);
 
 /* The denoisers' last layer (final_layer, dl_cs/models/swin3D.py:395): 3 x 3 x 3 'same' convolution down to Cout = 2 or 4 channels in
