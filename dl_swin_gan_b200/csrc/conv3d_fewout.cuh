@@ -130,5 +130,38 @@ __global__ void __launch_bounds__(kFewThreads, 2) conv3d_k3_fewout_kernel(FewOut
     }
 }
 
+// Second form of the last layer: z[v, tap*CO + co] = sum_ci w[co, ci, tap] * x[v, ci] is a pointwise 160 -> 27*CO linear (one pass over the
+// input on the tensor-core kernel, conv3d_tc.cuh with a single tap), and the convolution is the sum of z over the 27 shifted voxels:
+//     out[v, co] = bias[co] + sum_{tap: v + tap inside the volume} z[v + tap, tap*CO + co]
+// Every element of z is read once.  Thread = voxel; ZC = channel stride of z (>= 27*CO, padded to the GEMM's tile).
+template <int CO>
+__global__ void __launch_bounds__(256) conv3d_tapsum_kernel(const float* __restrict__ z, const float* __restrict__ bias, float* __restrict__ out,
+                                                           int T, int Y, int X, int ZC, long long NV) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= NV) return;
+    const long long YX = (long long)Y * X;
+    const long long r1 = v % YX;
+    const int vx = (int)(r1 % X), vy = (int)(r1 / X), vt = (int)((v / YX) % T);
+    float acc[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 27; ++tap) {
+        const int dt = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
+        if ((unsigned)(vt + dt) < (unsigned)T && (unsigned)(vy + dy) < (unsigned)Y && (unsigned)(vx + dx) < (unsigned)X) {
+            const float* q = z + (size_t)(v + (long long)dt * YX + (long long)dy * X + dx) * ZC + tap * CO;
+            if (CO == 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(q));
+                acc[0] += a.x; acc[1] += a.y; acc[2 % CO] += a.z; acc[3 % CO] += a.w;
+            } else {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(q));
+                acc[0] += a.x; acc[1] += a.y;
+            }
+        }
+    }
+    if (CO == 4) *reinterpret_cast<float4*>(out + (size_t)v * 4) = make_float4(acc[0], acc[1], acc[2 % CO], acc[3 % CO]);
+    else *reinterpret_cast<float2*>(out + (size_t)v * 2) = make_float2(acc[0], acc[1]);
+}
+
 }  // namespace dlsg
 #endif

@@ -121,6 +121,40 @@ int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const void* wprep, const floa
 #endif
 }
 
+int dlsg_conv3d_pointwise_tf32x3_f32(const float* x, const void* wprep, const float* bias, float* out,
+                                     int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream) {
+#if defined(__CUDACC__)
+    if (Cin % dlsg::kConvKC != 0) return DLSG_EUNSUPPORTED;
+    dlsg::ConvParams p{};
+    p.x = x; p.wprep = static_cast<const float*>(wprep); p.bias = bias; p.out = out;
+    p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin; p.Cout = Cout;
+    p.To = T; p.Yo = Y; p.Xo = X; p.ksz = 1; p.stride = 1; p.pad = 0; p.mode = dlsg::CONV_GATHER;
+    p.NV = (long long)NB * T * Y * X;
+    p.relu_in = relu_in ? 1 : 0;
+    return conv_launch(p, stream);
+#else
+    (void)x; (void)wprep; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)relu_in; (void)stream;
+    return DLSG_EUNSUPPORTED;
+#endif
+}
+
+int dlsg_conv3d_tapsum_f32(const float* z, const float* bias, float* out, int NB, int T, int Y, int X, int ZC, int Cout, void* stream) {
+#if defined(__CUDACC__)
+    using namespace dlsg;
+    if (!z || !out || NB <= 0 || T <= 0 || Y <= 0 || X <= 0) return DLSG_EINVAL;
+    if ((Cout != 2 && Cout != 4) || ZC < 27 * Cout || ZC % 4 != 0) return DLSG_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) & 15) return DLSG_EINVAL;
+    const long long NV = (long long)NB * T * Y * X;
+    const unsigned grid = (unsigned)((NV + 255) / 256);
+    const int rc = Cout == 2 ? launch(conv3d_tapsum_kernel<2>, dim3(grid), dim3(256), 0, (stream_t)stream, z, bias, out, T, Y, X, ZC, NV)
+                             : launch(conv3d_tapsum_kernel<4>, dim3(grid), dim3(256), 0, (stream_t)stream, z, bias, out, T, Y, X, ZC, NV);
+    return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
+#else
+    (void)z; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)ZC; (void)Cout; (void)stream;
+    return DLSG_EUNSUPPORTED;
+#endif
+}
+
 int dlsg_conv3d_k3_fewout_f32(const float* x, const float* w_tcc, const float* bias, float* out,
                               int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream) {
 #if defined(__CUDACC__)

@@ -13,6 +13,7 @@ import torch
 from .. import _lib
 
 K3, PATCH, UNPATCH, FEWOUT = "k3", "patch", "unpatch", "fewout"
+_FEWOUT_GEMM = True       # last layer as pointwise GEMM + tap sum (False: the direct CUDA-core kernel)
 
 
 def _split(t: torch.Tensor):
@@ -174,12 +175,49 @@ def conv3d_k3_fewout(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: 
     return out.permute(0, 4, 1, 2, 3)
 
 
+def conv3d_k3_fewout_gemm(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: bool = False) -> torch.Tensor:
+    """The last layer (Cout = 2 or 4) as a pointwise tensor-core GEMM to 27*Cout tap channels followed by the sum over the 27 shifted
+    voxels (csrc/conv3d_fewout.cuh): two passes, each reading its input once, instead of 27 passes over the activations."""
+    lib = _lib.load()
+    nb, cin, t, y, xx = x.shape
+    cout = weight.shape[0]
+    zc = -(-27 * cout // 32) * 32
+    xc = x.permute(0, 2, 3, 4, 1)
+    if not xc.is_contiguous():
+        xc = xc.contiguous()
+    try:
+        tag = (weight._version, weight.data_ptr())
+    except RuntimeError:
+        tag = None
+    hit = getattr(weight, "_dlsg_conv_tapimage", None)
+    if hit is not None and tag is not None and hit[0] == tag:
+        prep = hit[1]
+    else:
+        wz = torch.zeros(zc, cin, 1, 1, 1, device=weight.device, dtype=torch.float32)
+        wz[:27 * cout, :, 0, 0, 0] = weight.detach().float().reshape(cout, cin, 27).permute(2, 0, 1).reshape(27 * cout, cin)   # row = tap*Cout + co
+        prep = prepare_weight(wz, lib.dlsg_conv3d_k3_supported(cin, zc) & 0xff)
+        try:
+            weight._dlsg_conv_tapimage = (tag, prep)
+        except AttributeError:
+            pass
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    z = torch.empty((nb, t, y, xx, zc), device=x.device, dtype=torch.float32)
+    _lib.check(lib.dlsg_conv3d_pointwise_tf32x3_f32(xc.data_ptr(), prep.data_ptr(), None, z.data_ptr(), nb, t, y, xx, cin, zc, int(relu_in), stream),
+               "dlsg_conv3d_pointwise_tf32x3_f32")
+    out = torch.empty((nb, t, y, xx, cout), device=x.device, dtype=torch.float32)
+    b = bias.detach().float().contiguous() if bias is not None else None
+    _lib.check(lib.dlsg_conv3d_tapsum_f32(z.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(), nb, t, y, xx, zc, cout, stream),
+               "dlsg_conv3d_tapsum_f32")
+    return out.permute(0, 4, 1, 2, 3)
+
+
 def forward(conv: torch.nn.Module, x: torch.Tensor, which: str, relu_in: bool = False, residual=None, residual_scale: float = 1.0) -> torch.Tensor:
     """`conv(relu?(x)) (+ residual_scale * residual)` on the kernel `kind()` chose; what a kernel cannot fuse is done around it."""
     if which == K3:
         return conv3d_k3(x, conv.weight, conv.bias, relu_in, residual, residual_scale)
     if which == FEWOUT:
-        out = conv3d_k3_fewout(x, conv.weight, conv.bias, relu_in)
+        gemm = _FEWOUT_GEMM and bool(_lib.load().dlsg_conv3d_k3_supported(conv.in_channels, -(-27 * conv.out_channels // 32) * 32))
+        out = (conv3d_k3_fewout_gemm if gemm else conv3d_k3_fewout)(x, conv.weight, conv.bias, relu_in)
     else:
         if relu_in:
             x = torch.relu(x)

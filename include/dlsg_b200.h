@@ -305,7 +305,15 @@ int dlsg_conv3d_patch_tf32x3_f32(const float* x, const void* wprep, const float*
 int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const void* wprep, const float* bias, float* out,
                                    int NB, int T, int Y, int X, int Cin, int Cout, int patch, void* stream);
 
-/* The denoisers' last layer (final_layer, dl_cs/models/swin3D.py:395): 3 x 3 x 3 'same' convolution down to Cout = 2 or 4 channels in
+/* The denoisers' last layer (final_layer, dl_cs/models/swin3D.py:395) in two steps, each one pass over its input:
+ *   z[v, tap*Cout + co] = sum_ci weight[co,ci,tap] * relu?(x[v,ci])       dlsg_conv3d_pointwise_tf32x3_f32 (the tensor-core kernel with one tap;
+ *                                                                         its "Cout" is the padded 27*Cout, wprep the image of that [ZC, Cin] matrix)
+ *   out[v, co] = bias[co] + sum over the taps inside the volume of z[v + tap, tap*Cout + co]      dlsg_conv3d_tapsum_f32 (ZC = channel stride of z) */
+int dlsg_conv3d_pointwise_tf32x3_f32(const float* x, const void* wprep, const float* bias, float* out,
+                                     int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream);
+int dlsg_conv3d_tapsum_f32(const float* z, const float* bias, float* out, int NB, int T, int Y, int X, int ZC, int Cout, void* stream);
+
+/* The same layer as ONE direct kernel: 3 x 3 x 3 'same' convolution down to Cout = 2 or 4 channels in
  * exact fp32 on the CUDA cores (packed FMAs).  x, out channels-last as above; w_tcc[tap][ci][co] = weight[co,ci,tap].  Cin % 32 == 0. */
 int dlsg_conv3d_k3_fewout_f32(const float* x, const float* w_tcc, const float* bias, float* out,
                               int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream);

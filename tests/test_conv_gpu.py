@@ -63,7 +63,7 @@ def test_patch_embed_and_unembed_match_fp64(case):
 
 @pytest.mark.parametrize("case", [(1, 160, 4, 3, 9, 20), (2, 64, 2, 4, 7, 13), (1, 32, 4, 1, 1, 3)])
 def test_last_layer_kernel_matches_fp64(case):
-    from dl_swin_gan_b200.models.conv3d import conv3d_k3_fewout
+    from dl_swin_gan_b200.models.conv3d import conv3d_k3_fewout, conv3d_k3_fewout_gemm
     nb, cin, cout, t, y, x = case
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(cin + cout)
@@ -74,6 +74,9 @@ def test_last_layer_kernel_matches_fp64(case):
     assert rel(conv3d_k3_fewout(inp, w, b), ref) < 2e-6                      # plain fp32 FMAs
     ref_r = torch.nn.functional.conv3d(inp.double().relu(), w.double(), None, padding=1)
     assert rel(conv3d_k3_fewout(inp, w, None, relu_in=True), ref_r) < 2e-6
+    # the same layer as pointwise tensor-core GEMM + sum over the shifted taps (split bf16 operands)
+    assert rel(conv3d_k3_fewout_gemm(inp, w, b), ref) < 3e-5
+    assert rel(conv3d_k3_fewout_gemm(inp, w, None, relu_in=True), ref_r) < 3e-5
 
 
 def test_conv_forward_routes_to_the_kernel_and_matches_cudnn_path():
