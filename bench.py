@@ -734,6 +734,11 @@ def main():
             y_bytes = hy.numel() * 8
         h2d = y_bytes + hm.numel() * 8 + hw.numel()
 
+        # the sampling pattern's own bound on sampled ky lines per frame (what VDktMaskFunc knows about its masks; here taken from
+        # the plan of the resident batch, outside the timed region); checked after the run with lines_overflowed()
+        lines_bound = int(plan[1]) if plan is not None else None
+        last_ops = [None]
+
         def e2e_step():
             with torch.no_grad():
                 for i in range(n_chunk):
@@ -743,8 +748,9 @@ def main():
                         dw = hw[sl].to(dev, non_blocking=True)
                         dm = hm[sl].to(dev, non_blocking=True)
                         dy = hy[sl] if host_y else hy[sl].to(dev, non_blocking=True)
-                        A_i = SenseModel(dm, weights=dw)
+                        A_i = SenseModel(dm, weights=dw, max_lines=lines_bound)   # no read-back: the host never waits for the stream
                         aty_i = A_i(dy, adjoint=True)
+                        last_ops[0] = A_i
                         ev = torch.cuda.Event()
                         ev.record(xfer)
                     with torch.cuda.stream(st):
@@ -784,6 +790,8 @@ def main():
             return max_over_ranks(time.perf_counter() - t0, dev)
 
         el = timed(e2e_step)
+        if last_ops[0] is not None and lines_bound is not None:
+            assert not last_ops[0].lines_overflowed(), "the k-t mask has more sampled lines per frame than the bound passed to SenseModel"
         el_copy = timed(copy_only_step)
         e2e = {"value": total_slices * n_e2e / el, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
@@ -794,7 +802,9 @@ def main():
                "pipeline": f"{n_chunk} chunks of {cb} slices: H2D + line plan + A^H y on a high-priority transfer stream, DC steps + D2H on {n_streams} streams",
                "kspace": ("left in pinned host memory, sampled ky lines read in place over PCIe" if host_y
                           else "dense copy to the device"),
-               "mask": "uint8 on the host, converted to fp32 on the device by SenseModel", "numa": numa}
+               "mask": "uint8 on the host, converted to fp32 on the device by SenseModel",
+               "line_plan": ("built per chunk without a host read-back (SenseModel(max_lines=%d), the pattern's bound on sampled lines per frame)" % lines_bound
+                             if lines_bound is not None else "dense weights: no plan"), "numa": numa}
 
     full = None
     if rank == 0 and world == 1 and not args.skip_full and preset is None:

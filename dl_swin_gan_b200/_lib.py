@@ -37,6 +37,7 @@ SIGNATURES = {
     "dlsg_sense_dc_step_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _sz] + _shape7 + [_vp]),
     "dlsg_sense_line_plan_bytes": (_sz, [_i, _i, _i]),
     "dlsg_sense_line_plan_build": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "dlsg_sense_line_plan_build_capped": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "dlsg_sense_lines_supported": (_i, [_i, _i, _i, _i]),
     "dlsg_sense_lines_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _sz]),
     "dlsg_sense_forward_lines_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz] + [_i] * 6 + [_vp]),

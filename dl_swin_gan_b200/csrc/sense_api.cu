@@ -668,7 +668,12 @@ size_t dlsg_sense_line_plan_bytes(int B, int T, int Y) {
 
 int dlsg_sense_line_plan_build(const float* weights, const long long* w_strides, int B, int C, int T, int Y, int X,
                                void* plan, void* stream) {
-    if (B <= 0 || C <= 0 || T <= 0 || Y <= 0 || X <= 0) return DLSG_EINVAL;
+    return dlsg_sense_line_plan_build_capped(weights, w_strides, B, C, T, Y, X, 0, plan, stream);
+}
+
+int dlsg_sense_line_plan_build_capped(const float* weights, const long long* w_strides, int B, int C, int T, int Y, int X,
+                                      int max_lines, void* plan, void* stream) {
+    if (B <= 0 || C <= 0 || T <= 0 || Y <= 0 || X <= 0 || max_lines < 0) return DLSG_EINVAL;
     if (!weights || !w_strides || !plan) return DLSG_EINVAL;
     const dlsg::WeightStrides ws{w_strides[0], w_strides[1], w_strides[2], w_strides[3], w_strides[4]};
     int* counts = static_cast<int*>(plan);
@@ -678,7 +683,7 @@ int dlsg_sense_line_plan_build(const float* weights, const long long* w_strides,
     int* cls = order + (size_t)B * T * Y;
     float* wq = reinterpret_cast<float*>(counts + dlsg::line_plan_wq_offset(B, T, Y));
     const int rc = dlsg::launch(dlsg::sense_line_plan_kernel, dim3((unsigned)((long long)B * T)), dim3(256), (size_t)Y * sizeof(int),
-                                static_cast<dlsg::stream_t>(stream), weights, ws, C, T, Y, X, counts, list, pos, order, cls, wq);
+                                static_cast<dlsg::stream_t>(stream), weights, ws, C, T, Y, X, counts, list, pos, order, cls, wq, max_lines);
     return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
 }
 

@@ -61,7 +61,7 @@ DLSG_DEVICE size_t idx_lines(const SenseDims& d, int lmax, int b, int c, int t, 
 // CTA = (b, t): flags the ky lines that carry any non-zero (or NaN) weight, then one thread compacts them.
 DLSG_KERNEL void DLSG_LAUNCH_BOUNDS(256)
 sense_line_plan_kernel(const float* __restrict__ w, WeightStrides ws, int C, int T, int Y, int X,
-                       int* counts, int* list, int* pos, int* order, int* cls, float* wq) {
+                       int* counts, int* list, int* pos, int* order, int* cls, float* wq, int cap) {
     DLSG_DYN_SMEM(int, flag);                    // [Y]
     const int bt = blockIdx.x, b = bt / T, t = bt - b * T;
     for (int y = threadIdx.x; y < Y; y += blockDim.x) flag[y] = 0;
@@ -78,9 +78,12 @@ sense_line_plan_kernel(const float* __restrict__ w, WeightStrides ws, int C, int
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int n = 0;
+        // cap > 0: the caller sized the intermediate for at most `cap` lines per frame without reading counts[] back; lines beyond
+        // the promise are dropped (treated as unsampled) and flagged in cls[.][35], so nothing is ever written out of bounds
+        int n = 0, dropped = 0;
         for (int y = 0; y < Y; ++y) {
-            const bool on = flag[ny == 1 ? 0 : y] != 0;
+            bool on = flag[ny == 1 ? 0 : y] != 0;
+            if (on && cap > 0 && n >= cap) { on = false; dropped = 1; }
             pos[(size_t)bt * Y + y] = on ? n : -1;
             if (on) list[(size_t)bt * Y + n++] = y;
         }
@@ -102,7 +105,7 @@ sense_line_plan_kernel(const float* __restrict__ w, WeightStrides ws, int C, int
             cnt[k] = seg[k];                         // running write position of the class
         }
         seg[16] = s;
-        clist[16] = m; clist[17] = mask; clist[18] = 0;
+        clist[16] = m; clist[17] = mask; clist[18] = dropped;
         int* ord = order + (size_t)bt * Y;
         for (int i = 0; i < n; ++i) ord[cnt[lst[i] & 15]++] = i;
         for (int i = n; i < Y; ++i) ord[i] = 0;

@@ -227,9 +227,17 @@ class SenseModel(nn.Module):
     scripts/train_swin.py:116); layout preparation happens on first use and is cached.
     """
 
-    def __init__(self, maps: torch.Tensor, weights: Optional[torch.Tensor] = None) -> None:
+    def __init__(self, maps: torch.Tensor, weights: Optional[torch.Tensor] = None, max_lines: Optional[int] = None) -> None:
+        """`max_lines` (not in the reference; optional): the caller's promise that no (slice, frame) of `weights` has more than this many
+        non-zero ky lines - what a k-t mask generator knows about its own pattern.  With it the sampled-line plan is built without
+        the one scalar read-back, so constructing and using the operator never synchronises the host with the stream (a pipeline
+        of chunks on several streams then overlaps as enqueued).  Lines beyond the promise would be treated as unsampled;
+        `lines_overflowed()` tells (it synchronises)."""
         super().__init__()
         assert torch.is_complex(maps)  # force complex (transforms.py:70)
+        if max_lines is not None and int(max_lines) < 1:
+            raise ValueError("max_lines must be a positive number of ky lines")
+        self.max_lines = None if max_lines is None else int(max_lines)
         self.maps = maps
         ndims = len(list(maps[0, 0, 0, ...].squeeze().shape))
         self.fft = FFT(ndims)
@@ -337,7 +345,7 @@ class SenseModel(nn.Module):
             return None
         key = tuple(dims)
         if key not in self._line_plans:
-            if torch.cuda.is_current_stream_capturing():
+            if self.max_lines is None and torch.cuda.is_current_stream_capturing():
                 raise RuntimeError(
                     "SenseModel builds its sampled-line plan on first use (one scalar read-back), which is not allowed while a CUDA "
                     "graph is being captured: call the operator once before the capture")
@@ -349,13 +357,28 @@ class SenseModel(nn.Module):
                 wstr = (ctypes.c_longlong * 5)(*wexp.stride())
                 with torch.cuda.device(wexp.device):
                     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-                    _lib.check(lib.dlsg_sense_line_plan_build(wexp.data_ptr(), wstr, B, C, T, Y, X, buf.data_ptr(), stream),
-                               "dlsg_sense_line_plan_build")
-                lmax = max(1, int(buf[: B * T].max().item()))          # the one read-back: sizes the intermediate
+                    _lib.check(lib.dlsg_sense_line_plan_build_capped(wexp.data_ptr(), wstr, B, C, T, Y, X, int(self.max_lines or 0),
+                                                                     buf.data_ptr(), stream), "dlsg_sense_line_plan_build_capped")
+                if self.max_lines is not None:
+                    lmax = min(self.max_lines, Y)                      # the caller's promise: no read-back, no host synchronisation
+                else:
+                    lmax = max(1, int(buf[: B * T].max().item()))      # the one read-back: sizes the intermediate
                 if lmax <= _LINES_MAX_FRACTION * Y and lib.dlsg_sense_lines_supported(E, Y, X, lmax):
                     plan = (buf, lmax)
             self._line_plans[key] = plan
         return self._line_plans[key]
+
+    def lines_overflowed(self) -> bool:
+        """True when a `max_lines` promise was broken for any plan built so far (some frame had more sampled lines; they were dropped).
+        Reads the plans back, i.e. synchronises."""
+        for key, plan in self._line_plans.items():
+            if plan is None:
+                continue
+            B, _, _, T, Y, _ = key
+            cls0 = B * T * (1 + 3 * Y)
+            if bool(plan[0][cls0: cls0 + B * T * 36].view(B * T, 36)[:, 35].any().item()):
+                return True
+        return False
 
     def _dims(self, data: torch.Tensor, kind: str):
         maps5 = self._prepared_maps()

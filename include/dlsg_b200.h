@@ -125,6 +125,13 @@ size_t dlsg_sense_line_plan_bytes(int B, int T, int Y);
 int dlsg_sense_line_plan_build(const float* weights, const long long* w_strides, int B, int C, int T, int Y, int X,
                                void* plan, void* stream);
 
+/* The same with a promise instead of the read-back: the caller knows (from the sampling pattern) that no frame has more than
+ * max_lines sampled ky lines, passes lmax = max_lines to the operators and never touches counts[].  Lines beyond the promise are
+ * dropped - the operators then behave as if their weights were zero - and cls[(b*T+t)*36 + 35] is set to 1 for that frame, so a
+ * broken promise can be detected later; nothing is written out of bounds.  max_lines = 0: no cap (the function above). */
+int dlsg_sense_line_plan_build_capped(const float* weights, const long long* w_strides, int B, int C, int T, int Y, int X,
+                                      int max_lines, void* plan, void* stream);
+
 /* 1 when the sampled-line kernels cover this problem (compiled radices and shared-memory budget). */
 int dlsg_sense_lines_supported(int E, int Y, int X, int lmax);
 

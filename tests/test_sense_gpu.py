@@ -533,3 +533,31 @@ def test_kt_preprocessing_matches_reference(dev):
                       ((torch.roll(big, 2 - i, 2).narrow(2, 0, 5).abs() > 1e-12).float().sum(2, keepdim=True) + 1e-6)
                       for i in range(20)], dim=2)
     assert rel_l2(to_np(U.sliding_window(big, 2, 5)), to_np(want)) < 1e-6
+
+
+def test_max_lines_promise_skips_the_read_back_and_flags_a_broken_promise():
+    """SenseModel(max_lines=...) builds the sampled-line plan without reading counts back: same results when the promise holds,
+    dropped lines + a flag (no out-of-bounds write) when it does not."""
+    from dl_swin_gan_b200.mri import SenseModel
+    from dl_swin_gan_b200.mri.subsample import VDktMaskFunc
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    B, E, C, T, Y, X = 2, 1, 4, 3, 192, 160
+    maps = torch.view_as_complex(torch.randn(B, E, C, 1, Y, X, 2, generator=g, device=dev))
+    x = torch.view_as_complex(torch.randn(B, E, T, Y, X, 2, generator=g, device=dev))
+    mask = torch.cat([VDktMaskFunc((12, 12), 0.25, 0.25)((1, 1, T, Y, X), seed=7 + b) for b in range(B)], 0).to(dev)
+    n_lines = int((mask.sum(-1) > 0).sum(-1).max())
+    ref = SenseModel(maps, weights=mask)
+    want = ref.dc_step(x, ref(ref(x), adjoint=True), -2.0)
+    A = SenseModel(maps, weights=mask, max_lines=n_lines + 3)
+    got = A.dc_step(x, A(A(x), adjoint=True), -2.0)
+    assert A._line_plans and all(p is not None and p[1] == n_lines + 3 for p in A._line_plans.values())
+    assert not A.lines_overflowed()
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-6
+    # broken promise: fewer lines than the mask has -> the extra lines count as unsampled, flagged, nothing crashes
+    A2 = SenseModel(maps, weights=mask, max_lines=max(1, n_lines - 4))
+    k2 = A2(x)
+    torch.cuda.synchronize()
+    assert A2.lines_overflowed() and torch.isfinite(torch.view_as_real(k2)).all()
+    with pytest.raises(ValueError):
+        SenseModel(maps, weights=mask, max_lines=0)
