@@ -739,7 +739,13 @@ def main():
         lines_bound = int(plan[1]) if plan is not None else None
         last_ops = [None]
 
+        # the host may not run more than two steps ahead of the device: without a bound the caching allocator cannot reuse the
+        # per-chunk buffers of steps that are still in flight, keeps growing and eventually stalls everything in a synchronous trim
+        inflight = []
+
         def e2e_step():
+            if len(inflight) >= 2:
+                inflight.pop(0).synchronize()
             with torch.no_grad():
                 for i in range(n_chunk):
                     sl = slice(i * cb, (i + 1) * cb)
@@ -761,6 +767,9 @@ def main():
                         hx[sl].copy_(res, non_blocking=True)
                 for st in streams:
                     torch.cuda.current_stream(dev).wait_stream(st)
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(dev))
+                inflight.append(done)
 
         hy_flat = hy.view(-1)                                  # for the byte-equivalent contiguous copy below
         y_elems = max(1, y_bytes // 8 // n_chunk)
