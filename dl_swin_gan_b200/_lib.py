@@ -58,9 +58,9 @@ SIGNATURES = {
     "dlsg_swin_proj_scatter_residual_f32": (_i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _vp]),
     "dlsg_swin_proj_scatter_f32": (_i, [_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _vp]),
     "dlsg_conv3d_k3_supported": (_i, [_i, _i]),
-    "dlsg_conv3d_k3_tf32x3_f32": (_i, [_vp, _vp, _vp, _vp, _f, _vp] + [_i] * 7 + [_vp]),
-    "dlsg_conv3d_pointwise_tf32x3_f32": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),
-    "dlsg_conv3d_tapsum_f32": (_i, [_vp, _vp, _vp] + [_i] * 6 + [_vp]),
+    "dlsg_conv3d_k3_tf32x3_f32": (_i, [_vp, _vp, _vp, _vp, _f, _vp] + [_i] * 9 + [_vp]),
+    "dlsg_conv3d_pointwise_tf32x3_f32": (_i, [_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp]),
+    "dlsg_conv3d_tapsum_f32": (_i, [_vp, _vp, _vp] + [_i] * 8 + [_vp]),
     "dlsg_conv3d_k3_fewout_f32": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),
     "dlsg_conv3d_patch_tf32x3_f32": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),
     "dlsg_conv3d_unpatch_tf32x3_f32": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),

@@ -136,10 +136,11 @@ __global__ void __launch_bounds__(kFewThreads, 2) conv3d_k3_fewout_kernel(FewOut
 // Every element of z is read once.  Thread = voxel; ZC = channel stride of z (>= 27*CO, padded to the GEMM's tile).
 template <int CO>
 __global__ void __launch_bounds__(256) conv3d_tapsum_kernel(const float* __restrict__ z, const float* __restrict__ bias, float* __restrict__ out,
-                                                           int T, int Y, int X, int ZC, long long NV) {
-    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= NV) return;
+                                                           int T, int Y, int X, int ZC, long long NV, int tlo, int tn) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;        // row of the frame window tlo .. tlo + tn - 1 of every sample
+    if (w >= NV) return;
     const long long YX = (long long)Y * X;
+    const long long v = w + ((w / (YX * tn)) * (T - tn) + tlo) * YX;              // voxel of the volume
     const long long r1 = v % YX;
     const int vx = (int)(r1 % X), vy = (int)(r1 / X), vt = (int)((v / YX) % T);
     float acc[CO];

@@ -52,7 +52,10 @@ struct ConvParams {
     int ksz, stride, pad;  // CONV_GATHER: out[o] = sum over the ksz^3 taps of x[o * stride - pad + tap];  3,1,1 = 'same' 3x3x3;  P,P,0 = patch embedding
                            // CONV_UNPATCH: out[i * ksz + tap] = W_tap x[i]  (transposed convolution with kernel = stride = ksz: patch unembedding)
     int mode;
-    long long NV;          // GEMM rows: output voxels (CONV_GATHER) or input voxels (CONV_UNPATCH)
+    int tlo, tn;           // CONV_GATHER: only the output frames tlo .. tlo + tn - 1 of every sample are computed (tn = To: all).  The denoisers
+                           // pad the time axis circularly and crop it at the end (swin3D.py:401-417): a layer's outer frames that no later
+                           // layer reads are never computed; the frames that are computed are bit-identical to the full convolution
+    long long NV;          // GEMM rows: output voxels in the frame window (CONV_GATHER) or input voxels (CONV_UNPATCH)
     int relu_in;           // rectify the input on the fly (ConvBlock's pre-activation)
     const float* resid;    // optional [NB, To, Yo, Xo, Cout]: out = conv + bias + resid_scale * resid (the blocks' skip connections)
     float resid_scale;
@@ -171,8 +174,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                     if (unpatch) { coord[i] = 0; ibase[i] = (int)vi; }
                     else {
                         const long long r1 = vi % YXo;
-                        const int n = (int)(vi / (YXo * p.To));
-                        const int t0 = (int)((vi / YXo) % p.To) * p.stride - p.pad, y0 = (int)(r1 / p.Xo) * p.stride - p.pad,
+                        const int n = (int)(vi / (YXo * p.tn));
+                        const int t0 = ((int)((vi / YXo) % p.tn) + p.tlo) * p.stride - p.pad, y0 = (int)(r1 / p.Xo) * p.stride - p.pad,
                                   x0 = (int)(r1 % p.Xo) * p.stride - p.pad;
                         coord[i] = (t0 + 1) << 20 | (y0 + 1) << 10 | (x0 + 1);
                         ibase[i] = (int)((((long long)n * p.T + t0) * p.Y + y0) * p.X + x0);
@@ -288,6 +291,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
             const bool live = v < p.NV;
             const unsigned taddr = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(eti * 256);
             long long vout = v;
+            if (!unpatch && p.tn != p.To) vout = v + ((v / (YXo * p.tn)) * (p.To - p.tn) + p.tlo) * YXo;     // row of the frame window -> voxel of the volume
             if (unpatch && live) {                                                   // input voxel (n, t, y, x) -> output voxel (n, t k + a, y k + b, x k + c)
                 const long long r1 = v % YX;
                 const long long nt = v / YX;                                          // n * T + t
@@ -421,20 +425,23 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
         unsigned g = 0, tcount = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
             const long long v0 = tile * kConvTileRows + wrow0 + rsub;
+            const long long win = YX * p.tn;                        // GEMM rows per sample (frame window tlo .. tlo + tn - 1)
             int coord[4];
+            long long vact[4];                                      // voxel of the volume behind each row
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const long long vi = v0 + 4 * i;
+                vact[i] = vi + ((vi / win) * (p.T - p.tn) + p.tlo) * YX;
                 if (vi < p.NV) {
                     const long long r1 = vi % YX;
-                    coord[i] = (int)((vi / YX) % p.T) << 20 | (int)(r1 / p.X) << 10 | (int)(r1 % p.X);
+                    coord[i] = ((int)((vi / YX) % p.tn) + p.tlo) << 20 | (int)(r1 / p.X) << 10 | (int)(r1 % p.X);
                 } else coord[i] = -1;
             }
             // the loads run one iteration ahead of the split / store; 32-bit element offsets, (tap, chunk) advanced incrementally
             unsigned okmask = 0, foff = 0;
             unsigned roff[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) roff[i] = (unsigned)(v0 + 4 * i) * (unsigned)p.Cin + 4u * k4;
+            for (int i = 0; i < 4; ++i) roff[i] = (unsigned)vact[i] * (unsigned)p.Cin + 4u * k4;
             auto tap_state = [&](int tap) {
                 const int dt = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
                 okmask = 0;
@@ -510,17 +517,21 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
                 asm volatile("bar.sync 1, 512;\n" ::: "memory");
                 if (half == 0) {
                     const long long vb = tile * kConvTileRows + colw + c0;
+                    // rows of the frame window -> voxels of the volume: a block of 32 rows crosses at most one sample boundary
+                    const long long win = YX * p.tn, nb0 = vb / win, edge = (nb0 + 1) * win;
+                    const long long sh0 = (nb0 * (p.T - p.tn) + p.tlo) * YX, sh1 = sh0 + (long long)(p.T - p.tn) * YX;
                     if (p.resid) {                                            // all 32 skip-connection loads in flight together
                         float rs[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) rs[j] = (vb + j < p.NV) ? __ldg(p.resid + (size_t)(vb + j) * Cout + cbase + lane) : 0.f;
+                        for (int j = 0; j < 32; ++j)
+                            rs[j] = (vb + j < p.NV) ? __ldg(p.resid + (size_t)(vb + j + (vb + j < edge ? sh0 : sh1)) * Cout + cbase + lane) : 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[j] = fmaf(p.resid_scale, rs[j], acc[j]);
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const long long v = vb + j;
-                        if (v < p.NV) p.out[(size_t)v * Cout + cbase + lane] = acc[j] + xb[j * 33 + lane] + bco;
+                        if (v < p.NV) p.out[(size_t)(v + (v < edge ? sh0 : sh1)) * Cout + cbase + lane] = acc[j] + xb[j * 33 + lane] + bco;
                     }
                 }
                 asm volatile("bar.sync 1, 512;\n" ::: "memory");

@@ -56,13 +56,16 @@ static int conv_launch(dlsg::ConvParams& p, void* stream) {
 #endif
 
 int dlsg_conv3d_k3_tf32x3_f32(const float* x, const void* wprep, const float* bias, const float* resid, float resid_scale, float* out,
-                              int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream) {
+                              int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, int t_lo, int t_n, void* stream) {
 #if defined(__CUDACC__)
+    if (t_n == 0) { t_lo = 0; t_n = T; }
+    if (t_lo < 0 || t_n < 1 || t_lo + t_n > T) return DLSG_EINVAL;
     dlsg::ConvParams p{};
     p.x = x; p.wprep = static_cast<const float*>(wprep); p.bias = bias; p.out = out;
     p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin; p.Cout = Cout;
     p.To = T; p.Yo = Y; p.Xo = X; p.ksz = 3; p.stride = 1; p.pad = 1; p.mode = dlsg::CONV_GATHER;
-    p.NV = (long long)NB * T * Y * X;
+    p.tlo = t_lo; p.tn = t_n;
+    p.NV = (long long)NB * t_n * Y * X;
     p.relu_in = relu_in ? 1 : 0;
     if (resid && (reinterpret_cast<uintptr_t>(resid) & 15)) return DLSG_EINVAL;
     p.resid = resid; p.resid_scale = resid_scale;
@@ -83,7 +86,8 @@ int dlsg_conv3d_k3_tf32x3_f32(const float* x, const void* wprep, const float* bi
     }
     return conv_launch(p, stream);
 #else
-    (void)x; (void)wprep; (void)bias; (void)resid; (void)resid_scale; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)relu_in; (void)stream;
+    (void)x; (void)wprep; (void)bias; (void)resid; (void)resid_scale; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)relu_in;
+    (void)t_lo; (void)t_n; (void)stream;
     return DLSG_EUNSUPPORTED;      // tcgen05 / TMEM have no host emulation
 #endif
 }
@@ -97,6 +101,7 @@ int dlsg_conv3d_patch_tf32x3_f32(const float* x, const void* wprep, const float*
     p.x = x; p.wprep = static_cast<const float*>(wprep); p.bias = bias; p.out = out;
     p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin; p.Cout = Cout;
     p.To = T / patch; p.Yo = Y / patch; p.Xo = X / patch; p.ksz = patch; p.stride = patch; p.pad = 0; p.mode = dlsg::CONV_GATHER;
+    p.tlo = 0; p.tn = p.To;
     p.NV = (long long)NB * p.To * p.Yo * p.Xo;
     return conv_launch(p, stream);
 #else
@@ -113,6 +118,7 @@ int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const void* wprep, const floa
     p.x = x; p.wprep = static_cast<const float*>(wprep); p.bias = bias; p.out = out;
     p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin; p.Cout = Cout;
     p.To = T * patch; p.Yo = Y * patch; p.Xo = X * patch; p.ksz = patch; p.stride = patch; p.pad = 0; p.mode = dlsg::CONV_UNPATCH;
+    p.tlo = 0; p.tn = p.To;
     p.NV = (long long)NB * T * Y * X;
     return conv_launch(p, stream);
 #else
@@ -122,35 +128,41 @@ int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const void* wprep, const floa
 }
 
 int dlsg_conv3d_pointwise_tf32x3_f32(const float* x, const void* wprep, const float* bias, float* out,
-                                     int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream) {
+                                     int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, int t_lo, int t_n, void* stream) {
 #if defined(__CUDACC__)
     if (Cin % dlsg::kConvKC != 0) return DLSG_EUNSUPPORTED;
+    if (t_n == 0) { t_lo = 0; t_n = T; }
+    if (t_lo < 0 || t_n < 1 || t_lo + t_n > T) return DLSG_EINVAL;
     dlsg::ConvParams p{};
     p.x = x; p.wprep = static_cast<const float*>(wprep); p.bias = bias; p.out = out;
     p.NB = NB; p.T = T; p.Y = Y; p.X = X; p.Cin = Cin; p.Cout = Cout;
     p.To = T; p.Yo = Y; p.Xo = X; p.ksz = 1; p.stride = 1; p.pad = 0; p.mode = dlsg::CONV_GATHER;
-    p.NV = (long long)NB * T * Y * X;
+    p.tlo = t_lo; p.tn = t_n;
+    p.NV = (long long)NB * t_n * Y * X;
     p.relu_in = relu_in ? 1 : 0;
     return conv_launch(p, stream);
 #else
-    (void)x; (void)wprep; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)relu_in; (void)stream;
+    (void)x; (void)wprep; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)Cin; (void)Cout; (void)relu_in; (void)t_lo; (void)t_n; (void)stream;
     return DLSG_EUNSUPPORTED;
 #endif
 }
 
-int dlsg_conv3d_tapsum_f32(const float* z, const float* bias, float* out, int NB, int T, int Y, int X, int ZC, int Cout, void* stream) {
+int dlsg_conv3d_tapsum_f32(const float* z, const float* bias, float* out, int NB, int T, int Y, int X, int ZC, int Cout,
+                           int t_lo, int t_n, void* stream) {
 #if defined(__CUDACC__)
     using namespace dlsg;
     if (!z || !out || NB <= 0 || T <= 0 || Y <= 0 || X <= 0) return DLSG_EINVAL;
+    if (t_n == 0) { t_lo = 0; t_n = T; }
+    if (t_lo < 0 || t_n < 1 || t_lo + t_n > T) return DLSG_EINVAL;
     if ((Cout != 2 && Cout != 4) || ZC < 27 * Cout || ZC % 4 != 0) return DLSG_EUNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) & 15) return DLSG_EINVAL;
-    const long long NV = (long long)NB * T * Y * X;
+    const long long NV = (long long)NB * t_n * Y * X;
     const unsigned grid = (unsigned)((NV + 255) / 256);
-    const int rc = Cout == 2 ? launch(conv3d_tapsum_kernel<2>, dim3(grid), dim3(256), 0, (stream_t)stream, z, bias, out, T, Y, X, ZC, NV)
-                             : launch(conv3d_tapsum_kernel<4>, dim3(grid), dim3(256), 0, (stream_t)stream, z, bias, out, T, Y, X, ZC, NV);
+    const int rc = Cout == 2 ? launch(conv3d_tapsum_kernel<2>, dim3(grid), dim3(256), 0, (stream_t)stream, z, bias, out, T, Y, X, ZC, NV, t_lo, t_n)
+                             : launch(conv3d_tapsum_kernel<4>, dim3(grid), dim3(256), 0, (stream_t)stream, z, bias, out, T, Y, X, ZC, NV, t_lo, t_n);
     return rc == 0 ? DLSG_OK : DLSG_ELAUNCH;
 #else
-    (void)z; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)ZC; (void)Cout; (void)stream;
+    (void)z; (void)bias; (void)out; (void)NB; (void)T; (void)Y; (void)X; (void)ZC; (void)Cout; (void)t_lo; (void)t_n; (void)stream;
     return DLSG_EUNSUPPORTED;
 #endif
 }

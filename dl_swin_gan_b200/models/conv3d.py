@@ -103,7 +103,7 @@ def supported(conv: torch.nn.Module, x: torch.Tensor) -> bool:
     return kind(conv, x) is not None
 
 
-def _run(fn_name, x, weight, bias, out_dims, last, transposed, residual=None, residual_scale=1.0):
+def _run(fn_name, x, weight, bias, out_dims, last, transposed, residual=None, residual_scale=1.0, t_range=None):
     lib = _lib.load()
     nb, cin, t, y, xx = x.shape
     cout = weight.shape[1] if transposed else weight.shape[0]
@@ -123,15 +123,31 @@ def _run(fn_name, x, weight, bias, out_dims, last, transposed, residual=None, re
             if not rc.is_contiguous():
                 rc = rc.contiguous()
         args += [rc.data_ptr() if rc is not None else None, float(residual_scale)]
-    st = getattr(lib, fn_name)(*args, out.data_ptr(), nb, t, y, xx, cin, cout, int(last), torch.cuda.current_stream(x.device).cuda_stream)
+    tail = [int(last)]
+    if fn_name == "dlsg_conv3d_k3_tf32x3_f32":
+        lo, hi = _window(t_range, t)
+        tail += [lo, hi - lo]
+    st = getattr(lib, fn_name)(*args, out.data_ptr(), nb, t, y, xx, cin, cout, *tail, torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(st, fn_name)
     return out.permute(0, 4, 1, 2, 3)
 
 
-def conv3d_k3(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: bool = False, residual=None, residual_scale: float = 1.0) -> torch.Tensor:
+def _window(t_range, t):
+    """(lo, hi) of the output frames to compute, clipped to the volume; None = all."""
+    if t_range is None:
+        return 0, t
+    lo, hi = max(0, int(t_range[0])), min(t, int(t_range[1]))
+    if hi <= lo:
+        raise ValueError(f"empty frame window {t_range} for {t} frames")
+    return lo, hi
+
+
+def conv3d_k3(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: bool = False, residual=None, residual_scale: float = 1.0,
+              t_range=None) -> torch.Tensor:
     """x [NB, Cin, T, Y, X] (any layout; used channels-last) -> conv(relu?(x)) + bias (+ residual_scale * residual),
-    [NB, Cout, T, Y, X] in channels_last_3d."""
-    return _run("dlsg_conv3d_k3_tf32x3_f32", x, weight, bias, x.shape[2:], relu_in, False, residual, residual_scale)
+    [NB, Cout, T, Y, X] in channels_last_3d.  `t_range = (lo, hi)`: only the output frames lo .. hi - 1 are computed (the others are left
+    uninitialised) - for callers that know the outer frames are never read (the denoisers' circular time padding)."""
+    return _run("dlsg_conv3d_k3_tf32x3_f32", x, weight, bias, x.shape[2:], relu_in, False, residual, residual_scale, t_range)
 
 
 def conv3d_patch(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
@@ -175,7 +191,7 @@ def conv3d_k3_fewout(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: 
     return out.permute(0, 4, 1, 2, 3)
 
 
-def conv3d_k3_fewout_gemm(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: bool = False) -> torch.Tensor:
+def conv3d_k3_fewout_gemm(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: bool = False, t_range=None) -> torch.Tensor:
     """The last layer (Cout = 2 or 4) as a pointwise tensor-core GEMM to 27*Cout tap channels followed by the sum over the 27 shifted
     voxels (csrc/conv3d_fewout.cuh): two passes, each reading its input once, instead of 27 passes over the activations."""
     lib = _lib.load()
@@ -201,23 +217,30 @@ def conv3d_k3_fewout_gemm(x: torch.Tensor, weight: torch.Tensor, bias=None, relu
         except AttributeError:
             pass
     stream = torch.cuda.current_stream(x.device).cuda_stream
+    lo, hi = _window(t_range, t)
+    zlo, zhi = max(0, lo - 1), min(t, hi + 1)                   # the tap sum reads z one frame beyond the output window
     z = torch.empty((nb, t, y, xx, zc), device=x.device, dtype=torch.float32)
-    _lib.check(lib.dlsg_conv3d_pointwise_tf32x3_f32(xc.data_ptr(), prep.data_ptr(), None, z.data_ptr(), nb, t, y, xx, cin, zc, int(relu_in), stream),
-               "dlsg_conv3d_pointwise_tf32x3_f32")
+    _lib.check(lib.dlsg_conv3d_pointwise_tf32x3_f32(xc.data_ptr(), prep.data_ptr(), None, z.data_ptr(), nb, t, y, xx, cin, zc, int(relu_in),
+                                                    zlo, zhi - zlo, stream), "dlsg_conv3d_pointwise_tf32x3_f32")
     out = torch.empty((nb, t, y, xx, cout), device=x.device, dtype=torch.float32)
     b = bias.detach().float().contiguous() if bias is not None else None
-    _lib.check(lib.dlsg_conv3d_tapsum_f32(z.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(), nb, t, y, xx, zc, cout, stream),
-               "dlsg_conv3d_tapsum_f32")
+    _lib.check(lib.dlsg_conv3d_tapsum_f32(z.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(), nb, t, y, xx, zc, cout,
+                                          lo, hi - lo, stream), "dlsg_conv3d_tapsum_f32")
     return out.permute(0, 4, 1, 2, 3)
 
 
-def forward(conv: torch.nn.Module, x: torch.Tensor, which: str, relu_in: bool = False, residual=None, residual_scale: float = 1.0) -> torch.Tensor:
-    """`conv(relu?(x)) (+ residual_scale * residual)` on the kernel `kind()` chose; what a kernel cannot fuse is done around it."""
+def forward(conv: torch.nn.Module, x: torch.Tensor, which: str, relu_in: bool = False, residual=None, residual_scale: float = 1.0,
+            t_range=None) -> torch.Tensor:
+    """`conv(relu?(x)) (+ residual_scale * residual)` on the kernel `kind()` chose; what a kernel cannot fuse is done around it.
+    `t_range`: output frames the caller will read (a hint: kernels without a frame window compute everything)."""
     if which == K3:
-        return conv3d_k3(x, conv.weight, conv.bias, relu_in, residual, residual_scale)
+        return conv3d_k3(x, conv.weight, conv.bias, relu_in, residual, residual_scale, t_range)
     if which == FEWOUT:
         gemm = _FEWOUT_GEMM and bool(_lib.load().dlsg_conv3d_k3_supported(conv.in_channels, -(-27 * conv.out_channels // 32) * 32))
-        out = (conv3d_k3_fewout_gemm if gemm else conv3d_k3_fewout)(x, conv.weight, conv.bias, relu_in)
+        if gemm:
+            out = conv3d_k3_fewout_gemm(x, conv.weight, conv.bias, relu_in, t_range)
+        else:
+            out = conv3d_k3_fewout(x, conv.weight, conv.bias, relu_in)
     else:
         if relu_in:
             x = torch.relu(x)

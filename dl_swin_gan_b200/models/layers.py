@@ -166,10 +166,11 @@ class ConvBlock(nn.Module):
         conv = (ComplexConv3d if is_complex else Conv3d)(in_chans, out_chans, kernel_size=kernel_size)
         self.layers = nn.Sequential(Normalization(in_chans, norm_type), Activation(act_type), conv)
 
-    def forward(self, input, residual=None, residual_scale=1.0, input_is_temp=False):
+    def forward(self, input, residual=None, residual_scale=1.0, input_is_temp=False, t_range=None):
         """`conv(act(input))` (+ residual_scale * residual).  The extra arguments only let the B200 kernels fuse what surrounds the
         convolution; the arithmetic is the reference's.  `input_is_temp`: nobody reads `input` after this call, so the in-place
-        ReLU of the reference (which would rectify `input` itself) may be applied inside the kernel's operand load instead."""
+        ReLU of the reference (which would rectify `input` itself) may be applied inside the kernel's operand load instead.
+        `t_range = (lo, hi)`: the caller reads only the output frames lo .. hi - 1 (the rest may be left uninitialised)."""
         act, conv_mod = self.layers[1], self.layers[2]
         fused = None
         if (_TC_CONV and _CONV_PRECISION == "tf32x3" and input.is_cuda and isinstance(conv_mod, Conv3d)
@@ -185,7 +186,7 @@ class ConvBlock(nn.Module):
         if relu and not input_is_temp:
             input = act(input)                      # in place, visible to the caller, exactly as in the reference
             relu = False
-        return conv3d.forward(conv_mod.conv, input, fused, relu_in=relu, residual=residual, residual_scale=residual_scale)
+        return conv3d.forward(conv_mod.conv, input, fused, relu_in=relu, residual=residual, residual_scale=residual_scale, t_range=t_range)
 
     def __repr__(self):
         return f"{self.name}(in_chans={self.in_chans}, out_chans={self.out_chans})"
@@ -199,10 +200,15 @@ class ResBlock(nn.Module):
         self.layers = nn.Sequential(ConvBlock(chans, chans, kernel_size, act_type=act_type, is_complex=is_complex),
                                     ConvBlock(chans, chans, kernel_size, act_type=act_type, is_complex=is_complex))
 
-    def forward(self, input):
+    def forward(self, input, t_range=None):
         # the first block rectifies `input` in place (reference quirk, see Activation), so the skip below adds relu(input)
-        h = self.layers[0](input)
-        return self.layers[1](h, residual=input, input_is_temp=True)
+        h = self.layers[0](input, t_range=grow_frames(t_range, 1))
+        return self.layers[1](h, residual=input, input_is_temp=True, t_range=t_range)
+
+
+def grow_frames(t_range, k):
+    """The frame window a layer must produce so that a 3-tap consumer can produce `t_range` (None stays None = all frames)."""
+    return None if t_range is None else (t_range[0] - k, t_range[1] + k)
 
 
 def time_pad_circular(x: torch.Tensor, pad: int) -> torch.Tensor:

@@ -7,7 +7,7 @@ from __future__ import annotations
 from torch import nn
 
 from ..mri.utils import center_crop
-from .layers import ConvBlock, ResBlock, channels_to_complex, complex_to_channels, time_pad_circular
+from .layers import ConvBlock, ResBlock, channels_to_complex, complex_to_channels, grow_frames, time_pad_circular
 
 
 class ResNet(nn.Module):
@@ -37,8 +37,12 @@ class ResNet(nn.Module):
 
     def forward(self, input):
         input = self._preprocess(input)
-        output = self.init_layer(input)
-        for res_block in self.res_blocks:
-            output = res_block(output)
-        output = self.final_layer(output, residual=input, input_is_temp=len(self.res_blocks) > 0)
+        # _postprocess keeps the frames pad_size .. T - pad_size; each 3-tap layer widens what its producer must deliver by one frame,
+        # and what nobody reads is not computed (bit-identical on the frames that are; the reference computes and discards them)
+        keep = (self.pad_size, input.shape[2] - self.pad_size)
+        n = len(self.res_blocks)
+        output = self.init_layer(input, t_range=grow_frames(keep, 2 * n + 1))
+        for i, res_block in enumerate(self.res_blocks):
+            output = res_block(output, t_range=grow_frames(keep, 2 * (n - 1 - i) + 1))
+        output = self.final_layer(output, residual=input, input_is_temp=n > 0, t_range=keep)
         return self._postprocess(output)

@@ -15,7 +15,7 @@ from torch import nn
 
 from ..mri.utils import center_crop
 from ..swin.backbone import SwinTransformer3D
-from .layers import ConvBlock, channels_to_complex, complex_to_channels, time_pad_circular
+from .layers import ConvBlock, channels_to_complex, complex_to_channels, grow_frames, time_pad_circular
 
 
 class SwinTransformer3DBlock(nn.Module):
@@ -35,8 +35,8 @@ class ResSwinTransformer3DBlock(nn.Module):
             SwinTransformer3DBlock(in_chans, chans, window_size, num_heads, num_layers, is_complex=is_complex),
             ConvBlock(chans, chans, kernel_size=3, act_type=act_type, is_complex=is_complex))
 
-    def forward(self, input):
-        return self.layers[1](self.layers[0](input), residual=input, input_is_temp=True)
+    def forward(self, input, t_range=None):
+        return self.layers[1](self.layers[0](input), residual=input, input_is_temp=True, t_range=t_range)
 
 
 class DeepFeatureExtraction(nn.Module):
@@ -48,12 +48,15 @@ class DeepFeatureExtraction(nn.Module):
         self.layers = nn.Sequential(*self.resswin_blocks,
                                     ConvBlock(chans, chans, kernel_size=3, act_type=act_type, is_complex=is_complex))
 
-    def forward(self, input, skip_scale=1.0):
-        """`layers(input) + skip_scale * input`; the caller's own `x + DFE(x)` (swin3D.py:430) rides in as skip_scale = 2."""
+    def forward(self, input, skip_scale=1.0, t_range=None):
+        """`layers(input) + skip_scale * input`; the caller's own `x + DFE(x)` (swin3D.py:430) rides in as skip_scale = 2.
+        `t_range`: the output frames the caller reads.  Only the last block's convolution can be narrowed with it - the Swin backbone
+        of every block attends over all frames."""
         x = input
-        for block in self.resswin_blocks:
-            x = block(x)
-        return self.layers[-1](x, residual=input, residual_scale=skip_scale, input_is_temp=x is not input)
+        last = len(self.resswin_blocks) - 1
+        for i, block in enumerate(self.resswin_blocks):
+            x = block(x, t_range=grow_frames(t_range, 1) if i == last else None)
+        return self.layers[-1](x, residual=input, residual_scale=skip_scale, input_is_temp=x is not input, t_range=t_range)
 
 
 class SwinTransformer3DNet(nn.Module):
@@ -88,7 +91,10 @@ class SwinTransformer3DNet(nn.Module):
 
     def forward(self, x):
         x = self._preprocess(x)
+        # _postprocess keeps the frames pad_size .. T - pad_size: a layer's outer frames that no later layer reads are not computed
+        # (bit-identical on the frames that are; the reference computes and discards them)
+        keep = (self.pad_size, x.shape[2] - self.pad_size)
         x = self.SFE(x)
-        x = self.DFE(x, skip_scale=2.0)              # x + DFE(x) = layers(x) + 2 x
-        x = self.final_layer(x, input_is_temp=True)
+        x = self.DFE(x, skip_scale=2.0, t_range=grow_frames(keep, 1))      # x + DFE(x) = layers(x) + 2 x
+        x = self.final_layer(x, input_is_temp=True, t_range=keep)
         return self._postprocess(x)

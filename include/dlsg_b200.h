@@ -296,9 +296,12 @@ int dlsg_conv3d_k3_supported(int Cin, int Cout);
  *                             wprep[k/32][h][(k%32)/8][co/8][co%8][k%8]
  * relu_in != 0 rectifies x on the fly (ConvBlock's pre-activation, :262-268).  resid (NULL or [NB,T,Y,X,Cout]) is a skip connection added
  * in the epilogue: out = conv + bias + resid_scale * resid (ResBlock :300, ResSwinTransformer3DBlock :340, DeepFeatureExtraction :369).
- * bias may be NULL.  NB*T*Y*X*Cin < 2^31. */
+ * bias may be NULL.  NB*T*Y*X*Cin < 2^31.
+ * t_lo, t_n: only the output frames t_lo .. t_lo + t_n - 1 of every sample are computed and written (t_n = 0: all T).  The denoisers pad the
+ * time axis circularly and crop it at the end (swin3D.py:401-417), so the outer frames of a layer that no later layer reads need not exist;
+ * the frames that are computed are bit-identical to the full convolution (x is still read one frame beyond the window). */
 int dlsg_conv3d_k3_tf32x3_f32(const float* x, const void* wprep, const float* bias, const float* resid, float resid_scale, float* out,
-                              int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream);
+                              int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, int t_lo, int t_n, void* stream);
 
 /* PatchEmbed3D.proj (dl_cs/models/video_swin_transformer_mri_downsample.py:455-476): nn.Conv3d(kernel = stride = patch, no padding) on
  * the same kernel.  x [NB,T,Y,X,Cin] (T, Y, X multiples of patch) -> out [NB,T/patch,Y/patch,X/patch,Cout]; wprep as above (first form) with
@@ -317,8 +320,9 @@ int dlsg_conv3d_unpatch_tf32x3_f32(const float* x, const void* wprep, const floa
  *                                                                         its "Cout" is the padded 27*Cout, wprep the image of that [ZC, Cin] matrix)
  *   out[v, co] = bias[co] + sum over the taps inside the volume of z[v + tap, tap*Cout + co]      dlsg_conv3d_tapsum_f32 (ZC = channel stride of z) */
 int dlsg_conv3d_pointwise_tf32x3_f32(const float* x, const void* wprep, const float* bias, float* out,
-                                     int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, void* stream);
-int dlsg_conv3d_tapsum_f32(const float* z, const float* bias, float* out, int NB, int T, int Y, int X, int ZC, int Cout, void* stream);
+                                     int NB, int T, int Y, int X, int Cin, int Cout, int relu_in, int t_lo, int t_n, void* stream);
+int dlsg_conv3d_tapsum_f32(const float* z, const float* bias, float* out, int NB, int T, int Y, int X, int ZC, int Cout,
+                           int t_lo, int t_n, void* stream);
 
 /* The same layer as ONE direct kernel: 3 x 3 x 3 'same' convolution down to Cout = 2 or 4 channels in
  * exact fp32 on the CUDA cores (packed FMAs).  x, out channels-last as above; w_tcc[tap][ci][co] = weight[co,ci,tap].  Cin % 32 == 0. */

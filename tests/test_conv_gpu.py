@@ -79,6 +79,31 @@ def test_last_layer_kernel_matches_fp64(case):
     assert rel(conv3d_k3_fewout_gemm(inp, w, None, relu_in=True), ref_r) < 3e-5
 
 
+@pytest.mark.parametrize("case", [(2, 96, 160, 7, 9, 12, 2, 6), (3, 64, 64, 8, 10, 16, 1, 7), (2, 4, 32, 6, 5, 9, 0, 4), (1, 64, 64, 5, 6, 7, 3, 5)])
+def test_frame_window_computes_exactly_the_requested_frames(case):
+    """t_range: the kernels write only the requested output frames of every sample, bit-identical to the full convolution there
+    (the denoisers use it to skip the outer frames of the circular time padding that no later layer reads)."""
+    from dl_swin_gan_b200.models.conv3d import conv3d_k3, conv3d_k3_fewout_gemm
+    nb, cin, cout, t, y, x, lo, hi = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(cin + 7 * cout + lo)
+    inp = torch.randn(nb, cin, t, y, x, generator=g, device=dev)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g, device=dev) / (27 * cin) ** 0.5
+    b = torch.randn(cout, generator=g, device=dev)
+    res = torch.randn(nb, cout, t, y, x, generator=g, device=dev)
+    full = conv3d_k3(inp, w, b, relu_in=True, residual=res)
+    part = conv3d_k3(inp, w, b, relu_in=True, residual=res, t_range=(lo, hi))
+    assert torch.equal(part[:, :, lo:hi], full[:, :, lo:hi])
+    # a window reaching beyond the volume is clipped
+    part = conv3d_k3(inp, w, b, t_range=(lo - 5, t + 3))
+    assert torch.equal(part, conv3d_k3(inp, w, b))
+    if cin % 32 == 0:
+        w4 = torch.randn(4, cin, 3, 3, 3, generator=g, device=dev) / (27 * cin) ** 0.5
+        full4 = conv3d_k3_fewout_gemm(inp, w4, b[:4])
+        part4 = conv3d_k3_fewout_gemm(inp, w4, b[:4], t_range=(lo, hi))
+        assert torch.equal(part4[:, :, lo:hi], full4[:, :, lo:hi])
+
+
 def test_conv_forward_routes_to_the_kernel_and_matches_cudnn_path():
     from dl_swin_gan_b200 import _lib
     from dl_swin_gan_b200.models import layers
