@@ -59,6 +59,7 @@ struct ConvParams {
     int relu_in;           // rectify the input on the fly (ConvBlock's pre-activation)
     const float* resid;    // optional [NB, To, Yo, Xo, Cout]: out = conv + bias + resid_scale * resid (the blocks' skip connections)
     float resid_scale;
+    int resid_relu;        // the skip connection is relu(resid): ResBlock's in-place pre-activation rectifies the tensor the skip re-reads (resnet3d.py:240)
 };
 
 __host__ __device__ inline size_t conv_stage_bytes(int Cout) { return (size_t)4 * kConvABytes + (size_t)2 * Cout * kConvKC * 2; }
@@ -306,7 +307,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3d_k3_tf32x3_kernel(ConvP
                 if (live && rrow) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + c0 + 4 * q));
+                        float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + c0 + 4 * q));
+                        if (p.resid_relu) { r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f); r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f); }
                         acc[4 * q] = fmaf(p.resid_scale, r4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(p.resid_scale, r4.y, acc[4 * q + 1]);
                         acc[4 * q + 2] = fmaf(p.resid_scale, r4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(p.resid_scale, r4.w, acc[4 * q + 3]);
                     }
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
                         for (int j = 0; j < 32; ++j)
                             rs[j] = (vb + j < p.NV) ? __ldg(p.resid + (size_t)(vb + j + (vb + j < edge ? sh0 : sh1)) * Cout + cbase + lane) : 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] = fmaf(p.resid_scale, rs[j], acc[j]);
+                        for (int j = 0; j < 32; ++j) acc[j] = fmaf(p.resid_scale, p.resid_relu ? fmaxf(rs[j], 0.f) : rs[j], acc[j]);
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {

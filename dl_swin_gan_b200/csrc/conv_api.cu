@@ -68,7 +68,7 @@ int dlsg_conv3d_k3_tf32x3_f32(const float* x, const void* wprep, const float* bi
     p.NV = (long long)NB * t_n * Y * X;
     p.relu_in = relu_in ? 1 : 0;
     if (resid && (reinterpret_cast<uintptr_t>(resid) & 15)) return DLSG_EINVAL;
-    p.resid = resid; p.resid_scale = resid_scale;
+    p.resid = resid; p.resid_scale = resid_scale < 0.f ? -resid_scale : resid_scale; p.resid_relu = resid_scale < 0.f ? 1 : 0;
     if (conv_c64(Cin, Cout)) {
         using namespace dlsg;
         if (!p.x || !p.wprep || !p.out || NB <= 0 || T <= 0 || Y <= 0 || X <= 0) return DLSG_EINVAL;

@@ -143,10 +143,14 @@ def _window(t_range, t):
 
 
 def conv3d_k3(x: torch.Tensor, weight: torch.Tensor, bias=None, relu_in: bool = False, residual=None, residual_scale: float = 1.0,
-              t_range=None) -> torch.Tensor:
+              t_range=None, residual_relu: bool = False) -> torch.Tensor:
     """x [NB, Cin, T, Y, X] (any layout; used channels-last) -> conv(relu?(x)) + bias (+ residual_scale * residual),
     [NB, Cout, T, Y, X] in channels_last_3d.  `t_range = (lo, hi)`: only the output frames lo .. hi - 1 are computed (the others are left
     uninitialised) - for callers that know the outer frames are never read (the denoisers' circular time padding)."""
+    if residual_relu:
+        if residual_scale <= 0:
+            raise ValueError("residual_relu needs a positive residual_scale")
+        residual_scale = -residual_scale            # the C ABI's encoding of |scale| * relu(residual)
     return _run("dlsg_conv3d_k3_tf32x3_f32", x, weight, bias, x.shape[2:], relu_in, False, residual, residual_scale, t_range)
 
 
@@ -230,11 +234,13 @@ def conv3d_k3_fewout_gemm(x: torch.Tensor, weight: torch.Tensor, bias=None, relu
 
 
 def forward(conv: torch.nn.Module, x: torch.Tensor, which: str, relu_in: bool = False, residual=None, residual_scale: float = 1.0,
-            t_range=None) -> torch.Tensor:
+            t_range=None, residual_relu: bool = False) -> torch.Tensor:
     """`conv(relu?(x)) (+ residual_scale * residual)` on the kernel `kind()` chose; what a kernel cannot fuse is done around it.
     `t_range`: output frames the caller will read (a hint: kernels without a frame window compute everything)."""
     if which == K3:
-        return conv3d_k3(x, conv.weight, conv.bias, relu_in, residual, residual_scale, t_range)
+        return conv3d_k3(x, conv.weight, conv.bias, relu_in, residual, residual_scale, t_range, residual_relu)
+    if residual is not None and residual_relu:
+        residual = torch.relu(residual)
     if which == FEWOUT:
         gemm = _FEWOUT_GEMM and bool(_lib.load().dlsg_conv3d_k3_supported(conv.in_channels, -(-27 * conv.out_channels // 32) * 32))
         if gemm:

@@ -166,7 +166,7 @@ class ConvBlock(nn.Module):
         conv = (ComplexConv3d if is_complex else Conv3d)(in_chans, out_chans, kernel_size=kernel_size)
         self.layers = nn.Sequential(Normalization(in_chans, norm_type), Activation(act_type), conv)
 
-    def forward(self, input, residual=None, residual_scale=1.0, input_is_temp=False, t_range=None):
+    def forward(self, input, residual=None, residual_scale=1.0, input_is_temp=False, t_range=None, residual_relu=False):
         """`conv(act(input))` (+ residual_scale * residual).  The extra arguments only let the B200 kernels fuse what surrounds the
         convolution; the arithmetic is the reference's.  `input_is_temp`: nobody reads `input` after this call, so the in-place
         ReLU of the reference (which would rectify `input` itself) may be applied inside the kernel's operand load instead.
@@ -180,13 +180,16 @@ class ConvBlock(nn.Module):
         if fused is None:
             out = self.layers(input)
             if residual is not None:
+                if residual_relu:
+                    residual = torch.relu(residual)
                 out = out + (residual if residual_scale == 1.0 else residual_scale * residual)
             return out
         relu = isinstance(act.activ, nn.ReLU)
         if relu and not input_is_temp:
             input = act(input)                      # in place, visible to the caller, exactly as in the reference
             relu = False
-        return conv3d.forward(conv_mod.conv, input, fused, relu_in=relu, residual=residual, residual_scale=residual_scale, t_range=t_range)
+        return conv3d.forward(conv_mod.conv, input, fused, relu_in=relu, residual=residual, residual_scale=residual_scale, t_range=t_range,
+                              residual_relu=residual_relu)
 
     def __repr__(self):
         return f"{self.name}(in_chans={self.in_chans}, out_chans={self.out_chans})"
@@ -200,10 +203,12 @@ class ResBlock(nn.Module):
         self.layers = nn.Sequential(ConvBlock(chans, chans, kernel_size, act_type=act_type, is_complex=is_complex),
                                     ConvBlock(chans, chans, kernel_size, act_type=act_type, is_complex=is_complex))
 
-    def forward(self, input, t_range=None):
-        # the first block rectifies `input` in place (reference quirk, see Activation), so the skip below adds relu(input)
-        h = self.layers[0](input, t_range=grow_frames(t_range, 1))
-        return self.layers[1](h, residual=input, input_is_temp=True, t_range=t_range)
+    def forward(self, input, t_range=None, input_is_temp=False):
+        # the first block rectifies `input` in place (reference quirk, see Activation), so the skip below adds relu(input).
+        # `input_is_temp` (nobody else reads `input` afterwards): the ReLU is folded into both reads instead and `input` is not rewritten
+        relu_skip = input_is_temp and isinstance(self.layers[0].layers[1].activ, nn.ReLU)
+        h = self.layers[0](input, t_range=grow_frames(t_range, 1), input_is_temp=input_is_temp)
+        return self.layers[1](h, residual=input, input_is_temp=True, t_range=t_range, residual_relu=relu_skip)
 
 
 def grow_frames(t_range, k):

@@ -43,6 +43,6 @@ class ResNet(nn.Module):
         n = len(self.res_blocks)
         output = self.init_layer(input, t_range=grow_frames(keep, 2 * n + 1))
         for i, res_block in enumerate(self.res_blocks):
-            output = res_block(output, t_range=grow_frames(keep, 2 * (n - 1 - i) + 1))
+            output = res_block(output, t_range=grow_frames(keep, 2 * (n - 1 - i) + 1), input_is_temp=True)
         output = self.final_layer(output, residual=input, input_is_temp=n > 0, t_range=keep)
         return self._postprocess(output)

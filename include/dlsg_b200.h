@@ -295,7 +295,9 @@ int dlsg_conv3d_k3_supported(int Cin, int Cout);
  *   Cin = 2 or 4 (first layer of a denoiser), K index k = tap*Cin + ci zero-padded to a multiple of 32:
  *                             wprep[k/32][h][(k%32)/8][co/8][co%8][k%8]
  * relu_in != 0 rectifies x on the fly (ConvBlock's pre-activation, :262-268).  resid (NULL or [NB,T,Y,X,Cout]) is a skip connection added
- * in the epilogue: out = conv + bias + resid_scale * resid (ResBlock :300, ResSwinTransformer3DBlock :340, DeepFeatureExtraction :369).
+ * in the epilogue: out = conv + bias + resid_scale * resid (ResBlock :300, ResSwinTransformer3DBlock :340, DeepFeatureExtraction :369);
+ * a NEGATIVE resid_scale means |resid_scale| * relu(resid): ResBlock's first ConvBlock rectifies, in place, the very tensor its skip
+ * connection re-reads (resnet3d.py:240) - with the ReLU folded into both reads that tensor is never rewritten.
  * bias may be NULL.  NB*T*Y*X*Cin < 2^31.
  * t_lo, t_n: only the output frames t_lo .. t_lo + t_n - 1 of every sample are computed and written (t_n = 0: all T).  The denoisers pad the
  * time axis circularly and crop it at the end (swin3D.py:401-417), so the outer frames of a layer that no later layer reads need not exist;

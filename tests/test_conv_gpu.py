@@ -39,6 +39,10 @@ def test_conv3d_k3_matches_fp64(case):
     out_r = conv3d_k3(inp, w, b, relu_in=True, residual=res, residual_scale=2.0)
     ref_r = torch.nn.functional.conv3d(inp.double().relu(), w.double(), b.double() if has_bias else None, padding=1) + 2.0 * res.double()
     assert rel(out_r, ref_r) < 3e-5
+    # skip connection through a ReLU (ResBlock's in-place pre-activation on the tensor its skip re-reads)
+    out_rr = conv3d_k3(inp, w, b, relu_in=True, residual=res, residual_scale=1.0, residual_relu=True)
+    ref_rr = torch.nn.functional.conv3d(inp.double().relu(), w.double(), b.double() if has_bias else None, padding=1) + res.double().relu()
+    assert rel(out_rr, ref_rr) < 3e-5
 
 
 @pytest.mark.parametrize("case", [(1, 32, 64, 2, 3, 5, 2), (2, 160, 160, 2, 6, 5, 4), (1, 64, 32, 3, 9, 7, 1)])
