@@ -386,7 +386,7 @@ constexpr int kC64LboB = 32 * 128 + 32;                 // bytes between the 8-c
 constexpr int kC64BBytes = (kConvKC / 8) * kC64LboB;    // one of X_hi / X_lo (bf16) for a stage
 constexpr int kC64WBytes = 128 * kConvKC * 2;           // [W_hi; W_lo] (bf16) for a stage
 constexpr int kC64Stage = 2 * kC64BBytes + kC64WBytes;
-inline size_t conv_c64_smem_bytes() { return (size_t)kConvStages * kC64Stage + 64 * 4 + 128; }
+inline size_t conv_c64_smem_bytes() { return (size_t)kConvStages * kC64Stage + 64 * 4 + 128 + 28 * 4 + 27 * kC64Producers; }
 
 template <bool RELU>
 __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParams p) {
@@ -396,6 +396,8 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
     float* sBias = reinterpret_cast<float*>(conv_smem + kConvStages * kC64Stage);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sBias + Cout);   // full[S], empty[S], accfull, accempty
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * kConvStages + 2);
+    int* sTapOff = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(bars) + 128);      // voxel offset of each of the 27 taps
+    unsigned char* sOk = reinterpret_cast<unsigned char*>(sTapOff + 28);                      // [27][producer thread]: in-volume flags of its 4 rows
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned s0 = smem_u32(conv_smem), bar0 = smem_u32(bars);
     const unsigned bempty = bar0 + 8u * kConvStages, baccfull = bar0 + 16u * kConvStages, baccempty = baccfull + 8u;
@@ -414,6 +416,7 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     for (int i = tid; i < Cout; i += kC64Threads) sBias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+    if (tid < 27) sTapOff[tid] = ((tid / 9 - 1) * p.Y + ((tid / 3) % 3 - 1)) * p.X + (tid % 3 - 1);
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -444,17 +447,23 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3d_k3_c64_kernel(ConvParam
             unsigned roff[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) roff[i] = (unsigned)vact[i] * (unsigned)p.Cin + 4u * k4;
-            auto tap_state = [&](int tap) {
+            // the in-volume flags of all 27 taps are worked out once per tile (they cost more than the split of a whole stage) and kept in
+            // this thread's own shared-memory bytes
+            for (int tap = 0; tap < 27; ++tap) {
                 const int dt = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
-                okmask = 0;
+                unsigned m = 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int c = coord[i];
                     const bool ok = c >= 0 && (unsigned)((c >> 20) + dt) < (unsigned)p.T && (unsigned)(((c >> 10) & 1023) + dy) < (unsigned)p.Y &&
                                     (unsigned)((c & 1023) + dx) < (unsigned)p.X;
-                    okmask |= (ok ? 1u : 0u) << i;
+                    m |= (ok ? 1u : 0u) << i;
                 }
-                foff = (unsigned)((dt * p.Y + dy) * p.X + dx) * (unsigned)p.Cin;
+                sOk[tap * kC64Producers + tid] = (unsigned char)m;
+            }
+            auto tap_state = [&](int tap) {
+                okmask = sOk[tap * kC64Producers + tid];
+                foff = (unsigned)sTapOff[tap] * (unsigned)p.Cin;
             };
             int ftap = 0, fch = 0;
             auto fetch = [&](float4* dst) {
