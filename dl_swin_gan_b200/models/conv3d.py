@@ -78,6 +78,10 @@ def kind(conv: torch.nn.Module, x: torch.Tensor):
         return None
     if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
         return None
+    # the kernels' limits (32-bit element offsets, packed voxel coordinates): larger volumes take the library path
+    nb, _, t, y, xx = x.shape
+    if t > 2046 or y > 1022 or xx > 1022 or x.numel() >= 2 ** 31 or nb * t * y * xx * max(conv.out_channels, 27 * 4 + 20) >= 2 ** 31:
+        return None
     lib = _lib.load()
     k, s, pd = tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding)
     cubic = k[0] == k[1] == k[2]

@@ -108,6 +108,15 @@ def test_frame_window_computes_exactly_the_requested_frames(case):
         assert torch.equal(part4[:, :, lo:hi], full4[:, :, lo:hi])
 
 
+def test_volumes_beyond_the_kernels_limits_take_the_library_path():
+    from dl_swin_gan_b200.models import conv3d
+    conv = torch.nn.Conv3d(64, 64, 3, padding=1)
+    big = torch.empty(0, device="cuda:0").new_empty((1, 64, 1, 8, 8)).expand(64, 64, 2048, 8, 8)      # a view: shape only, no memory
+    with torch.no_grad():
+        assert conv3d.kind(conv.cuda(), big) is None
+        assert conv3d.kind(conv.cuda(), torch.zeros(1, 64, 4, 8, 8, device="cuda:0")) == conv3d.K3
+
+
 def test_conv_forward_routes_to_the_kernel_and_matches_cudnn_path():
     from dl_swin_gan_b200 import _lib
     from dl_swin_gan_b200.models import layers
