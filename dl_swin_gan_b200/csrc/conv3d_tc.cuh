@@ -65,9 +65,6 @@ struct ConvParams {
 __host__ __device__ inline size_t conv_stage_bytes(int Cout) { return (size_t)4 * kConvABytes + (size_t)2 * Cout * kConvKC * 2; }
 inline size_t conv_smem_bytes(int Cout) { return kConvStages * conv_stage_bytes(Cout) + (size_t)Cout * 4 + 128; }
 
-__device__ __forceinline__ unsigned umma_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
-}
 // kind::f16 with bf16 operands (format 1), fp32 accumulation
 __device__ __forceinline__ unsigned umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
@@ -85,12 +82,6 @@ __device__ __forceinline__ void bf16_split4(float4 v, uint2& hi, uint2& lo) {
     hi = make_uint2(h01, h23);
     lo = make_uint2(l01, l23);
 }
-__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
-                                          unsigned idesc, unsigned accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 // bounded wait: a broken pipeline traps instead of hanging the GPU
 __device__ __forceinline__ void conv_mbar_wait(unsigned bar, unsigned parity) {
     unsigned done = 0;
@@ -103,10 +94,6 @@ __device__ __forceinline__ void conv_mbar_wait(unsigned bar, unsigned parity) {
 __device__ __forceinline__ void conv_bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
-    hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
-    lo = v - hi;
 }
 
 // CS = 0: Cin % 32 == 0, the K loop walks (tap, 32-channel chunk).  CS = 2 / 4: the first layer of a denoiser (Cin = 2 or 4 = re / im of the
