@@ -53,3 +53,18 @@ def test_transposed_and_patch_weights_use_their_own_tap_count():
     hi, _ = pieces(wt.transpose(0, 1).contiguous())
     tap, ci, co = 37, 5, 60
     assert img[tap, 0, 0, ci // 8, co // 8, co % 8, ci % 8] == hi.reshape(64, 32, 64)[co, ci, tap]
+
+
+def test_frame_windows_chain_through_the_denoisers_layers():
+    """The window a layer must produce grows by one frame per 3-tap consumer and is clipped to the volume by the kernel wrapper."""
+    from dl_swin_gan_b200.models.conv3d import _window
+    from dl_swin_gan_b200.models.layers import grow_frames
+    import pytest
+    assert grow_frames(None, 3) is None
+    keep = (6, 26)                                   # ResNet, 2 residual blocks: 32 padded frames, the crop keeps 6 .. 25
+    chain = [grow_frames(keep, k) for k in (5, 3, 1, 0)]     # init layer, block 1, block 2, last layer
+    assert chain == [(1, 31), (3, 29), (5, 27), (6, 26)]
+    assert _window(None, 32) == (0, 32) and _window((1, 31), 32) == (1, 31)
+    assert _window((-2, 40), 32) == (0, 32)          # beyond the volume: clipped, never an error
+    with pytest.raises(ValueError):
+        _window((10, 10), 32)
